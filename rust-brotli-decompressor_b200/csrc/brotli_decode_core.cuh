@@ -1,0 +1,1123 @@
+// brotli_decode_core.cuh -- warp-per-stream Brotli decoder for sm_100a (B200).
+//
+// One warp decodes one stream.  The serial part of the format (bit window -> prefix-code
+// symbol -> command) is executed warp-uniformly: every lane holds the same decoder state in
+// registers, table lookups are same-address (broadcast) loads, so no shuffles are needed to
+// distribute (insert_len, copy_len, distance).  The data-parallel part -- LZ77 backreference
+// copies, literal/uncompressed runs, dictionary words, table replication -- is lane-strided.
+// The output buffer IS the sliding window (no ring buffer, no second copy of every byte);
+// the reference's ring-buffer flush points are emulated arithmetically because they decide
+// `decoded_size` on errors.
+//
+// Reference path restated here (file:line under /root/reference):
+//   bit window        src/bit_reader/mod.rs:135-338        -> struct BitReader
+//   symbol decode     src/decode.rs:377-398                -> decode_symbol
+//   prefix codes      src/decode.rs:516-1013, src/huffman/mod.rs:196-471 -> read_huffman_code
+//   context maps      src/decode.rs:1096-1128,1272-1428    -> decode_context_map
+//   block switching   src/decode.rs:1469-1658              -> switch_*_block
+//   command loop      src/decode.rs:2330-2744              -> process_commands<SAFE>
+//   distance          src/decode.rs:2017-2131              -> read_distance
+//   dictionary        src/decode.rs:2593-2640, src/transform.rs:720-795 -> emit_dictionary_word
+//   stream driver     src/decode.rs:2779-3403, :152-372    -> decode_stream
+//
+// The same source also compiles for the host with warp width 1 (BROTLI_B200_HOSTSIM); that
+// build exists only so tests/ can exercise this logic in the GPU-less dev container.  It is
+// never part of the product library.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(BROTLI_B200_HOSTSIM)
+#include <string.h>
+#define BD_DEV inline
+#define BD_CONST_TABLE static const
+struct uint2 { uint32_t x, y; };
+namespace brotli_b200 {
+namespace hw {
+constexpr uint32_t kWarp = 1;
+static inline uint32_t lane() { return 0; }
+static inline void syncwarp() {}
+static inline bool all(bool p) { return p; }
+static inline uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
+  s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+static inline uint32_t brev(uint32_t v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+}
+static inline uint32_t ldg32(const uint32_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint8_t ldg8(const uint8_t* p) { return *p; }
+}  // namespace hw
+}  // namespace brotli_b200
+#else
+#define BD_DEV __device__ __forceinline__
+#define BD_CONST_TABLE __device__ const
+namespace brotli_b200 {
+namespace hw {
+constexpr uint32_t kWarp = 32;
+BD_DEV uint32_t lane() { return threadIdx.x & 31u; }
+BD_DEV void syncwarp() { __syncwarp(); }
+BD_DEV bool all(bool p) { return __all_sync(0xffffffffu, p); }
+BD_DEV uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+BD_DEV uint32_t brev(uint32_t v) { return __brev(v); }
+BD_DEV uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
+BD_DEV uint8_t ldg8(const uint8_t* p) { return __ldg(p); }
+}  // namespace hw
+}  // namespace brotli_b200
+#endif
+
+namespace brotli_b200 {
+
+// ---- RFC 7932 constant tables (generated; see tables/gen_tables.py) ----
+namespace tbl {
+#define BROTLI_TABLE_ATTR BD_CONST_TABLE
+#include "../../tables/brotli_tables.h"
+#undef BROTLI_TABLE_ATTR
+// src/decode.rs:55-61
+BD_CONST_TABLE uint8_t kCodeLengthCodeOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+BD_CONST_TABLE uint8_t kCodeLengthPrefixLength[16] = {2, 2, 2, 3, 2, 2, 2, 4, 2, 2, 2, 3, 2, 2, 2, 4};
+BD_CONST_TABLE uint8_t kCodeLengthPrefixValue[16] = {0, 4, 3, 2, 0, 4, 3, 1, 0, 4, 3, 2, 0, 4, 3, 5};
+}  // namespace tbl
+
+// BrotliDecoderErrorCode, src/state.rs:22-65 (c/brotli/decode.h:69-111)
+enum Status : int32_t {
+  kSuccess = 1, kNeedsMoreInput = 2, kNeedsMoreOutput = 3,
+  kErrExuberantNibble = -1, kErrReserved = -2, kErrExuberantMetaNibble = -3, kErrSimpleHuffmanAlphabet = -4,
+  kErrSimpleHuffmanSame = -5, kErrClSpace = -6, kErrHuffmanSpace = -7, kErrContextMapRepeat = -8,
+  kErrBlockLength1 = -9, kErrBlockLength2 = -10, kErrTransform = -11, kErrDictionary = -12, kErrWindowBits = -13,
+  kErrPadding1 = -14, kErrPadding2 = -15, kErrDistance = -16, kErrInvalidArguments = -20, kErrUnreachable = -31,
+  // internal (never leaves process_commands)
+  kNeedSafe = 100, kRetryFast = 101, kMetablockDone = 102
+};
+
+// ---- per-warp scratch arena in global memory (L1/L2 resident while a stream decodes) ----
+// Table entries are u16: leaf = symbol << 4 | code_len; root pointer = sub_offset << 4 | (8 + sub_bits).
+constexpr uint32_t kRootBits = 8;
+constexpr uint32_t kMaxLitTable = 630;    // alphabet 256, src/huffman/mod.rs:15-25
+constexpr uint32_t kMaxCmdTable = 1080;   // alphabet 704
+constexpr uint32_t kMaxDistTable = 920;   // alphabet <= 544 (large window max symbol)
+constexpr uint32_t kMaxBlockTypeTable = 632;  // alphabet <= 258
+constexpr uint32_t kMaxBlockLenTable = 396;   // alphabet 26
+constexpr uint32_t kMaxCtxMapTable = 646;     // alphabet <= 272
+constexpr uint32_t kMaxAlphabet = 1152;
+
+struct ArenaLayout {
+  static constexpr size_t kCtxMapLit = 0;                               // u8[16384]
+  static constexpr size_t kCtxMapDist = kCtxMapLit + 16384;             // u8[1024]
+  static constexpr size_t kCtxModes = kCtxMapDist + 1024;               // u8[256]
+  static constexpr size_t kMtf = kCtxModes + 256;                       // u8[256]
+  static constexpr size_t kCodeLen = kMtf + 256;                        // u8[kMaxAlphabet]
+  static constexpr size_t kSorted = kCodeLen + kMaxAlphabet;            // u16[kMaxAlphabet]
+  static constexpr size_t kTreeOffLit = kSorted + 2 * kMaxAlphabet;     // u32[256]
+  static constexpr size_t kTreeOffCmd = kTreeOffLit + 1024;             // u32[256]
+  static constexpr size_t kTreeOffDist = kTreeOffCmd + 1024;            // u32[256]
+  static constexpr size_t kBlockTypeTrees = kTreeOffDist + 1024;        // u16[3][632]
+  static constexpr size_t kBlockLenTrees = kBlockTypeTrees + 2 * 3 * kMaxBlockTypeTable;  // u16[3][396]
+  static constexpr size_t kCtxMapTree = kBlockLenTrees + 2 * 3 * kMaxBlockLenTable;       // u16[646]
+  static constexpr size_t kTables = (kCtxMapTree + 2 * kMaxCtxMapTable + 63) & ~size_t(63);
+  static constexpr size_t kTableEntries = 256 * (size_t)(kMaxLitTable + kMaxCmdTable + kMaxDistTable);
+  static constexpr size_t kBytes = (kTables + 2 * kTableEntries + 255) & ~size_t(255);
+};
+
+// Small per-warp scratch that wants dynamic indexing; lives in shared memory on the GPU.
+struct WarpScratch {
+  uint16_t cl_tab[32];    // code-length code lookup: value << 8 | bits
+  uint16_t count[16];     // histogram of code lengths
+  uint16_t offs[16];
+  uint8_t cl_cl[18];      // code length code lengths
+  uint8_t pad[2];
+  uint8_t word[72];       // dictionary word staging (<= 5 + 24 + 8 bytes, + uppercase overrun)
+};
+
+// Read-only lookup data shared by all warps of a CTA (shared memory on the GPU).
+struct SharedLuts {
+  const uint2* cmd_lut;     // [704] .x = insert_base | insert_extra<<16 | ctx<<24 | implicit<<26 ; .y = copy_base | copy_extra<<16
+  const uint8_t* ctx_lut;   // [2048]
+  const uint8_t* dictionary;
+};
+
+BD_DEV uint2 pack_cmd_lut(uint32_t code) {
+  const tbl::BrotliCmdLutElement& e = tbl::kBrotliCmdLut[code];
+  uint2 r;
+  r.x = (uint32_t)e.insert_len_offset | ((uint32_t)e.insert_len_extra_bits << 16) | ((uint32_t)e.context << 24) |
+        ((e.distance_code == 0 ? 1u : 0u) << 26);
+  r.y = (uint32_t)e.copy_len_offset | ((uint32_t)e.copy_len_extra_bits << 16);
+  return r;
+}
+
+// ======================= bit reader =======================
+// 96 bits of look-ahead (lo, hi, nx) over 32-bit aligned words of the input; bp = bits of `lo`
+// already consumed.  peek() always yields 32 valid bits.  Bits past the end of the stream read
+// as zero and the position keeps counting, so truncation is detected by position, not by
+// special-casing every read (same observable behaviour as the reference's byte-wise "safe"
+// reader, src/bit_reader/mod.rs:228-242,362-374).
+struct BitReader {
+  const uint32_t* w;
+  const uint8_t* bytes;
+  uint32_t lo, hi, nx;
+  uint32_t k;           // word index of `lo`
+  uint32_t bp;          // 0..31
+  uint32_t first_full;  // words [first_full, end_full) lie wholly inside the stream
+  uint32_t end_full;
+  uint32_t lead;        // bytes between the aligned base and the first stream byte (0..3)
+  uint64_t end_byte;    // lead + stream size
+
+  BD_DEV uint32_t load_checked(uint32_t j) const {
+    if (j >= first_full && j < end_full) return hw::ldg32(w + j);
+    uint32_t v = 0;
+    uint64_t b0 = (uint64_t)j * 4;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      uint64_t bi = b0 + b;
+      if (bi >= lead && bi < end_byte) v |= (uint32_t)hw::ldg8(bytes + bi) << (8 * b);
+    }
+    return v;
+  }
+  BD_DEV void seek_byte(uint64_t byte_off) {
+    uint64_t a = lead + byte_off;
+    k = (uint32_t)(a >> 2);
+    bp = (uint32_t)(a & 3) * 8;
+    lo = load_checked(k); hi = load_checked(k + 1); nx = load_checked(k + 2);
+  }
+  BD_DEV void init(const uint8_t* p, uint64_t size) {
+    uintptr_t a = (uintptr_t)p;
+    lead = (uint32_t)(a & 3);
+    bytes = p - lead;
+    w = (const uint32_t*)bytes;
+    end_byte = lead + size;
+    first_full = lead ? 1u : 0u;
+    end_full = (uint32_t)(end_byte >> 2);
+    if (end_full < first_full) end_full = first_full;
+    seek_byte(0);
+  }
+  BD_DEV uint32_t peek() const { return hw::funnelshift_r(lo, hi, bp); }
+  template <bool FAST>
+  BD_DEV void skip(uint32_t n) {  // n <= 32
+    bp += n;
+    if (bp >= 32) {
+      lo = hi; hi = nx; k++;
+      nx = FAST ? hw::ldg32(w + k + 2) : load_checked(k + 2);
+      bp -= 32;
+    }
+  }
+  template <bool FAST>
+  BD_DEV uint32_t read(uint32_t n) {  // n <= 31
+    uint32_t v = peek() & ((1u << n) - 1u);
+    skip<FAST>(n);
+    return v;
+  }
+  BD_DEV uint64_t bitpos() const { return ((uint64_t)k << 5) + bp; }
+  BD_DEV bool overrun() const { return bitpos() > end_byte * 8; }
+  BD_DEV uint64_t byte_pos() const { return (bitpos() >> 3) - lead; }  // valid when byte aligned
+  BD_DEV uint64_t size() const { return end_byte - lead; }
+  // src/bit_reader/mod.rs:378-385; false if the padding bits are not zero
+  BD_DEV bool jump_to_byte_boundary() {
+    uint32_t pad = (8u - (bp & 7u)) & 7u;
+    return pad == 0 || read<false>(pad) == 0;
+  }
+  // true while the unchecked fast path may run: >= `words` whole words remain beyond `nx`
+  BD_DEV bool fast_ok(uint32_t words) const { return k + 3 + words <= end_full; }
+};
+
+// ======================= prefix-code symbol decode (src/decode.rs:377-398) =======================
+BD_DEV uint32_t decode_symbol(const uint16_t* tab, uint32_t bits, uint32_t& len) {
+  uint32_t e = tab[bits & 0xFFu];
+  uint32_t l = e & 15u;
+  if (l > kRootBits) {
+    uint32_t wbits = l - kRootBits;
+    e = tab[(e >> 4) + ((bits >> kRootBits) & ((1u << wbits) - 1u))];
+    l = kRootBits + (e & 15u);
+  }
+  len = l;
+  return e >> 4;
+}
+
+// ======================= decoder state (warp-uniform) =======================
+enum CmdState : uint32_t { kCmdBegin = 0, kCmdInner = 1, kCmdPostLiterals = 2 };
+
+struct Decoder {
+  BitReader br;
+  uint8_t* out;
+  uint32_t cap;           // output capacity (clamped to < 2^32 - 64)
+  uint32_t pos;           // bytes produced so far
+  int32_t mlen;           // meta_block_remaining_len
+  uint32_t wbits;
+  uint32_t max_backward;  // (1 << wbits) - 16
+  uint32_t large_window;  // stream carries the large-window marker (src/decode.rs:152-187)
+  // ring-buffer flush emulation (src/decode.rs:1693-1738,1808-1871)
+  uint32_t rb_allocated;
+  uint64_t rbsize;
+  uint64_t next_flush;    // absolute position of the next flush event
+  uint64_t flushed;       // bytes the reference would have handed to the caller before a fatal error
+  uint64_t discarded;     // literals decoded past the capacity while a command overshoots MLEN (SAFE only)
+  uint32_t full_ring;
+  // last four distances, d0 most recent (src/state.rs:295-296)
+  int32_t d0, d1, d2, d3;
+  // block-split state per category: literal, command, distance (src/state.rs:146-154)
+  uint32_t nbt_l, nbt_c, nbt_d;
+  uint32_t bl_l, bl_c, bl_d;
+  uint32_t rbt_l0, rbt_l1, rbt_c0, rbt_c1, rbt_d0, rbt_d1;
+  uint32_t n_lit_trees, n_dist_trees;
+  uint32_t npostfix, ndirect;     // ndirect includes the 16 short codes
+  uint32_t dist_alphabet, dist_max_symbol;
+  // current trees
+  const uint16_t* cmd_tree;
+  const uint16_t* lit_tree;       // valid when trivial_ctx
+  uint32_t trivial_ctx;
+  uint32_t ctx_slice;             // literal block type << 6
+  uint32_t ctx_mode_off;          // mode * 512 into ctx_lut
+  uint32_t dist_slice;            // distance block type << 2
+  // command in flight (for the fast -> safe hand-over)
+  uint32_t state;
+  uint32_t ins_rem;               // literals still to emit
+  uint32_t copy_len;
+  uint32_t implicit_dist;         // 1: reuse last distance, no symbol
+  uint32_t dist_ctx;
+  // arena views
+  uint8_t* arena;
+  uint16_t* tables;
+  WarpScratch* ws;
+  SharedLuts luts;
+
+  BD_DEV uint8_t* ctx_map_lit() const { return arena + ArenaLayout::kCtxMapLit; }
+  BD_DEV uint8_t* ctx_map_dist() const { return arena + ArenaLayout::kCtxMapDist; }
+  BD_DEV uint8_t* ctx_modes() const { return arena + ArenaLayout::kCtxModes; }
+  BD_DEV uint32_t* tree_off_lit() const { return (uint32_t*)(arena + ArenaLayout::kTreeOffLit); }
+  BD_DEV uint32_t* tree_off_cmd() const { return (uint32_t*)(arena + ArenaLayout::kTreeOffCmd); }
+  BD_DEV uint32_t* tree_off_dist() const { return (uint32_t*)(arena + ArenaLayout::kTreeOffDist); }
+  BD_DEV uint16_t* block_type_tree(int cat) const { return (uint16_t*)(arena + ArenaLayout::kBlockTypeTrees) + cat * kMaxBlockTypeTable; }
+  BD_DEV uint16_t* block_len_tree(int cat) const { return (uint16_t*)(arena + ArenaLayout::kBlockLenTrees) + cat * kMaxBlockLenTable; }
+  BD_DEV uint16_t* ctx_map_tree() const { return (uint16_t*)(arena + ArenaLayout::kCtxMapTree); }
+};
+
+BD_DEV uint32_t bit_width(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++; } return r; }  // Log2Floor, src/decode.rs:502-509
+
+// ======================= prefix-code descriptions -> lookup tables =======================
+// Builds the 2-level table for code lengths clen[0..n) (count[] = histogram, complete code).
+// Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386): 8-bit root, 2nd-level
+// tables as wide as the longest code under their root prefix.  The serial walk over the sorted
+// symbols is warp-uniform; the replication of each entry is lane-strided.
+BD_DEV int build_table(Decoder& d, uint16_t* tab, uint32_t cap_entries, uint32_t n, uint32_t& table_size) {
+  const uint32_t lane = hw::lane();
+  const uint8_t* clen = d.arena + ArenaLayout::kCodeLen;
+  uint16_t* sorted = (uint16_t*)(d.arena + ArenaLayout::kSorted);
+  uint16_t* count = d.ws->count;
+  uint16_t* offs = d.ws->offs;
+  uint32_t max_len = 0, acc = 0;
+  for (uint32_t l = 1; l <= 15; l++) { offs[l] = (uint16_t)acc; acc += count[l]; if (count[l]) max_len = l; }
+  for (uint32_t s = 0; s < n; s++) {  // counting sort by (length, symbol)
+    uint32_t l = clen[s];
+    if (l) { sorted[offs[l]] = (uint16_t)s; offs[l]++; }
+  }
+  uint32_t code = 0, idx = 0;
+  const uint32_t root_len = max_len < kRootBits ? max_len : kRootBits;
+  for (uint32_t l = 1; l <= root_len; l++) {
+    const uint32_t reps = 256u >> l;
+    for (uint32_t j = count[l]; j != 0; j--) {
+      const uint32_t e = ((uint32_t)sorted[idx++] << 4) | l;
+      const uint32_t rev = hw::brev(code) >> (32 - l);
+      for (uint32_t r = lane; r < reps; r += hw::kWarp) tab[rev + (r << l)] = (uint16_t)e;
+      code++;
+    }
+    code <<= 1;
+  }
+  uint32_t next_free = 256;
+  if (max_len > kRootBits) {
+    uint32_t cur_prefix = 0xFFFFFFFFu, sub_off = 0, sub_bits = 0;
+    for (uint32_t l = kRootBits + 1; l <= max_len; l++) {
+      const uint32_t sl = l - kRootBits;
+      while (count[l] != 0) {
+        const uint32_t prefix = code >> sl;
+        if (prefix != cur_prefix) {
+          // NextTableBitSize, src/huffman/mod.rs:181-193
+          uint32_t len2 = l; int32_t left = 1 << (len2 - kRootBits);
+          while (len2 < 15) { left -= count[len2]; if (left <= 0) break; len2++; left <<= 1; }
+          sub_bits = len2 - kRootBits;
+          sub_off = next_free;
+          next_free += 1u << sub_bits;
+          if (next_free > cap_entries) return kErrUnreachable;
+          cur_prefix = prefix;
+          tab[hw::brev(prefix) >> 24] = (uint16_t)((sub_off << 4) | (kRootBits + sub_bits));
+        }
+        const uint32_t e = ((uint32_t)sorted[idx++] << 4) | sl;
+        const uint32_t rev = hw::brev(code & ((1u << sl) - 1u)) >> (32 - sl);
+        const uint32_t reps = 1u << (sub_bits - sl);
+        for (uint32_t r = lane; r < reps; r += hw::kWarp) tab[sub_off + rev + (r << sl)] = (uint16_t)e;
+        code++;
+        count[l]--;
+      }
+      code <<= 1;
+    }
+  }
+  table_size = next_free;
+  hw::syncwarp();
+  return kSuccess;
+}
+
+// ReadHuffmanCode, src/decode.rs:868-1013 (+ :516-556, :565-658, :661-853).  Truncation is
+// detected by the caller through br.overrun(); reads past the end see zero bits, every loop
+// below still terminates and stays inside its arrays.
+BD_DEV int read_huffman_code(Decoder& d, uint32_t alphabet_size, uint32_t max_symbol, uint16_t* tab, uint32_t cap_entries,
+                             uint32_t& table_size) {
+  BitReader& br = d.br;
+  const uint32_t lane = hw::lane();
+  alphabet_size &= 0x7ff;
+  const uint32_t hskip = br.read<false>(2);
+  if (hskip == 1) {  // simple code: 1..4 symbols
+    const uint32_t nsym = br.read<false>(2) + 1;
+    const uint32_t max_bits = bit_width(alphabet_size - 1);
+    uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+      if (i < nsym) {
+        v[i] = br.read<false>(max_bits);
+        if (v[i] >= max_symbol) return br.overrun() ? kNeedsMoreInput : kErrSimpleHuffmanAlphabet;
+      }
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 3; i++)
+#pragma unroll
+      for (uint32_t j = i + 1; j < 4; j++)
+        if (j < nsym && v[i] == v[j]) return br.overrun() ? kNeedsMoreInput : kErrSimpleHuffmanSame;
+    uint32_t tree_select = 0;
+    if (nsym == 4) tree_select = br.read<false>(1);
+    // BrotliBuildSimpleHuffmanTable, src/huffman/mod.rs:390-471 (pattern of period <= 8, replicated)
+    uint32_t p[8];
+    uint32_t period;
+#define BD_SWAP(a, b) { uint32_t t_ = a; a = b; b = t_; }
+    if (nsym == 1) {
+      period = 1; p[0] = v[0] << 4;
+    } else if (nsym == 2) {
+      if (v[1] < v[0]) BD_SWAP(v[0], v[1]);
+      period = 2; p[0] = (v[0] << 4) | 1; p[1] = (v[1] << 4) | 1;
+    } else if (nsym == 3) {
+      if (v[2] < v[1]) BD_SWAP(v[1], v[2]);
+      period = 4; p[0] = p[2] = (v[0] << 4) | 1; p[1] = (v[1] << 4) | 2; p[3] = (v[2] << 4) | 2;
+    } else if (!tree_select) {
+      for (int i = 0; i < 3; i++) for (int j = i + 1; j < 4; j++) if (v[j] < v[i]) BD_SWAP(v[i], v[j]);
+      period = 4; p[0] = (v[0] << 4) | 2; p[2] = (v[1] << 4) | 2; p[1] = (v[2] << 4) | 2; p[3] = (v[3] << 4) | 2;
+    } else {
+      if (v[3] < v[2]) BD_SWAP(v[2], v[3]);
+      period = 8;
+      p[0] = p[2] = p[4] = p[6] = (v[0] << 4) | 1;
+      p[1] = p[5] = (v[1] << 4) | 2; p[3] = (v[2] << 4) | 3; p[7] = (v[3] << 4) | 3;
+    }
+#undef BD_SWAP
+    if (256 > cap_entries) return kErrUnreachable;
+    for (uint32_t i = lane; i < 256; i += hw::kWarp) {
+      uint32_t q = i & (period - 1), e = p[0];
+#pragma unroll
+      for (uint32_t t = 1; t < 8; t++) if (q == t) e = p[t];
+      tab[i] = (uint16_t)e;
+    }
+    table_size = 256;
+    hw::syncwarp();
+    return kSuccess;
+  }
+  // ---- complex code: code-length code lengths (src/decode.rs:801-853) ----
+  WarpScratch& ws = *d.ws;
+  for (uint32_t i = 0; i < 16; i++) ws.count[i] = 0;
+  for (uint32_t i = 0; i < 18; i++) ws.cl_cl[i] = 0;
+  uint32_t space = 32, num_codes = 0, last_sym = 0;
+  for (uint32_t i = hskip; i < 18; i++) {
+    const uint32_t ix = br.peek() & 15u;
+    const uint32_t v = tbl::kCodeLengthPrefixValue[ix];
+    br.skip<false>(tbl::kCodeLengthPrefixLength[ix]);
+    const uint32_t sym = tbl::kCodeLengthCodeOrder[i];
+    ws.cl_cl[sym] = (uint8_t)v;
+    if (v != 0) {
+      space -= 32u >> v; num_codes++; ws.count[v]++; last_sym = sym;
+      if (space - 1u >= 32u) break;
+    }
+  }
+  if (!(num_codes == 1 || space == 0)) return br.overrun() ? kNeedsMoreInput : kErrClSpace;
+  // BrotliBuildCodeLengthsHuffmanTable, src/huffman/mod.rs:196-271
+  if (num_codes == 1) {
+    for (uint32_t i = 0; i < 32; i++) ws.cl_tab[i] = (uint16_t)(last_sym << 8);
+  } else {
+    uint32_t code = 0;
+    for (uint32_t l = 1; l <= 5; l++) {
+      for (uint32_t s = 0; s < 18; s++) {
+        if (ws.cl_cl[s] == l) {
+          const uint32_t rev = hw::brev(code) >> (32 - l);
+          for (uint32_t r = rev; r < 32; r += 1u << l) ws.cl_tab[r] = (uint16_t)((s << 8) | l);
+          code++;
+        }
+      }
+      code <<= 1;
+    }
+  }
+  // ---- symbol code lengths (src/decode.rs:565-731) ----
+  uint8_t* clen = d.arena + ArenaLayout::kCodeLen;
+  for (uint32_t i = 0; i < 16; i++) ws.count[i] = 0;
+  for (uint32_t i = lane; i < max_symbol; i += hw::kWarp) clen[i] = 0;
+  hw::syncwarp();
+  uint32_t symbol = 0, prev_code_len = 8, repeat = 0, repeat_code_len = 0;
+  space = 32768;
+  while (symbol < max_symbol && space > 0) {
+    const uint32_t bits = br.peek();
+    const uint32_t p = ws.cl_tab[bits & 31u];
+    const uint32_t code_len = p >> 8;
+    if (code_len < 16) {
+      br.skip<false>(p & 0xFF);
+      repeat = 0;
+      if (code_len != 0) {
+        clen[symbol] = (uint8_t)code_len;
+        prev_code_len = code_len;
+        space -= 32768u >> code_len;
+        ws.count[code_len]++;
+      }
+      symbol++;
+    } else {  // ProcessRepeatedCodeLength, src/decode.rs:600-658
+      const uint32_t extra_bits = code_len - 14;
+      uint32_t repeat_delta = (bits >> (p & 0xFF)) & ((1u << extra_bits) - 1u);
+      br.skip<false>((p & 0xFF) + extra_bits);
+      const uint32_t new_len = code_len == 16 ? prev_code_len : 0;
+      if (repeat_code_len != new_len) { repeat = 0; repeat_code_len = new_len; }
+      const uint32_t old_repeat = repeat;
+      if (repeat > 0) { repeat -= 2; repeat <<= extra_bits; }
+      repeat += repeat_delta + 3;
+      repeat_delta = repeat - old_repeat;
+      if (symbol + repeat_delta > max_symbol) { symbol = max_symbol; space = 0xFFFFF; break; }
+      if (repeat_code_len != 0) {
+        for (uint32_t r = lane; r < repeat_delta; r += hw::kWarp) clen[symbol + r] = (uint8_t)repeat_code_len;
+        space -= repeat_delta << (15 - repeat_code_len);
+        ws.count[repeat_code_len] = (uint16_t)(ws.count[repeat_code_len] + repeat_delta);
+      }
+      symbol += repeat_delta;
+    }
+  }
+  if (space != 0) return br.overrun() ? kNeedsMoreInput : kErrHuffmanSpace;
+  hw::syncwarp();
+  return build_table(d, tab, cap_entries, max_symbol, table_size);
+}
+
+// ======================= small header pieces =======================
+// DecodeVarLenUint8, src/decode.rs:193-241
+BD_DEV uint32_t read_varlen_uint8(BitReader& br) {
+  if (!br.read<false>(1)) return 0;
+  const uint32_t n = br.read<false>(3);
+  if (n == 0) return 1;
+  return (1u << n) + br.read<false>(n);
+}
+
+// ReadBlockLength, src/decode.rs:1016-1026
+template <bool FAST>
+BD_DEV uint32_t read_block_length(BitReader& br, const uint16_t* tree) {
+  uint32_t len;
+  const uint32_t code = decode_symbol(tree, br.peek(), len);
+  br.skip<FAST>(len);
+  const uint32_t nbits = tbl::kBrotliBlockLengthNBits[code];
+  return tbl::kBrotliBlockLengthOffset[code] + br.read<FAST>(nbits);
+}
+
+// DecodeBlockTypeAndLength, src/decode.rs:1469-1524 (caller has checked num_types > 1)
+template <bool FAST>
+BD_DEV void read_block_switch(Decoder& d, int cat, uint32_t num_types, uint32_t& rb0, uint32_t& rb1, uint32_t& block_length) {
+  uint32_t len;
+  uint32_t block_type = decode_symbol(d.block_type_tree(cat), d.br.peek(), len);
+  d.br.skip<FAST>(len);
+  block_length = read_block_length<FAST>(d.br, d.block_len_tree(cat));
+  if (block_type == 1) block_type = rb1 + 1;
+  else if (block_type == 0) block_type = rb0;
+  else block_type -= 2;
+  if (block_type >= num_types) block_type -= num_types;
+  rb0 = rb1; rb1 = block_type;
+}
+
+// PrepareLiteralDecoding + DetectTrivialLiteralBlockTypes, src/decode.rs:1525-1570
+BD_DEV void prepare_literal_decoding(Decoder& d) {
+  const uint32_t block_type = d.rbt_l1;
+  d.ctx_slice = block_type << 6;
+  const uint8_t* map = d.ctx_map_lit() + d.ctx_slice;
+  const uint32_t sample = map[0];
+  bool same = true;
+  for (uint32_t j = hw::lane(); j < 64; j += hw::kWarp) same = same && (map[j] == sample);
+  d.trivial_ctx = hw::all(same) ? 1u : 0u;
+  d.lit_tree = d.tables + d.tree_off_lit()[sample];
+  d.ctx_mode_off = (uint32_t)(d.ctx_modes()[block_type] & 3u) * 512u;
+}
+
+// InverseMoveToFrontTransform, src/decode.rs:1096-1128 (warp-uniform, serial)
+BD_DEV void inverse_move_to_front(Decoder& d, uint8_t* v, uint32_t n) {
+  uint8_t* mtf = d.arena + ArenaLayout::kMtf;
+  for (uint32_t i = hw::lane(); i < 256; i += hw::kWarp) mtf[i] = (uint8_t)i;
+  hw::syncwarp();
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t index = v[i];
+    const uint8_t value = mtf[index];
+    v[i] = value;
+    for (; index > 0; index--) mtf[index] = mtf[index - 1];
+    mtf[0] = value;
+  }
+  hw::syncwarp();
+}
+
+// DecodeContextMap, src/decode.rs:1272-1428
+BD_DEV int decode_context_map(Decoder& d, uint32_t map_size, uint8_t* map, uint32_t& num_htrees) {
+  BitReader& br = d.br;
+  const uint32_t lane = hw::lane();
+  num_htrees = read_varlen_uint8(br) + 1;
+  for (uint32_t i = lane; i < map_size; i += hw::kWarp) map[i] = 0;
+  hw::syncwarp();
+  if (num_htrees <= 1) return kSuccess;
+  uint32_t max_rle = 0;
+  const uint32_t b5 = br.peek() & 31u;
+  if (b5 & 1) { max_rle = (b5 >> 1) + 1; br.skip<false>(5); } else { br.skip<false>(1); }
+  const uint32_t alphabet = num_htrees + max_rle;
+  uint32_t tsize;
+  int r = read_huffman_code(d, alphabet, alphabet, d.ctx_map_tree(), kMaxCtxMapTable, tsize);
+  if (r != kSuccess) return r;
+  const uint16_t* tree = d.ctx_map_tree();
+  uint32_t idx = 0;
+  while (idx < map_size) {
+    uint32_t len;
+    const uint32_t code = decode_symbol(tree, br.peek(), len);
+    br.skip<false>(len);
+    if (code == 0) { idx++; continue; }  // already zero
+    if (code > max_rle) { map[idx++] = (uint8_t)(code - max_rle); continue; }
+    const uint32_t reps = (1u << code) + br.read<false>(code);
+    if (idx + reps > map_size) return br.overrun() ? kNeedsMoreInput : kErrContextMapRepeat;
+    idx += reps;  // zeros
+    if (br.overrun()) return kNeedsMoreInput;
+  }
+  hw::syncwarp();
+  if (br.read<false>(1)) inverse_move_to_front(d, map, map_size);
+  return kSuccess;
+}
+
+// ======================= output primitives =======================
+// LZ77 copy of `len` bytes from `dist` back with byte-serial (overlapping) semantics,
+// src/decode.rs:2641-2720.  Caller guarantees pos + len <= cap and dist <= pos.
+BD_DEV void warp_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
+  const uint32_t lane = hw::lane();
+  hw::syncwarp();  // earlier stores by other lanes must be visible to the loads below
+  uint8_t* dst = out + pos;
+  const uint8_t* src = dst - dist;
+  if (dist >= len) {  // no overlap at all
+    for (uint32_t i = lane; i < len; i += hw::kWarp) dst[i] = src[i];
+  } else if (dist >= hw::kWarp) {  // overlap only across 32-byte steps
+    for (uint32_t base = 0; base < len; base += hw::kWarp) {
+      const uint32_t i = base + lane;
+      if (i < len) dst[i] = src[i];
+      hw::syncwarp();
+    }
+  } else {  // periodic pattern: every source byte lies before pos
+    for (uint32_t i = lane; i < len; i += hw::kWarp) dst[i] = src[i % dist];
+  }
+}
+
+// Static dictionary word + transform (src/decode.rs:2597-2620, src/transform.rs:720-795) into ws.word.
+BD_DEV uint32_t build_dictionary_word(Decoder& d, uint32_t offset, uint32_t wlen, uint32_t transform_idx) {
+  uint8_t* o = d.ws->word;
+  const uint8_t* dict = d.luts.dictionary + offset;
+  const uint8_t* prefix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[transform_idx * 3]];
+  const uint32_t t = tbl::kBrotliTransforms[transform_idx * 3 + 1];
+  const uint8_t* suffix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[transform_idx * 3 + 2]];
+  uint32_t idx = 0;
+  while (prefix[idx]) { o[idx] = prefix[idx]; idx++; }
+  int32_t len = (int32_t)wlen;
+  int32_t skip = t < tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 ? 0 : (int32_t)t - (tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 - 1);
+  if (skip > len) skip = len;
+  dict += skip; len -= skip;
+  if (t <= tbl::BROTLI_TRANSFORM_OMIT_LAST_9) len -= (int32_t)t;
+  const uint32_t body = idx;
+  for (int32_t i = 0; i < len; i++) o[idx++] = hw::ldg8(dict + i);
+  if (t == tbl::BROTLI_TRANSFORM_UPPERCASE_FIRST || t == tbl::BROTLI_TRANSFORM_UPPERCASE_ALL) {
+    // ToUpperCase, src/transform.rs:720-735.  The reference may touch up to two bytes past the
+    // word; those bytes are then overwritten by the suffix / later output, so confine the
+    // effect to the staging buffer (zero-filled tail is harmless).
+    o[idx] = 0; o[idx + 1] = 0;
+    uint32_t q = body; int32_t left = len;
+    do {
+      uint32_t step;
+      if (o[q] < 0xc0) { if (o[q] >= 'a' && o[q] <= 'z') o[q] ^= 32; step = 1; }
+      else if (o[q] < 0xe0) { o[q + 1] ^= 32; step = 2; }
+      else { o[q + 2] ^= 5; step = 3; }
+      q += step; left -= (int32_t)step;
+    } while (t == tbl::BROTLI_TRANSFORM_UPPERCASE_ALL && left > 0);
+  }
+  for (uint32_t i = 0; suffix[i]; i++) o[idx++] = suffix[i];
+  hw::syncwarp();
+  return idx;
+}
+
+// ======================= distance (src/decode.rs:2017-2131) =======================
+template <bool FAST>
+BD_DEV int32_t read_distance(Decoder& d, uint32_t& push_to_ring) {
+  BitReader& br = d.br;
+  const uint32_t tree_idx = d.ctx_map_dist()[d.dist_slice + d.dist_ctx];
+  const uint16_t* tree = d.tables + d.tree_off_dist()[tree_idx];
+  uint32_t len;
+  const uint32_t code = decode_symbol(tree, br.peek(), len);
+  br.skip<FAST>(len);
+  d.bl_d--;
+  push_to_ring = 1;
+  if (code < 16) {  // TakeDistanceFromRingBuffer
+    if (code == 0) { push_to_ring = 0; return d.d0; }
+    // codes 1..3: d1..d3; 4..9: d0 -1,+1,-2,+2,-3,+3; 10..15: d1 likewise
+    int32_t base;
+    if (code < 4) return code == 1 ? d.d1 : (code == 2 ? d.d2 : d.d3);
+    const uint32_t c = code - 4;
+    base = c < 6 ? d.d0 : d.d1;
+    const uint32_t m = c < 6 ? c : c - 6;
+    const int32_t delta = (int32_t)(m >> 1) + 1;
+    int32_t v = (m & 1) ? base + delta : base - delta;
+    if (!(m & 1) && v <= 0) v = 0x7fffffff;  // src/decode.rs:2042-2046
+    return v;
+  }
+  int32_t distval = (int32_t)code - (int32_t)d.ndirect;
+  uint32_t dc = code;
+  if (distval >= 0) {
+    const uint32_t postfix = (uint32_t)distval & ((1u << d.npostfix) - 1u);
+    const uint32_t hcode = (uint32_t)distval >> d.npostfix;
+    const uint32_t nbits = (hcode >> 1) + 1;
+    const uint32_t bits = br.read<FAST>(nbits);
+    const uint32_t offset = ((2u + (hcode & 1u)) << nbits) - 4u;
+    dc = ((offset + bits) << d.npostfix) + postfix + d.ndirect;
+  }
+  return (int32_t)(dc - 16u + 1u);
+}
+
+// ======================= command loop (src/decode.rs:2330-2744) =======================
+// FAST (SAFE=false): unchecked word loads, no per-byte limits; entered only when the input has
+// >= 16 whole words of slack and the command cannot reach the output capacity or a flush point.
+// SAFE: bounds-aware loads, truncation checked before anything is emitted, output split at the
+// capacity and at the emulated ring-buffer flush points.  SAFE handles one command and returns
+// kRetryFast so that long streams drop back to the fast loop.
+BD_DEV int flush_event(Decoder& d) {  // WriteRingBuffer at pos >= ringbuffer_size, src/decode.rs:1693-1738
+  if (d.mlen < 0) return kErrBlockLength1;
+  d.flushed = d.next_flush;
+  d.next_flush = d.full_ring ? d.next_flush + d.rbsize : ~(uint64_t)0;
+  return kSuccess;
+}
+
+template <bool SAFE>
+BD_DEV int process_commands(Decoder& d) {
+  BitReader& br = d.br;
+  const uint32_t lane = hw::lane();
+  constexpr bool FAST = !SAFE;
+  for (;;) {
+    if (d.state == kCmdBegin) {
+      if (FAST && !br.fast_ok(16)) return kNeedSafe;
+      if (d.bl_c == 0) {  // DecodeCommandBlockSwitch, src/decode.rs:1609-1621
+        if (d.nbt_c <= 1) return kNeedsMoreInput;  // reference quirk, src/decode.rs:2368-2373 with :1479-1481
+        read_block_switch<FAST>(d, 1, d.nbt_c, d.rbt_c0, d.rbt_c1, d.bl_c);
+        d.cmd_tree = d.tables + d.tree_off_cmd()[d.rbt_c1];
+      }
+      // ReadCommandInternal, src/decode.rs:2134-2189
+      uint32_t len;
+      const uint32_t sym = decode_symbol(d.cmd_tree, br.peek(), len);
+      br.skip<FAST>(len);
+      const uint2 lut = d.luts.cmd_lut[sym];
+      const uint32_t ie = (lut.x >> 16) & 0xFF, ce = lut.y >> 16;
+      uint32_t insert_len = lut.x & 0xFFFF;
+      if (ie) insert_len += br.read<FAST>(ie);
+      d.copy_len = (lut.y & 0xFFFF) + br.read<FAST>(ce);
+      d.implicit_dist = (lut.x >> 26) & 1;
+      d.dist_ctx = (lut.x >> 24) & 3;
+      d.bl_c--;
+      if (SAFE && br.overrun()) return kNeedsMoreInput;
+      d.ins_rem = insert_len;
+      d.mlen -= (int32_t)insert_len;
+      d.state = insert_len ? kCmdInner : kCmdPostLiterals;
+      if (FAST) {
+        // everything this command can write must stay clear of cap and of the next flush point
+        const uint64_t limit = d.next_flush < d.cap ? d.next_flush : d.cap;
+        if ((uint64_t)d.pos + insert_len + (d.copy_len > 40 ? d.copy_len : 40) >= limit) return kNeedSafe;
+      }
+    }
+    if (d.state == kCmdInner) {
+      uint32_t i = d.ins_rem;
+      if (d.trivial_ctx) {  // src/decode.rs:2393-2462
+        do {
+          if (FAST && !br.fast_ok(4)) { d.ins_rem = i; return kNeedSafe; }
+          if (d.bl_l == 0) {
+            if (d.nbt_l > 1) {
+              read_block_switch<FAST>(d, 0, d.nbt_l, d.rbt_l0, d.rbt_l1, d.bl_l);
+              prepare_literal_decoding(d);
+              if (!d.trivial_ctx) break;
+            } else if (SAFE) { d.ins_rem = i; return kNeedsMoreInput; }
+          }
+          uint32_t len;
+          const uint32_t lit = decode_symbol(d.lit_tree, br.peek(), len);
+          br.skip<FAST>(len);
+          bool keep = true;
+          if (SAFE) {
+            if (br.overrun()) { d.ins_rem = i; return kNeedsMoreInput; }
+            // The reference decodes into its ring buffer and only notices a full output buffer at
+            // a flush; a truncated input or an MLEN overshoot (BLOCK_LENGTH_1/2) is reported first.
+            // So past the capacity keep consuming this literal run without storing it.
+            if (d.pos >= d.cap) keep = false;
+          }
+          if (keep) { if (lane == 0) d.out[d.pos] = (uint8_t)lit; }
+          if (d.bl_l == 0) return kErrWindowBits;  // src/decode.rs:2434-2438
+          d.bl_l--;
+          if (keep) d.pos++; else d.discarded++;
+          i--;
+          if (SAFE && (uint64_t)d.pos + d.discarded == d.next_flush) { d.ins_rem = i; int r = flush_event(d); if (r != kSuccess) return r; }
+        } while (i != 0);
+      }
+      if (i != 0) {  // context-dependent literals, src/decode.rs:2463-2551
+        hw::syncwarp();
+        uint32_t p1 = d.pos >= 1 ? d.out[d.pos - 1] : 0, p2 = d.pos >= 2 ? d.out[d.pos - 2] : 0;
+        const uint8_t* map = d.ctx_map_lit();
+        const uint32_t* toff = d.tree_off_lit();
+        do {
+          if (FAST && !br.fast_ok(4)) { d.ins_rem = i; return kNeedSafe; }
+          if (d.bl_l == 0) {
+            if (d.nbt_l > 1) {
+              read_block_switch<FAST>(d, 0, d.nbt_l, d.rbt_l0, d.rbt_l1, d.bl_l);
+              prepare_literal_decoding(d);
+              if (d.trivial_ctx) break;
+            } else if (SAFE) { d.ins_rem = i; return kNeedsMoreInput; }
+          }
+          const uint32_t context = d.luts.ctx_lut[d.ctx_mode_off + p1] | d.luts.ctx_lut[d.ctx_mode_off + 256 + p2];
+          const uint16_t* tree = d.tables + toff[map[d.ctx_slice + context]];
+          uint32_t len;
+          const uint32_t lit = decode_symbol(tree, br.peek(), len);
+          br.skip<FAST>(len);
+          bool keep = true;
+          if (SAFE) {
+            if (br.overrun()) { d.ins_rem = i; return kNeedsMoreInput; }
+            if (d.pos >= d.cap) keep = false;
+          }
+          p2 = p1; p1 = lit;
+          if (keep) { if (lane == 0) d.out[d.pos] = (uint8_t)lit; }
+          if (d.bl_l == 0) return kErrWindowBits;  // src/decode.rs:2522-2526
+          d.bl_l--;
+          if (keep) d.pos++; else d.discarded++;
+          i--;
+          if (SAFE && (uint64_t)d.pos + d.discarded == d.next_flush) { d.ins_rem = i; int r = flush_event(d); if (r != kSuccess) return r; }
+        } while (i != 0);
+      }
+      d.ins_rem = i;
+      if (i != 0) continue;  // literal block switch flipped trivial <-> contextual: re-dispatch
+      if (SAFE && d.discarded != 0 && d.mlen >= 0) return kNeedsMoreOutput;
+      if (d.mlen <= 0) return kMetablockDone;
+      d.state = kCmdPostLiterals;
+    }
+    // ---- kCmdPostLiterals: distance, then copy or dictionary word (src/decode.rs:2559-2689) ----
+    if (FAST && !br.fast_ok(8)) return kNeedSafe;
+    int32_t dist;
+    uint32_t push = 0;
+    if (d.implicit_dist) {
+      dist = d.d0;
+    } else {
+      if (d.bl_d == 0 && d.nbt_d > 1) {  // DecodeDistanceBlockSwitch, src/decode.rs:1643-1658
+        read_block_switch<FAST>(d, 2, d.nbt_d, d.rbt_d0, d.rbt_d1, d.bl_d);
+        d.dist_slice = d.rbt_d1 << 2;
+      } else if (d.bl_d == 0 && SAFE) {
+        return kNeedsMoreInput;
+      }
+      dist = read_distance<FAST>(d, push);
+      if (SAFE && br.overrun()) return kNeedsMoreInput;
+    }
+    const uint32_t max_distance = d.pos < d.max_backward ? d.pos : d.max_backward;  // src/decode.rs:2583-2589
+    const uint32_t copy_len = d.copy_len;
+    if (dist > (int32_t)max_distance) {  // static dictionary, src/decode.rs:2593-2640
+      if (dist > 0x7FFFFFFC) return kErrDistance;
+      if (copy_len < 4 || copy_len > 24) return kErrDictionary;
+      const uint32_t word_id = (uint32_t)dist - max_distance - 1;
+      const uint32_t shift = tbl::kBrotliDictSizeBitsByLength[copy_len];
+      const uint32_t word_idx = word_id & ((1u << shift) - 1u);
+      const uint32_t transform_idx = word_id >> shift;
+      if (transform_idx >= 121) return kErrTransform;
+      const uint32_t offset = tbl::kBrotliDictOffsetsByLength[copy_len] + word_idx * copy_len;
+      uint32_t n;
+      if (transform_idx == 0) {
+        n = copy_len;
+        hw::syncwarp();
+        for (uint32_t i = lane; i < n; i += hw::kWarp) d.ws->word[i] = hw::ldg8(d.luts.dictionary + offset + i);
+        hw::syncwarp();
+      } else {
+        hw::syncwarp();
+        n = build_dictionary_word(d, offset, copy_len, transform_idx);
+      }
+      uint32_t room = n;
+      if (SAFE && d.cap - d.pos < n) room = d.cap - d.pos;
+      for (uint32_t i = lane; i < room; i += hw::kWarp) d.out[d.pos + i] = d.ws->word[i];
+      if (room < n) {
+        if (d.mlen - (int32_t)n < 0)  // overshoots MLEN: the reference fails before it ever flushes (see literal loop)
+          return (uint64_t)d.pos + d.discarded + n >= d.next_flush ? kErrBlockLength1 : kErrBlockLength2;
+        d.pos += room; return kNeedsMoreOutput;
+      }
+      d.pos += n;
+      d.mlen -= (int32_t)n;
+      if (SAFE && d.pos >= d.next_flush) { int r = flush_event(d); if (r != kSuccess) return r; }
+    } else {
+      if (dist <= 0) return kErrUnreachable;  // cannot happen for symbols < max_symbol; keeps the copy in bounds
+      if (push) { d.d3 = d.d2; d.d2 = d.d1; d.d1 = d.d0; d.d0 = dist; }
+      d.mlen -= (int32_t)copy_len;
+      if (FAST) {
+        warp_copy(d.out, d.pos, (uint32_t)dist, copy_len);
+        d.pos += copy_len;
+      } else {
+        uint32_t left = copy_len;
+        while (left > 0) {
+          if (d.pos >= d.cap) {
+            if (d.mlen < 0) return (uint64_t)d.pos + d.discarded + left >= d.next_flush ? kErrBlockLength1 : kErrBlockLength2;
+            return kNeedsMoreOutput;
+          }
+          uint64_t seg = left;
+          if (seg > d.cap - d.pos) seg = d.cap - d.pos;
+          if (seg > d.next_flush - d.pos) seg = d.next_flush - d.pos;
+          warp_copy(d.out, d.pos, (uint32_t)dist, (uint32_t)seg);
+          d.pos += (uint32_t)seg; left -= (uint32_t)seg;
+          if (d.pos == d.next_flush) { int r = flush_event(d); if (r != kSuccess) return r; }
+        }
+      }
+    }
+    d.state = kCmdBegin;
+    if (d.mlen <= 0) return kMetablockDone;
+    if (SAFE) return kRetryFast;
+  }
+}
+
+// ======================= metablock header (src/decode.rs:243-372, :3046-3288) =======================
+BD_DEV int read_block_split_header(Decoder& d, int cat, uint32_t& num_types, uint32_t& block_length) {
+  num_types = read_varlen_uint8(d.br) + 1;
+  block_length = 1u << 24;
+  if (num_types < 2) return kSuccess;
+  uint32_t tsize;
+  int r = read_huffman_code(d, num_types + 2, num_types + 2, d.block_type_tree(cat), kMaxBlockTypeTable, tsize);
+  if (r != kSuccess) return r;
+  r = read_huffman_code(d, 26, 26, d.block_len_tree(cat), kMaxBlockLenTable, tsize);
+  if (r != kSuccess) return r;
+  block_length = read_block_length<false>(d.br, d.block_len_tree(cat));
+  return kSuccess;
+}
+
+// BrotliMaxDistanceSymbol, src/decode.rs:2766-2777
+BD_DEV uint32_t max_distance_symbol(uint32_t ndirect, uint32_t npostfix) {
+  const uint32_t bound = npostfix == 0 ? 0u : npostfix == 1 ? 4u : npostfix == 2 ? 12u : 28u;
+  const uint32_t diff = npostfix == 0 ? 73u : npostfix == 1 ? 126u : npostfix == 2 ? 228u : 424u;
+  const uint32_t postfix = 1u << npostfix;
+  if (ndirect < bound) return ndirect + diff + postfix;
+  if (ndirect > bound + postfix) return ndirect + diff;
+  return bound + diff + postfix;
+}
+
+BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint32_t max_symbol, uint32_t* tree_off, uint32_t& next_off) {
+  for (uint32_t i = 0; i < ntrees; i++) {
+    uint32_t tsize = 0;
+    const uint32_t room = (uint32_t)(ArenaLayout::kTableEntries - next_off);
+    int r = read_huffman_code(d, alphabet, max_symbol, d.tables + next_off, room, tsize);
+    if (r != kSuccess) return r;
+    tree_off[i] = next_off;
+    next_off += tsize;
+  }
+  hw::syncwarp();
+  return kSuccess;
+}
+
+// Everything between MLEN and the first command of a compressed metablock.
+BD_DEV int read_compressed_metablock_header(Decoder& d) {
+  BitReader& br = d.br;
+  int r;
+  if ((r = read_block_split_header(d, 0, d.nbt_l, d.bl_l)) != kSuccess) return r;
+  if ((r = read_block_split_header(d, 1, d.nbt_c, d.bl_c)) != kSuccess) return r;
+  if ((r = read_block_split_header(d, 2, d.nbt_d, d.bl_d)) != kSuccess) return r;
+  d.rbt_l0 = 1; d.rbt_l1 = 0; d.rbt_c0 = 1; d.rbt_c1 = 0; d.rbt_d0 = 1; d.rbt_d1 = 0;  // src/state.rs:430-435
+  const uint32_t bits = br.read<false>(6);  // src/decode.rs:3141-3153
+  d.npostfix = bits & 3;
+  d.ndirect = 16 + ((bits >> 2) << d.npostfix);
+  uint8_t* modes = d.ctx_modes();
+  for (uint32_t i = 0; i < d.nbt_l; i++) modes[i] = (uint8_t)br.read<false>(2);  // ReadContextModes, :1991-2015
+  if (br.overrun()) return kNeedsMoreInput;
+  if ((r = decode_context_map(d, d.nbt_l << 6, d.ctx_map_lit(), d.n_lit_trees)) != kSuccess) return r;
+  if (br.overrun()) return kNeedsMoreInput;
+  const uint32_t num_direct_codes = d.ndirect - 16;  // src/decode.rs:3189-3200
+  d.dist_alphabet = 16 + num_direct_codes + ((d.large_window ? 62u : 24u) << (d.npostfix + 1));
+  d.dist_max_symbol = d.large_window ? max_distance_symbol(num_direct_codes, d.npostfix) : d.dist_alphabet;
+  if ((r = decode_context_map(d, d.nbt_d << 2, d.ctx_map_dist(), d.n_dist_trees)) != kSuccess) return r;
+  if (br.overrun()) return kNeedsMoreInput;
+  uint32_t next_off = 0;
+  if ((r = read_tree_group(d, d.n_lit_trees, 256, 256, d.tree_off_lit(), next_off)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.nbt_c, 704, 704, d.tree_off_cmd(), next_off)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.n_dist_trees, d.dist_alphabet, d.dist_max_symbol, d.tree_off_dist(), next_off)) != kSuccess) return r;
+  if (br.overrun()) return kNeedsMoreInput;
+  prepare_literal_decoding(d);
+  d.dist_slice = 0;
+  d.cmd_tree = d.tables + d.tree_off_cmd()[0];
+  d.state = kCmdBegin;
+  return kSuccess;
+}
+
+// "canny" ring-buffer sizing, src/decode.rs:1808-1871 -- only its size matters here.
+BD_DEV void allocate_ring_emulation(Decoder& d, uint32_t is_last, uint32_t is_uncompressed) {
+  if (is_uncompressed) {  // peek at the header of the next metablock: ISLAST + ISLASTEMPTY
+    const uint64_t at = d.br.byte_pos() + (uint64_t)d.mlen;
+    if (at < d.br.size() && (hw::ldg8(d.br.bytes + d.br.lead + at) & 3) == 3) is_last = 1;
+  }
+  uint64_t size = (uint64_t)1 << d.wbits;
+  if (is_last)
+    while (size >= ((uint64_t)d.mlen + 16) * 2 && size > 32) size >>= 1;
+  d.rbsize = size;
+  d.full_ring = size == ((uint64_t)1 << d.wbits);
+  d.next_flush = size;
+  d.rb_allocated = 1;
+}
+
+// CopyUncompressedBlockToOutput, src/decode.rs:1754-1806
+BD_DEV int copy_uncompressed(Decoder& d) {
+  const uint32_t lane = hw::lane();
+  uint64_t in_pos = d.br.byte_pos();
+  const uint64_t in_size = d.br.size();
+  const uint8_t* in = d.br.bytes + d.br.lead;
+  int result = kSuccess;
+  for (;;) {
+    uint64_t n = in_size > in_pos ? in_size - in_pos : 0;
+    if (n > (uint64_t)d.mlen) n = (uint64_t)d.mlen;
+    if (n > d.next_flush - d.pos) n = d.next_flush - d.pos;
+    uint64_t n2 = n;
+    if (n2 > d.cap - d.pos) n2 = d.cap - d.pos;
+    for (uint64_t i = lane; i < n2; i += hw::kWarp) d.out[d.pos + i] = hw::ldg8(in + in_pos + i);
+    d.pos += (uint32_t)n2; d.mlen -= (int32_t)n2; in_pos += n2;
+    if (n2 < n) {
+      // Output full.  The reference keeps copying into its ring buffer and reports a truncated
+      // input first unless a flush point (which needs output space) comes before the input ends.
+      const uint64_t in_left = in_size - in_pos;
+      const uint64_t vend = (uint64_t)d.pos + (in_left < (uint64_t)d.mlen ? in_left : (uint64_t)d.mlen);
+      result = (in_left < (uint64_t)d.mlen && !(d.full_ring && vend >= d.next_flush)) ? kNeedsMoreInput : kNeedsMoreOutput;
+      break;
+    }
+    if (d.full_ring && d.pos == d.next_flush) {
+      int r = flush_event(d);
+      if (r != kSuccess) { result = r; break; }
+      continue;
+    }
+    result = d.mlen == 0 ? kSuccess : kNeedsMoreInput;
+    break;
+  }
+  d.br.seek_byte(in_pos);
+  return result;
+}
+
+// ======================= stream driver (src/decode.rs:2779-3403) =======================
+// Returns the BrotliDecoderErrorCode; *decoded_size follows the reference's flush rules:
+// success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity, fatal -> only
+// what the ring buffer had flushed (multiples of its size).
+BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint32_t allow_large_window,
+                         uint64_t* decoded_size) {
+  BitReader& br = d.br;
+  br.init(in, in_size);
+  d.out = out;
+  d.cap = out_cap > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)out_cap;
+  d.pos = 0; d.mlen = 0; d.rb_allocated = 0; d.rbsize = 0; d.next_flush = ~(uint64_t)0; d.flushed = 0; d.full_ring = 0; d.discarded = 0;
+  d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
+  d.large_window = 0;
+  int result;
+  do {
+    if (in_size >= ((uint64_t)1 << 32)) { result = kErrInvalidArguments; break; }  // src/decode.rs:2799-2801
+    if (in_size == 0) { result = kNeedsMoreInput; break; }
+    // DecodeWindowBits, src/decode.rs:152-187,2940-2951
+    if (br.read<false>(1) == 0) {
+      d.wbits = 16;
+    } else {
+      uint32_t n = br.read<false>(3);
+      if (n != 0) {
+        d.wbits = 17 + n;
+      } else {
+        n = br.read<false>(3);
+        if (n == 1) {
+          if (!allow_large_window || br.read<false>(1) == 1) { result = kErrWindowBits; break; }
+          d.large_window = 1;
+          d.wbits = br.read<false>(6);
+          if (br.overrun()) { result = kNeedsMoreInput; break; }
+          if (d.wbits < 10 || d.wbits > 30) { result = kErrWindowBits; break; }
+        } else {
+          d.wbits = n != 0 ? 8 + n : 17;
+        }
+      }
+    }
+    d.max_backward = (1u << d.wbits) - 16;
+    for (;;) {  // metablocks
+      // DecodeMetaBlockLength, src/decode.rs:243-372
+      const uint32_t is_last = br.read<false>(1);
+      uint32_t is_uncompressed = 0, is_metadata = 0, empty_last = 0;
+      d.mlen = 0;
+      result = kSuccess;
+      if (is_last && br.read<false>(1)) {
+        empty_last = 1;
+      } else {
+        const uint32_t nib = br.read<false>(2);
+        if (nib == 3) {
+          is_metadata = 1;
+          if (br.read<false>(1) != 0) { result = kErrReserved; }
+          else {
+            const uint32_t nbytes = br.read<false>(2);
+            uint32_t v = 0;
+            for (uint32_t i = 0; i < nbytes; i++) {
+              const uint32_t b = br.read<false>(8);
+              if (i + 1 == nbytes && nbytes > 1 && b == 0) { result = kErrExuberantMetaNibble; break; }
+              v |= b << (i * 8);
+            }
+            if (nbytes != 0) d.mlen = (int32_t)v + 1;
+          }
+        } else {
+          const uint32_t nn = nib + 4;
+          uint32_t v = 0;
+          for (uint32_t i = 0; i < nn; i++) {
+            const uint32_t b = br.read<false>(4);
+            if (i + 1 == nn && nn > 4 && b == 0) { result = kErrExuberantNibble; break; }
+            v |= b << (i * 4);
+          }
+          if (result == kSuccess) {
+            if (!is_last) is_uncompressed = br.read<false>(1);
+            d.mlen = (int32_t)v + 1;
+          }
+        }
+      }
+      if (br.overrun()) result = kNeedsMoreInput;
+      if (result != kSuccess) break;
+      if ((is_metadata || is_uncompressed) && !br.jump_to_byte_boundary()) {  // src/decode.rs:2990-2994
+        result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break;
+      }
+      if (br.overrun()) { result = kNeedsMoreInput; break; }
+      if (is_metadata) {  // src/decode.rs:3031-3045
+        const uint64_t at = br.byte_pos(), left = br.size() - at;
+        if (left < (uint64_t)d.mlen) { result = kNeedsMoreInput; break; }
+        br.seek_byte(at + (uint64_t)d.mlen);
+        d.mlen = 0;
+      } else if (d.mlen != 0) {
+        if (!d.rb_allocated) allocate_ring_emulation(d, is_last, is_uncompressed);
+        if (is_uncompressed) {
+          result = copy_uncompressed(d);
+          if (result != kSuccess) break;
+        } else {
+          result = read_compressed_metablock_header(d);
+          if (result == kSuccess && br.overrun()) result = kNeedsMoreInput;
+          if (result != kSuccess) break;
+          for (;;) {  // ProcessCommands / SafeProcessCommands, src/decode.rs:3289-3298
+            result = process_commands<false>(d);
+            if (result == kNeedSafe) result = process_commands<true>(d);
+            if (result != kRetryFast) break;
+          }
+          if (result != kMetablockDone) break;
+          result = kSuccess;
+        }
+      }
+      // BROTLI_STATE_METABLOCK_DONE, src/decode.rs:3345-3381
+      (void)empty_last;
+      if (d.mlen < 0) { result = kErrBlockLength2; break; }
+      if (!is_last) continue;
+      if (!br.jump_to_byte_boundary()) { result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break; }
+      if (br.overrun()) { result = kNeedsMoreInput; break; }
+      result = kSuccess;
+      break;
+    }
+  } while (0);
+  hw::syncwarp();
+  // On NeedsMoreInput the reference flushes its ring buffer (src/decode.rs:2834-2846); that
+  // flush fails with BLOCK_LENGTH_1 when the command in flight has overshot MLEN (:1709-1711).
+  if (result == kNeedsMoreInput && d.rb_allocated && d.mlen < 0) result = kErrBlockLength1;
+  if (result == kSuccess || result == kNeedsMoreInput || result == kNeedsMoreOutput) *decoded_size = d.pos;
+  else *decoded_size = d.flushed;
+  return result;
+}
+
+}  // namespace brotli_b200

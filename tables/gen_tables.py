@@ -98,7 +98,7 @@ def c_array(name, ctype, values, per_line=16, fmt="{}"):
     lines = []
     for i in range(0, len(values), per_line):
         lines.append("  " + ", ".join(fmt.format(v) for v in values[i:i + per_line]) + ",")
-    return "static const %s %s[%d] = {\n%s\n};\n" % (ctype, name, len(values), "\n".join(lines))
+    return "BROTLI_TABLE_ATTR %s %s[%d] = {\n%s\n};\n" % (ctype, name, len(values), "\n".join(lines))
 
 
 def main():
@@ -133,7 +133,9 @@ def main():
              " * RFC 7932 constants shared by oracle/ (CPU checker) and the CUDA decoder.\n"
              " * Reference counterparts: src/prefix.rs, src/context.rs, src/transform.rs:32-716,\n"
              " * src/dictionary/mod.rs:3-15 of dropbox/rust-brotli-decompressor. */\n"
-             "#ifndef BROTLI_B200_TABLES_H_\n#define BROTLI_B200_TABLES_H_\n#include <stdint.h>\n\n")
+             "#ifndef BROTLI_B200_TABLES_H_\n#define BROTLI_B200_TABLES_H_\n#include <stdint.h>\n"
+             "/* storage class of the arrays; the CUDA TU defines it as `__device__ const` */\n"
+             "#ifndef BROTLI_TABLE_ATTR\n#define BROTLI_TABLE_ATTR static const\n#endif\n\n")
     h.append("#define BROTLI_DICTIONARY_SIZE 122784\n"
              "#define BROTLI_MIN_DICTIONARY_WORD_LENGTH 4\n"
              "#define BROTLI_MAX_DICTIONARY_WORD_LENGTH 24\n"
@@ -162,7 +164,7 @@ def main():
     rows = ["  {%d, %d, %d, %d, %d, %d}," % (e["insert_len_extra_bits"], e["copy_len_extra_bits"],
                                             e["distance_code"], e["context"], e["insert_len_offset"],
                                             e["copy_len_offset"]) for e in lut]
-    h.append("static const BrotliCmdLutElement kBrotliCmdLut[704] = {\n" + "\n".join(rows) + "\n};\n")
+    h.append("BROTLI_TABLE_ATTR BrotliCmdLutElement kBrotliCmdLut[704] = {\n" + "\n".join(rows) + "\n};\n")
     h.append("\n#endif  /* BROTLI_B200_TABLES_H_ */\n")
     with open(os.path.join(HERE, "brotli_tables.h"), "w") as f:
         f.write("".join(h))
