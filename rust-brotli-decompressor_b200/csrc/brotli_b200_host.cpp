@@ -1,0 +1,573 @@
+// brotli_b200_host.cpp -- host runtime and C ABI of libbrotli_b200.so (include/brotli_b200/decode.h).
+//
+// The reference's host side is Rust; rustc is not available in the build image, so the host layer
+// above the CUDA kernels is C++ and keeps the reference's names and semantics:
+//   BrotliDecoderDecompress{,WithReturnInfo,Prealloc}   src/ffi/mod.rs:178-292  (-> brotli_decode, src/lib.rs:446-468)
+//   BrotliDecoderDecompressStream & state queries       src/ffi/mod.rs:108-176,389-590
+// plus the batch entry points.  There is no CPU decoder in this file or in anything it links:
+// every byte is decoded by brotli_decode_batch_kernel; without a CUDA device calls fail loudly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/brotli_b200/decode.h"
+#include "brotli_b200_runtime.h"
+
+extern "C" const uint8_t kBrotliDictionaryData[];  // tables/brotli_dictionary.c (122 784 bytes)
+
+namespace {
+
+using brotli_b200::BatchArgs;
+
+constexpr size_t kDictionaryBytes = 122784;
+constexpr int kMaxDevices = 16;
+constexpr size_t kPipelineChunkBytes = 256u << 20;  // in+out bytes per pipeline stage of the host-batch path
+
+thread_local std::string tl_error;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<double> g_last_kernel_ms{0.0};
+
+void set_error(const std::string& s) { tl_error = s; }
+
+const char* error_name(int c) {  // BrotliDecoderErrorStr, src/state.rs:533-578
+  switch (c) {
+    case 0: return "NO_ERROR";
+    case 1: return "SUCCESS";
+    case 2: return "NEEDS_MORE_INPUT";
+    case 3: return "NEEDS_MORE_OUTPUT";
+    case -1: return "ERROR_FORMAT_EXUBERANT_NIBBLE";
+    case -2: return "ERROR_FORMAT_RESERVED";
+    case -3: return "ERROR_FORMAT_EXUBERANT_META_NIBBLE";
+    case -4: return "ERROR_FORMAT_SIMPLE_HUFFMAN_ALPHABET";
+    case -5: return "ERROR_FORMAT_SIMPLE_HUFFMAN_SAME";
+    case -6: return "ERROR_FORMAT_FL_SPACE";  // sic, src/state.rs:547
+    case -7: return "ERROR_FORMAT_HUFFMAN_SPACE";
+    case -8: return "ERROR_FORMAT_CONTEXT_MAP_REPEAT";
+    case -9: return "ERROR_FORMAT_BLOCK_LENGTH_1";
+    case -10: return "ERROR_FORMAT_BLOCK_LENGTH_2";
+    case -11: return "ERROR_FORMAT_TRANSFORM";
+    case -12: return "ERROR_FORMAT_DICTIONARY";
+    case -13: return "ERROR_FORMAT_WINDOW_BITS";
+    case -14: return "ERROR_FORMAT_PADDING_1";
+    case -15: return "ERROR_FORMAT_PADDING_2";
+    case -16: return "ERROR_FORMAT_DISTANCE";
+    case -19: return "ERROR_DICTIONARY_NOT_SET";
+    case -20: return "ERROR_INVALID_ARGUMENTS";
+    case -21: return "ERROR_ALLOC_CONTEXT_MODES";
+    case -22: return "ERROR_ALLOC_TREE_GROUPS";
+    case -25: return "ERROR_ALLOC_CONTEXT_MAP";
+    case -26: return "ERROR_ALLOC_RING_BUFFER_1";
+    case -27: return "ERROR_ALLOC_RING_BUFFER_2";
+    case -30: return "ERROR_ALLOC_BLOCK_TYPE_TREES";
+    default: return "ERROR_UNREACHABLE";
+  }
+}
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Everything the library owns on one GPU.  Created on first use of that device.
+struct DeviceCtx {
+  std::mutex mu;       // serialises users of the staging buffers / arena / streams
+  bool ready = false;
+  int device = -1;
+  int ctas = 0;
+  uint8_t* arena = nullptr;
+  uint8_t* dictionary = nullptr;
+  uint32_t* ticket = nullptr;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  std::mutex launch_mu;          // orders launches: decode kernels share the scratch arena and the ticket
+  cudaEvent_t ev_arena = nullptr;  // completion of the most recent decode launch
+  bool arena_busy = false;
+  DevBuf in, out, in_off, out_off, out_len, codes, in_used;
+  void* pinned = nullptr;  // small pinned staging area for one-shot calls
+  size_t pinned_cap = 0;
+};
+
+DeviceCtx g_ctx[kMaxDevices];
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      set_error(std::string("brotli_b200: CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+      return BROTLI_DECODER_ERROR_UNREACHABLE;                                                    \
+    }                                                                                             \
+  } while (0)
+
+// Returns the context of the current device (initialising it), or nullptr with the error set.
+DeviceCtx* acquire_ctx() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  int count = 0;
+  if (e == cudaSuccess) e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1 || dev >= kMaxDevices) {
+    cudaGetLastError();
+    set_error("brotli_b200: no CUDA device (this library has no CPU decode path)");
+    return nullptr;
+  }
+  DeviceCtx* c = &g_ctx[dev];
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (c->ready) return c;
+  c->device = dev;
+  c->ctas = brotli_b200::query_resident_ctas(dev);
+  if (c->ctas <= 0) { set_error("brotli_b200: occupancy query failed (kernel image not loadable on this device?)"); return nullptr; }
+  const size_t arena_bytes = (size_t)c->ctas * brotli_b200::kWarpsPerCta * brotli_b200::arena_bytes_per_warp();
+  bool ok = cudaMalloc((void**)&c->arena, arena_bytes) == cudaSuccess &&
+            cudaMalloc((void**)&c->dictionary, kDictionaryBytes + 64) == cudaSuccess &&
+            cudaMalloc((void**)&c->ticket, 256) == cudaSuccess &&
+            cudaMemcpy(c->dictionary, kBrotliDictionaryData, kDictionaryBytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev_k0) == cudaSuccess && cudaEventCreate(&c->ev_k1) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_arena, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    set_error(std::string("brotli_b200: device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  c->ready = true;
+  return c;
+}
+
+// ---- device-resident batch -------------------------------------------------------------------
+int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
+                  const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_codes, uint64_t* d_in_used, uint32_t large_window,
+                  cudaStream_t stream) {
+  if (n == 0) return 0;
+  if (n > 0xFFFFFFF0ull) { set_error("brotli_b200: batch too large"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+  BatchArgs a;
+  a.in = d_in; a.in_off = d_in_off; a.out = d_out; a.out_off = d_out_off; a.out_len = d_out_len; a.codes = d_codes;
+  a.in_used = d_in_used;
+  a.order = nullptr; a.ticket = c->ticket; a.arena = c->arena; a.dictionary = c->dictionary;
+  a.n = (uint32_t)n; a.large_window = large_window;
+  std::lock_guard<std::mutex> lock(c->launch_mu);
+  if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
+  CU_TRY(brotli_b200::launch_decode_batch(a, c->ctas, stream));
+  CU_TRY(cudaEventRecord(c->ev_arena, stream));
+  c->arena_busy = true;
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// ---- host-resident packed batch: chunked H2D -> decode -> D2H pipeline ------------------------
+// Chunks are contiguous stream ranges of about kPipelineChunkBytes (in + out).  Copies run on
+// their own streams and are ordered against the decode stream with events, so the H2D of chunk
+// k+1 and the D2H of chunk k-1 overlap the decode of chunk k.  Decode kernels stay on one stream
+// because they share the per-warp scratch arena.
+int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const uint64_t* in_off, uint8_t* out_bytes,
+                       const uint64_t* out_off, uint64_t* out_len, int32_t* codes, uint64_t* in_used, uint32_t large_window) {
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  const uint64_t in_base = in_off[0], out_base = out_off[0];
+  const uint64_t in_total = in_off[n] - in_base, out_total = out_off[n] - out_base;
+  for (size_t i = 0; i < n; i++)
+    if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) { set_error("brotli_b200: offsets must be non-decreasing"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+  CU_TRY(c->in.reserve(in_total + 16));
+  CU_TRY(c->out.reserve(out_total + 16));
+  CU_TRY(c->in_off.reserve((n + 1) * 8));
+  CU_TRY(c->out_off.reserve((n + 1) * 8));
+  CU_TRY(c->out_len.reserve(n * 8));
+  CU_TRY(c->codes.reserve(n * 4));
+  if (in_used) CU_TRY(c->in_used.reserve(n * 8));
+  uint8_t* d_in = (uint8_t*)c->in.p - in_base;   // absolute offsets index the device mirrors directly
+  uint8_t* d_out = (uint8_t*)c->out.p - out_base;
+  CU_TRY(cudaMemcpyAsync(c->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+  CU_TRY(cudaMemcpyAsync(c->out_off.p, out_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+
+  struct Chunk { size_t b, e; cudaEvent_t h2d, done; };
+  std::vector<Chunk> chunks;
+  for (size_t b = 0; b < n;) {
+    size_t e = b; uint64_t acc = 0;
+    while (e < n && (e == b || acc < kPipelineChunkBytes)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
+    chunks.push_back(Chunk{b, e, nullptr, nullptr});
+    b = e;
+  }
+  int rc = 0;
+  for (auto& k : chunks) {
+    if (cudaEventCreateWithFlags(&k.h2d, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) { rc = BROTLI_DECODER_ERROR_UNREACHABLE; set_error("brotli_b200: cudaEventCreate failed"); break; }
+  }
+  bool timed = false;
+  for (size_t ci = 0; ci < chunks.size() && rc == 0; ci++) {
+    Chunk& k = chunks[ci];
+    const uint64_t i0 = in_off[k.b], i1 = in_off[k.e], o0 = out_off[k.b], o1 = out_off[k.e];
+    cudaError_t e = cudaSuccess;
+    if (i1 > i0) e = cudaMemcpyAsync(d_in + i0, in_bytes + i0, i1 - i0, cudaMemcpyHostToDevice, c->s_h2d);
+    if (e == cudaSuccess) e = cudaEventRecord(k.h2d, c->s_h2d);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_compute, k.h2d, 0);
+    if (e == cudaSuccess && ci == 0) { e = cudaEventRecord(c->ev_k0, c->s_compute); timed = true; }
+    if (e != cudaSuccess) { set_error(std::string("brotli_b200: H2D stage failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; break; }
+    rc = decode_device(c, k.e - k.b, d_in, (const uint64_t*)c->in_off.p + k.b, d_out, (const uint64_t*)c->out_off.p + k.b,
+                       (uint64_t*)c->out_len.p + k.b, (int32_t*)c->codes.p + k.b, in_used ? (uint64_t*)c->in_used.p + k.b : nullptr,
+                       large_window, c->s_compute);
+    if (rc != 0) break;
+    if (ci + 1 == chunks.size()) cudaEventRecord(c->ev_k1, c->s_compute);
+    e = cudaEventRecord(k.done, c->s_compute);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_d2h, k.done, 0);
+    if (e == cudaSuccess && o1 > o0) e = cudaMemcpyAsync(out_bytes + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, c->s_d2h);
+    if (e != cudaSuccess) { set_error(std::string("brotli_b200: D2H stage failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; break; }
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_len, c->out_len.p, n * 8, cudaMemcpyDeviceToHost, c->s_d2h);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(codes, c->codes.p, n * 4, cudaMemcpyDeviceToHost, c->s_d2h);
+    if (e == cudaSuccess && in_used) e = cudaMemcpyAsync(in_used, c->in_used.p, n * 8, cudaMemcpyDeviceToHost, c->s_d2h);
+    if (e != cudaSuccess) { set_error(std::string("brotli_b200: result copy failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_compute), e3 = cudaStreamSynchronize(c->s_d2h);
+  if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    set_error(std::string("brotli_b200: batch failed on the device: ") + cudaGetErrorString(e));
+    rc = BROTLI_DECODER_ERROR_UNREACHABLE;
+  }
+  if (rc == 0 && timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) == cudaSuccess) g_last_kernel_ms.store(ms); }
+  for (auto& k : chunks) { if (k.h2d) cudaEventDestroy(k.h2d); if (k.done) cudaEventDestroy(k.done); }
+  return rc;
+}
+
+// is_valid_slice_ptr, src/ffi/mod.rs:45-60
+template <typename T>
+bool valid_slice(const T* p, size_t len, size_t align) {
+  if (len == 0) return true;
+  if (p == nullptr) return false;
+  if (((uintptr_t)p) % align != 0) return false;
+  if (len > (size_t)INTPTR_MAX / sizeof(T)) return false;
+  return (uintptr_t)p + len * sizeof(T) >= (uintptr_t)p;
+}
+
+BrotliDecoderReturnInfo make_info(int result, int code, size_t decoded, const char* msg) {
+  BrotliDecoderReturnInfo r;
+  memset(&r, 0, sizeof(r));
+  r.decoded_size = decoded;
+  r.result = (BrotliDecoderResult)result;
+  r.code = (BrotliDecoderErrorCode)code;
+  strncpy(r.error, msg ? msg : error_name(code), sizeof(r.error) - 1);
+  return r;
+}
+
+BrotliDecoderReturnInfo invalid_arguments_info() {  // src/ffi/mod.rs:83-106
+  return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, 0, nullptr);
+}
+
+// brotli_decode (src/lib.rs:446-468) on the GPU: a batch of one.
+BrotliDecoderReturnInfo one_shot(const uint8_t* in, size_t in_size, uint8_t* out, size_t out_cap, uint32_t large_window,
+                                 uint64_t* in_used) {
+  DeviceCtx* c = acquire_ctx();
+  if (!c) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
+  if (in_size >= ((uint64_t)1 << 32)) return invalid_arguments_info();  // src/decode.rs:2799-2812
+  uint64_t in_off[2] = {0, in_size}, out_off[2] = {0, out_cap}, out_len = 0, used = 0;
+  int32_t code = 0;
+  static const uint8_t kNothing[1] = {0};
+  uint8_t dummy_out[1];
+  int rc = decode_host_packed(c, 1, in ? in : kNothing, in_off, out ? out : dummy_out, out_off, &out_len, &code, &used, large_window);
+  if (rc != 0) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
+  if (in_used) *in_used = used;
+  int result = code == 1 ? 1 : (code == 2 ? 2 : (code == 3 ? 3 : 0));  // BrotliResult
+  return make_info(result, code, (size_t)out_len, nullptr);
+}
+
+}  // namespace
+
+// =========================================== C ABI ===========================================
+extern "C" {
+
+BrotliDecoderResult BrotliDecoderDecompress(size_t encoded_size, const uint8_t* encoded_buffer, size_t* decoded_size,
+                                            uint8_t* decoded_buffer) {
+  try {
+    if (!valid_slice(decoded_size, 1, alignof(size_t))) return BROTLI_DECODER_RESULT_ERROR;
+    BrotliDecoderReturnInfo r = BrotliDecoderDecompressWithReturnInfo(encoded_size, encoded_buffer, *decoded_size, decoded_buffer);
+    *decoded_size = r.decoded_size;
+    return r.result == BROTLI_DECODER_RESULT_SUCCESS ? BROTLI_DECODER_RESULT_SUCCESS : BROTLI_DECODER_RESULT_ERROR;
+  } catch (...) {
+    if (decoded_size) *decoded_size = 0;
+    return BROTLI_DECODER_RESULT_ERROR;
+  }
+}
+
+BrotliDecoderReturnInfo BrotliDecoderDecompressWithReturnInfo(size_t encoded_size, const uint8_t* encoded_buffer,
+                                                              size_t decoded_size, uint8_t* decoded_buffer) {
+  try {
+    if (!valid_slice(encoded_buffer, encoded_size, 1) || !valid_slice(decoded_buffer, decoded_size, 1)) return invalid_arguments_info();
+    return one_shot(encoded_buffer, encoded_size, decoded_buffer, decoded_size, 1u, nullptr);
+  } catch (const std::exception& e) {
+    return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, e.what());
+  } catch (...) {
+    return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, "brotli_b200: unknown exception");
+  }
+}
+
+BrotliDecoderReturnInfo BrotliDecoderDecompressPrealloc(size_t encoded_size, const uint8_t* encoded_buffer, size_t decoded_size,
+                                                        uint8_t* decoded_buffer, size_t scratch_u8_size, uint8_t* scratch_u8_buffer,
+                                                        size_t scratch_u32_size, uint32_t* scratch_u32_buffer,
+                                                        size_t scratch_hc_size, HuffmanCode* scratch_hc_buffer) {
+  if (!valid_slice(scratch_u8_buffer, scratch_u8_size, 1) || !valid_slice(scratch_u32_buffer, scratch_u32_size, alignof(uint32_t)) ||
+      !valid_slice(scratch_hc_buffer, scratch_hc_size, alignof(uint16_t)))
+    return invalid_arguments_info();
+  return BrotliDecoderDecompressWithReturnInfo(encoded_size, encoded_buffer, decoded_size, decoded_buffer);
+}
+
+// ---- streaming state: GPU-backed, re-submits the bytes received so far -----------------------
+struct BrotliDecoderStateStruct {
+  brotli_alloc_func alloc_func;
+  brotli_free_func free_func;
+  void* opaque;
+  std::vector<uint8_t> input;    // every byte handed in so far that belongs to the stream
+  std::vector<uint8_t> output;   // decoded bytes of the stream so far
+  size_t taken;                  // bytes of `output` already handed to the caller
+  size_t consumed_reported;      // input bytes reported as consumed to the caller
+  int last_code;                 // BrotliDecoderErrorCode of the last decode
+  bool used, large_window, failed, finished;
+  char error[256];
+};
+
+BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
+  if ((alloc_func == nullptr) != (free_func == nullptr)) return nullptr;  // src/ffi/mod.rs:132-135
+  void* mem = alloc_func ? alloc_func(opaque, sizeof(BrotliDecoderStateStruct)) : malloc(sizeof(BrotliDecoderStateStruct));
+  if (!mem) return nullptr;
+  BrotliDecoderStateStruct* s = new (mem) BrotliDecoderStateStruct();
+  s->alloc_func = alloc_func; s->free_func = free_func; s->opaque = opaque;
+  s->taken = 0; s->consumed_reported = 0; s->last_code = 0;
+  s->used = false; s->large_window = false; s->failed = false; s->finished = false;
+  s->error[0] = 0;
+  return s;
+}
+
+void BrotliDecoderDestroyInstance(BrotliDecoderState* s) {
+  if (!s) return;
+  brotli_free_func f = s->free_func; void* opaque = s->opaque;
+  s->~BrotliDecoderStateStruct();
+  if (f) f(opaque, s); else free(s);
+}
+
+int BrotliDecoderSetParameter(BrotliDecoderState* s, BrotliDecoderParameter param, uint32_t value) {
+  if (!s || s->used) return 0;  // src/ffi/mod.rs:163-166
+  switch (param) {
+    case BROTLI_DECODER_PARAM_DISABLE_RING_BUFFER_REALLOCATION: return 1;  // no ring buffer exists on the GPU path
+    case BROTLI_DECODER_PARAM_LARGE_WINDOW: s->large_window = value != 0; return 1;
+    default: return 0;
+  }
+}
+
+static BrotliDecoderResult stream_fail(BrotliDecoderState* s, int code, const char* msg) {
+  s->failed = true; s->last_code = code;
+  strncpy(s->error, msg ? msg : error_name(code), sizeof(s->error) - 1);
+  return BROTLI_DECODER_RESULT_ERROR;
+}
+
+static size_t stream_drain(BrotliDecoderState* s, size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  size_t n = s->output.size() - s->taken;
+  if (n > *available_out) n = *available_out;
+  if (n) {
+    memcpy(*next_out, s->output.data() + s->taken, n);
+    *next_out += n; *available_out -= n; s->taken += n;
+  }
+  if (total_out) *total_out = s->taken;
+  return n;
+}
+
+BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t* available_in, const uint8_t** next_in,
+                                                  size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  if (!s) return BROTLI_DECODER_RESULT_ERROR;
+  try {
+    if (!available_in || !next_in || !available_out || !next_out) return stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr);
+    if ((*available_in && !*next_in) || (*available_out && !*next_out)) return stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr);
+    if (s->failed) return BROTLI_DECODER_RESULT_ERROR;  // sticky, src/decode.rs:2796-2798
+    if (s->taken < s->output.size()) {  // hand out what is pending before touching new input
+      stream_drain(s, available_out, next_out, total_out);
+      if (s->taken < s->output.size()) return BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT;
+    }
+    if (s->finished) { if (total_out) *total_out = s->taken; return BROTLI_DECODER_RESULT_SUCCESS; }
+    if (*available_in == 0 && s->used && s->last_code == BROTLI_DECODER_NEEDS_MORE_INPUT) {
+      if (total_out) *total_out = s->taken;
+      return BROTLI_DECODER_RESULT_NEEDS_MORE_INPUT;
+    }
+    const size_t fresh = *available_in;
+    s->input.insert(s->input.end(), *next_in, *next_in + fresh);
+    if (fresh) s->used = true;
+    // decode everything received so far; grow the output until it fits
+    size_t cap = s->output.capacity() > (1u << 16) ? s->output.capacity() : (1u << 16);
+    if (cap < s->input.size() * 6) cap = s->input.size() * 6;
+    BrotliDecoderReturnInfo r;
+    uint64_t used = 0;
+    std::vector<uint8_t> buf;
+    for (;;) {
+      buf.resize(cap);
+      r = one_shot(s->input.data(), s->input.size(), buf.data(), cap, s->large_window ? 1u : 0u, &used);
+      if (r.code != BROTLI_DECODER_NEEDS_MORE_OUTPUT) break;
+      if (cap >= ((size_t)1 << 31)) break;
+      cap *= 4;
+    }
+    if (r.code == BROTLI_DECODER_ERROR_UNREACHABLE && strncmp(r.error, "brotli_b200", 11) == 0) return stream_fail(s, r.code, r.error);
+    if (s->input.size()) s->used = true;
+    // new suffix of the output
+    if (r.decoded_size > s->output.size()) s->output.insert(s->output.end(), buf.data() + s->output.size(), buf.data() + r.decoded_size);
+    s->last_code = r.code;
+    // input accounting: a finished stream leaves trailing bytes unconsumed (src/ffi/mod.rs:452-453)
+    size_t consumed_total = s->input.size();
+    if (r.code == BROTLI_DECODER_SUCCESS) { consumed_total = (size_t)used; s->finished = true; s->input.resize(consumed_total); }
+    const size_t newly = consumed_total > s->consumed_reported ? consumed_total - s->consumed_reported : 0;
+    const size_t adv = newly < fresh ? newly : fresh;
+    *next_in += adv; *available_in -= adv; s->consumed_reported += adv;
+    stream_drain(s, available_out, next_out, total_out);
+    if (r.code < 0) return stream_fail(s, r.code, nullptr);
+    if (s->taken < s->output.size()) return BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT;
+    if (r.code == BROTLI_DECODER_SUCCESS) return BROTLI_DECODER_RESULT_SUCCESS;
+    if (r.code == BROTLI_DECODER_NEEDS_MORE_OUTPUT) return stream_fail(s, BROTLI_DECODER_ERROR_ALLOC_RING_BUFFER_1, nullptr);
+    return BROTLI_DECODER_RESULT_NEEDS_MORE_INPUT;
+  } catch (const std::exception& e) {
+    return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, e.what());
+  } catch (...) {
+    return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, "brotli_b200: unknown exception");
+  }
+}
+
+BrotliDecoderResult BrotliDecoderDecompressStreaming(BrotliDecoderState* s, size_t* available_in, const uint8_t* next_in,
+                                                     size_t* available_out, uint8_t* next_out) {
+  if (!available_in || !available_out) return BrotliDecoderDecompressStream(s, nullptr, nullptr, nullptr, nullptr, nullptr);
+  const uint8_t* in = next_in; uint8_t* out = next_out;
+  return BrotliDecoderDecompressStream(s, available_in, &in, available_out, &out, nullptr);
+}
+
+int BrotliDecoderHasMoreOutput(const BrotliDecoderState* s) { return s && !s->failed && s->taken < s->output.size() ? 1 : 0; }
+
+const uint8_t* BrotliDecoderTakeOutput(BrotliDecoderState* s, size_t* size) {
+  if (!s || !size) return nullptr;
+  size_t avail = s->output.size() - s->taken;
+  size_t n = *size == 0 ? avail : (*size < avail ? *size : avail);
+  if (s->failed || n == 0) { *size = 0; return nullptr; }
+  const uint8_t* p = s->output.data() + s->taken;
+  s->taken += n; *size = n;
+  return p;
+}
+
+int BrotliDecoderIsUsed(const BrotliDecoderState* s) { return s && s->used ? 1 : 0; }
+int BrotliDecoderIsFinished(const BrotliDecoderState* s) { return s && s->finished && !s->failed && s->taken == s->output.size() ? 1 : 0; }
+BrotliDecoderErrorCode BrotliDecoderGetErrorCode(const BrotliDecoderState* s) { return (BrotliDecoderErrorCode)(s ? s->last_code : 0); }
+const char* BrotliDecoderGetErrorString(const BrotliDecoderState* s) { return s && s->error[0] ? s->error : ""; }
+const char* BrotliDecoderErrorString(BrotliDecoderErrorCode c) { return error_name((int)c); }
+uint32_t BrotliDecoderVersion(void) { return 0x1000f00; }  // src/ffi/mod.rs:588-590
+
+uint8_t* BrotliDecoderMallocU8(BrotliDecoderState* s, size_t size) {
+  return (uint8_t*)(s && s->alloc_func ? s->alloc_func(s->opaque, size) : malloc(size));
+}
+void BrotliDecoderFreeU8(BrotliDecoderState* s, uint8_t* data, size_t) {
+  if (s && s->free_func) s->free_func(s->opaque, data); else free(data);
+}
+size_t* BrotliDecoderMallocUsize(BrotliDecoderState* s, size_t size) {
+  return (size_t*)(s && s->alloc_func ? s->alloc_func(s->opaque, size * sizeof(size_t)) : malloc(size * sizeof(size_t)));
+}
+void BrotliDecoderFreeUsize(BrotliDecoderState* s, size_t* data, size_t) {
+  if (s && s->free_func) s->free_func(s->opaque, data); else free(data);
+}
+
+// ---- batch extension -------------------------------------------------------------------------
+int BrotliB200DecompressBatchDevice(size_t n, const uint8_t* d_in_bytes, const uint64_t* d_in_off, uint8_t* d_out_bytes,
+                                    const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_codes, void* cuda_stream) {
+  try {
+    if (n == 0) return 0;
+    if (!d_in_off || !d_out_off || !d_out_len || !d_codes) { set_error("brotli_b200: null batch array"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+    DeviceCtx* c = acquire_ctx();
+    if (!c) return BROTLI_DECODER_ERROR_UNREACHABLE;
+    return decode_device(c, n, d_in_bytes, d_in_off, d_out_bytes, d_out_off, d_out_len, d_codes, nullptr, 1u, (cudaStream_t)cuda_stream);
+  } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
+}
+
+int BrotliB200DecompressBatchPacked(size_t n, const uint8_t* in_bytes, const uint64_t* in_off, uint8_t* out_bytes,
+                                    const uint64_t* out_off, uint64_t* out_len, int32_t* codes) {
+  try {
+    if (n == 0) return 0;
+    if (!in_off || !out_off || !out_len || !codes || !in_bytes || !out_bytes) { set_error("brotli_b200: null batch array"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+    DeviceCtx* c = acquire_ctx();
+    if (!c) return BROTLI_DECODER_ERROR_UNREACHABLE;
+    return decode_host_packed(c, n, in_bytes, in_off, out_bytes, out_off, out_len, codes, nullptr, 1u);
+  } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
+}
+
+int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in, const size_t* in_size, uint8_t* const* out, size_t* out_size,
+                              BrotliDecoderResult* results, BrotliDecoderErrorCode* codes) {
+  try {
+    if (n == 0) return 0;
+    if (!in || !in_size || !out || !out_size || !results) { set_error("brotli_b200: null batch array"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+    DeviceCtx* c = acquire_ctx();
+    if (!c) return BROTLI_DECODER_ERROR_UNREACHABLE;
+    // pack the scattered streams into one blob (8-byte aligned slots), decode, scatter back
+    std::vector<uint64_t> in_off(n + 1), out_off(n + 1), out_len(n);
+    std::vector<int32_t> cds(n);
+    uint64_t ia = 0, oa = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (!valid_slice(in[i], in_size[i], 1) || !valid_slice(out[i], out_size[i], 1)) { set_error("brotli_b200: invalid stream pointer"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+      in_off[i] = ia; out_off[i] = oa; ia += in_size[i]; oa += out_size[i];
+    }
+    in_off[n] = ia; out_off[n] = oa;
+    std::vector<uint8_t> in_blob(ia + 1), out_blob(oa + 1);
+    for (size_t i = 0; i < n; i++) if (in_size[i]) memcpy(in_blob.data() + in_off[i], in[i], in_size[i]);
+    int rc = decode_host_packed(c, n, in_blob.data(), in_off.data(), out_blob.data(), out_off.data(), out_len.data(), cds.data(), nullptr, 1u);
+    if (rc != 0) return rc;
+    for (size_t i = 0; i < n; i++) {
+      if (out_len[i]) memcpy(out[i], out_blob.data() + out_off[i], out_len[i]);
+      out_size[i] = (size_t)out_len[i];
+      results[i] = cds[i] == 1 ? BROTLI_DECODER_RESULT_SUCCESS : BROTLI_DECODER_RESULT_ERROR;
+      if (codes) codes[i] = (BrotliDecoderErrorCode)cds[i];
+    }
+    return 0;
+  } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
+}
+
+int BrotliB200ChecksumBatchDevice(size_t n, const uint8_t* d_bytes, const uint64_t* d_off, const uint64_t* d_len, uint64_t* d_sums,
+                                  void* cuda_stream) {
+  if (n == 0) return 0;
+  if (n > 0xFFFFFFF0ull || !d_off || !d_len || !d_sums) { set_error("brotli_b200: bad checksum arguments"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+  if (!acquire_ctx()) return BROTLI_DECODER_ERROR_UNREACHABLE;
+  CU_TRY(brotli_b200::launch_checksum_batch((uint32_t)n, d_bytes, d_off, d_len, d_sums, (cudaStream_t)cuda_stream));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+uint64_t BrotliB200KernelLaunchCount(void) { return g_launches.load(); }
+double BrotliB200LastKernelMs(void) { return g_last_kernel_ms.load(); }
+const char* BrotliB200LastError(void) { return tl_error.c_str(); }
+
+int BrotliB200ResidentWarps(void) {
+  DeviceCtx* c = acquire_ctx();
+  return c ? c->ctas * brotli_b200::kWarpsPerCta : -1;
+}
+
+void BrotliB200Shutdown(void) {
+  for (int d = 0; d < kMaxDevices; d++) {
+    DeviceCtx* c = &g_ctx[d];
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!c->ready) continue;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    cudaFree(c->arena); cudaFree(c->dictionary); cudaFree(c->ticket);
+    c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
+    cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
+    cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); cudaEventDestroy(c->ev_arena); c->arena_busy = false;
+    c->ready = false;
+    cudaSetDevice(prev);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// brotli_b200_kernels.cu -- sm_100a kernels of the batched Brotli decoder and their launchers.
+//
+//   brotli_decode_batch_kernel   persistent warps; each warp pulls stream indices from an atomic
+//                                ticket and decodes one stream at a time (brotli_decode_core.cuh)
+//   brotli_checksum_batch_kernel per-stream 64-bit checksum of decoded regions (parity at scale)
+//
+// Host code reaches these only through the launch_* functions declared in brotli_b200_runtime.h.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "brotli_decode_core.cuh"
+#include "brotli_b200_runtime.h"
+
+namespace brotli_b200 {
+
+__global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_batch_kernel(BatchArgs a) {
+  __shared__ uint2 s_cmd_lut[704];
+  __shared__ __align__(16) uint8_t s_ctx_lut[2048];
+  __shared__ WarpScratch s_ws[kWarpsPerCta];
+  for (uint32_t i = threadIdx.x; i < 704; i += blockDim.x) s_cmd_lut[i] = pack_cmd_lut(i);
+  for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_ctx_lut[i] = tbl::kBrotliContextLookup[i];
+  __syncthreads();
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+
+  Decoder d;
+  d.arena = a.arena + gwarp * ArenaLayout::kBytes;
+  d.tables = (uint16_t*)(d.arena + ArenaLayout::kTables);
+  d.ws = &s_ws[warp];
+  d.luts.cmd_lut = s_cmd_lut;
+  d.luts.ctx_lut = s_ctx_lut;
+  d.luts.dictionary = a.dictionary;
+
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.n) break;
+    const uint32_t i = a.order ? a.order[t] : t;
+    const uint64_t in0 = a.in_off[i], in1 = a.in_off[i + 1];
+    const uint64_t out0 = a.out_off[i], out1 = a.out_off[i + 1];
+    uint64_t decoded = 0, used = 0;
+    const int code = decode_stream(d, a.in + in0, in1 - in0, a.out + out0, out1 - out0, a.large_window, &decoded, &used);
+    if (lane == 0) {
+      a.out_len[i] = decoded;
+      a.codes[i] = code;
+      if (a.in_used) a.in_used[i] = used;
+    }
+  }
+}
+
+// Order-independent 64-bit sum of position-keyed byte hashes, one warp per stream: byte j
+// contributes mix((b + 1) * (K1 + 2j)) * K2, so any changed, moved or missing byte shows.
+// tests/ and bench.py recompute it with numpy over the oracle's output.
+__global__ void brotli_checksum_batch_kernel(uint32_t n, const uint8_t* bytes, const uint64_t* off, const uint64_t* len,
+                                             uint64_t* sums) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = gwarp; i < n; i += nwarps) {
+    const uint8_t* p = bytes + off[i];
+    const uint64_t L = len[i];
+    uint64_t acc = 0;
+    for (uint64_t j = lane; j < L; j += 32) {
+      uint64_t x = (uint64_t)p[j] + 1u;
+      x *= 0x9E3779B97F4A7C15ull + 2 * j;  // position-dependent odd multiplier
+      x ^= x >> 29;
+      acc += x * 0xBF58476D1CE4E5B9ull;
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) sums[i] = acc ^ (L * 0x94D049BB133111EBull);
+  }
+}
+
+size_t arena_bytes_per_warp() { return ArenaLayout::kBytes; }
+
+int query_resident_ctas(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brotli_decode_batch_kernel, kThreadsPerCta, 0) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * sms;
+}
+
+cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_checksum_batch(uint32_t n, const uint8_t* bytes, const uint64_t* off, const uint64_t* len, uint64_t* sums,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  uint32_t blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  brotli_checksum_batch_kernel<<<blocks, 256, 0, stream>>>(n, bytes, off, len, sums);
+  return cudaGetLastError();
+}
+
+}  // namespace brotli_b200

@@ -1002,7 +1002,7 @@ BD_DEV int copy_uncompressed(Decoder& d) {
 // success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity, fatal -> only
 // what the ring buffer had flushed (multiples of its size).
 BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint32_t allow_large_window,
-                         uint64_t* decoded_size) {
+                         uint64_t* decoded_size, uint64_t* in_used) {
   BitReader& br = d.br;
   br.init(in, in_size);
   d.out = out;
@@ -1038,11 +1038,11 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
     for (;;) {  // metablocks
       // DecodeMetaBlockLength, src/decode.rs:243-372
       const uint32_t is_last = br.read<false>(1);
-      uint32_t is_uncompressed = 0, is_metadata = 0, empty_last = 0;
+      uint32_t is_uncompressed = 0, is_metadata = 0;
       d.mlen = 0;
       result = kSuccess;
       if (is_last && br.read<false>(1)) {
-        empty_last = 1;
+        // ISLASTEMPTY: nothing else in this metablock
       } else {
         const uint32_t nib = br.read<false>(2);
         if (nib == 3) {
@@ -1102,7 +1102,6 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
         }
       }
       // BROTLI_STATE_METABLOCK_DONE, src/decode.rs:3345-3381
-      (void)empty_last;
       if (d.mlen < 0) { result = kErrBlockLength2; break; }
       if (!is_last) continue;
       if (!br.jump_to_byte_boundary()) { result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break; }
@@ -1117,6 +1116,9 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   if (result == kNeedsMoreInput && d.rb_allocated && d.mlen < 0) result = kErrBlockLength1;
   if (result == kSuccess || result == kNeedsMoreInput || result == kNeedsMoreOutput) *decoded_size = d.pos;
   else *decoded_size = d.flushed;
+  // input bytes consumed (whole bytes; on success the reference un-reads its look-ahead, src/decode.rs:3374-3376)
+  uint64_t used = ((br.bitpos() + 7) >> 3) - br.lead;
+  *in_used = used < in_size ? used : in_size;
   return result;
 }
 

@@ -1,0 +1,50 @@
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product's Python binding (rust-brotli-decompressor_b200/__init__.py)."""
+    return importlib.import_module("rust-brotli-decompressor_b200")
+
+
+@pytest.fixture(scope="session")
+def corpus():
+    return importlib.import_module("rust-brotli-decompressor_b200.corpus")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import helpers
+    return helpers.Oracle()
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    import helpers
+    return helpers.HostSim()
+
+
+@pytest.fixture(scope="session")
+def gpu_lib(pkg):
+    """libbrotli_b200.so on a machine with a GPU; GPU tests must never silently run anything else."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    L = pkg.lib()
+    assert L.BrotliB200ResidentWarps() > 0, L.BrotliB200LastError()
+    return L

@@ -1,0 +1,126 @@
+"""Shared test plumbing: ctypes bindings of the CPU oracle (oracle/liboracle.so) and of the
+host-simulation build of the kernel logic (tests/hostsim), plus stream mutation helpers.
+Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("%s failed:\n%s" % (" ".join(cmd), r.stdout))
+
+
+class OracleReturnInfo(ctypes.Structure):
+    _fields_ = [("decoded_size", ctypes.c_size_t), ("error", ctypes.c_char * 256), ("result", ctypes.c_int), ("error_code", ctypes.c_int)]
+
+
+class OracleHuffmanCode(ctypes.Structure):
+    _fields_ = [("value", ctypes.c_uint16), ("bits", ctypes.c_uint8)]
+
+
+class OracleBitReader(ctypes.Structure):
+    _fields_ = [("val_", ctypes.c_uint64), ("bit_pos_", ctypes.c_uint32), ("next_in", ctypes.c_uint32), ("avail_in", ctypes.c_uint32)]
+
+
+class Oracle:
+    """oracle/liboracle.so: CPU restatement of the reference decoder (the parity checker)."""
+
+    def __init__(self):
+        _run(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        L.oracle_brotli_decode.restype = OracleReturnInfo
+        L.oracle_brotli_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.oracle_brotli_decode_ex.restype = OracleReturnInfo
+        L.oracle_brotli_decode_ex.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                              ctypes.c_char_p, ctypes.c_size_t]
+        L.oracle_brotli_decode_batch.restype = ctypes.c_int
+        L.oracle_brotli_decode_batch.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
+        L.oracle_error_string.restype = ctypes.c_char_p
+        L.oracle_error_string.argtypes = [ctypes.c_int]
+        self.lib = L
+
+    def decode(self, data, capacity, large_window=True, custom_dict=None):
+        data = bytes(data)
+        buf = ctypes.create_string_buffer(max(int(capacity), 1))
+        if custom_dict is None and large_window:
+            r = self.lib.oracle_brotli_decode(data, len(data), buf, int(capacity))
+        else:
+            cd = bytes(custom_dict) if custom_dict else None
+            r = self.lib.oracle_brotli_decode_ex(data, len(data), buf, int(capacity), 1 if large_window else 0, cd, len(cd) if cd else 0)
+        return r.result, r.error_code, buf.raw[:r.decoded_size]
+
+    def decode_batch(self, in_bytes, in_off, out_bytes, out_off, out_len, codes, threads=1):
+        n = len(out_len)
+        return self.lib.oracle_brotli_decode_batch(n, in_bytes.ctypes.data, in_off.ctypes.data, out_bytes.ctypes.data, out_off.ctypes.data,
+                                                   out_len.ctypes.data, codes.ctypes.data, int(threads))
+
+
+class HostSim:
+    """tests/hostsim: csrc/brotli_decode_core.cuh compiled for the host with warp width 1."""
+
+    def __init__(self):
+        d = os.path.join(ROOT, "tests", "hostsim")
+        so = os.path.join(d, "libhostsim.so")
+        srcs = [os.path.join(d, "hostsim.cpp"), os.path.join(ROOT, "rust-brotli-decompressor_b200", "csrc", "brotli_decode_core.cuh"),
+                os.path.join(ROOT, "tables", "brotli_tables.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            _run(["g++", "-O2", "-g", "-shared", "-fPIC", "-o", so, srcs[0], os.path.join(ROOT, "tables", "brotli_dictionary.c"),
+                  '-DBROTLI_DICT_PATH="%s"' % os.path.join(ROOT, "tables", "brotli_dictionary.bin")])
+        L = ctypes.CDLL(so)
+        L.hostsim_decode.restype = ctypes.c_int
+        L.hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_uint64)]
+        self.lib = L
+
+    def decode(self, data, capacity, large_window=True):
+        """-> (code, bytes): code is the BrotliDecoderErrorCode, bytes the reference's decoded_size prefix."""
+        data = bytes(data)
+        buf = ctypes.create_string_buffer(max(int(capacity), 1))
+        n = ctypes.c_uint64(0)
+        code = self.lib.hostsim_decode(data, len(data), buf, int(capacity), 1 if large_window else 0, ctypes.byref(n))
+        return code, buf.raw[:n.value]
+
+
+def result_of(code):
+    """BrotliDecoderErrorCode -> BrotliResult (src/decode.rs:33-40)."""
+    return code if code in (1, 2, 3) else 0
+
+
+def mutations(stream, rng, count):
+    """Truncations and bit/byte corruptions of a valid stream (deterministic for a seeded rng)."""
+    out = []
+    s = bytes(stream)
+    for _ in range(count):
+        kind = int(rng.integers(0, 4))
+        if kind == 0 and len(s) > 1:
+            out.append(s[: int(rng.integers(0, len(s)))])
+        elif kind == 1:
+            b = bytearray(s); i = int(rng.integers(0, len(b))); b[i] ^= 1 << int(rng.integers(0, 8)); out.append(bytes(b))
+        elif kind == 2:
+            b = bytearray(s); i = int(rng.integers(0, len(b))); b[i] = int(rng.integers(0, 256)); out.append(bytes(b))
+        else:
+            b = bytearray(s)
+            for _ in range(3):
+                i = int(rng.integers(0, len(b))); b[i] ^= int(rng.integers(1, 256))
+            out.append(bytes(b))
+    return out
+
+
+def golden_manifest():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+
+
+def golden_fixture(name):
+    return open(os.path.join(ROOT, "tests", "golden", "fixtures", name), "rb").read()
+
+
+def inline_vectors():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "inline_vectors.json")))

@@ -26,5 +26,6 @@ extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, s
   d.luts.cmd_lut = cmd_lut.data();
   d.luts.ctx_lut = tbl::kBrotliContextLookup;
   d.luts.dictionary = kBrotliDictionaryData;
-  return decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded);
+  uint64_t used = 0;
+  return decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used);
 }

@@ -1,0 +1,220 @@
+"""Parity tests proper: the CUDA path, called through the C ABI of libbrotli_b200.so, against the
+CPU oracle on the same inputs -- bit-exact bytes, same decoded_size, same BrotliDecoderErrorCode.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+MAN = helpers.golden_manifest()
+SMALL = [n for n, e in MAN.items() if "original_sha256" in e]
+
+
+def oracle_batch(oracle, streams, caps):
+    return [oracle.decode(s, c) for s, c in zip(streams, caps)]
+
+
+def check_batch(pkg, oracle, streams, caps, roomy=True):
+    """Decode the batch on the GPU (scattered host API) and compare every stream with the oracle."""
+    got = pkg.decompress_batch(streams, caps)
+    n_ok = 0
+    for i, ((gres, gcode, gout), s, c) in enumerate(zip(got, streams, caps)):
+        ores, ocode, oout = oracle.decode(s, c)
+        if not roomy and gcode == 3 and ocode not in (1, 3):
+            continue  # corrupt AND too little room: see tests/test_hostsim.py::same
+        assert gcode == ocode, (i, gcode, ocode, len(s), c)
+        assert gres == (1 if ocode == 1 else 0)
+        assert gout == oout, (i, ocode, len(gout), len(oout))
+        n_ok += ocode == 1
+    return n_ok
+
+
+def test_fixtures_one_shot(gpu_lib, pkg, oracle):
+    for name in SMALL:
+        e = MAN[name]
+        info, out = pkg.brotli_decode(helpers.golden_fixture(name), e["original_size"])
+        assert (info.result, info.code) == (1, 1), (name, info.code, info.error)
+        assert len(out) == e["original_size"] and hashlib.sha256(out).hexdigest() == e["original_sha256"], name
+        assert info.error == b"SUCCESS"
+
+
+def test_fixtures_as_one_batch(gpu_lib, pkg, oracle):
+    streams = [helpers.golden_fixture(n) for n in SMALL] + [helpers.golden_fixture("borked.compressed")]
+    caps = [MAN[n]["original_size"] for n in SMALL] + [1 << 16]
+    assert check_batch(pkg, oracle, streams, caps) == len(SMALL)
+
+
+def test_c_one_shot_semantics(gpu_lib, pkg):
+    """BrotliDecoderDecompress: SUCCESS only for a complete decode (src/ffi/mod.rs:279-283)."""
+    data = helpers.golden_fixture("alice29.txt.compressed")
+    size = MAN["alice29.txt.compressed"]["original_size"]
+    r, out = pkg.BrotliDecoderDecompress(data, size)
+    assert r == 1 and len(out) == size
+    r, out = pkg.BrotliDecoderDecompress(data, size - 1)          # too small -> ERROR, decoded_size = written (App. D-3)
+    assert r == 0 and len(out) == size - 1
+    r, out = pkg.BrotliDecoderDecompress(data[:-10], size)        # truncated -> ERROR
+    assert r == 0
+    r, out = pkg.BrotliDecoderDecompress(data + b"trailing", size)  # trailing bytes ignored (App. D-2)
+    assert r == 1 and len(out) == size
+    info, out = pkg.brotli_decode(helpers.golden_fixture("borked.compressed"), 1 << 16)
+    assert info.result == 0 and info.code < 0 and info.error.startswith(b"ERROR_")
+
+
+def test_inline_vectors_and_one_byte_streams(gpu_lib, pkg, oracle):
+    vec = helpers.inline_vectors()
+    streams = [bytes.fromhex(v["input_hex"]) for v in vec["vectors"]] + [bytes([b]) for b in range(256)] + [b""]
+    caps = [1 << 18] * len(vec["vectors"]) + [64] * 257
+    check_batch(pkg, oracle, streams, caps)
+    got = pkg.decompress_batch(streams[len(vec["vectors"]):-1], [64] * 256)
+    assert sorted(b for b in range(256) if got[b][0] == 1) == vec["one_byte_ok"]
+    info, _ = pkg.brotli_decode(bytes.fromhex(vec["vectors"][6]["input_hex"]), 4096)  # c/main.c:55-77
+    assert info.code == -8 and info.error == b"ERROR_FORMAT_CONTEXT_MAP_REPEAT"
+
+
+def test_large_window(gpu_lib, pkg, oracle):
+    e = MAN["rnd_chunk.br"]
+    info, out = pkg.brotli_decode(helpers.golden_fixture("rnd_chunk.br"), e["original_size"])
+    assert (info.result, len(out)) == (1, e["original_size"])
+    _, _, oout = oracle.decode(helpers.golden_fixture("rnd_chunk.br"), e["original_size"])
+    assert out == oout
+
+
+@pytest.mark.parametrize("config,n,size", [("C2", 256, 65536), ("C3", 1024, 4096), ("C5", 264, 65536), ("C4", 6, 3 << 20)])
+def test_config_samples(gpu_lib, pkg, oracle, corpus, config, n, size):
+    """Seeded samples of every BASELINE config, ragged capacities included."""
+    comp, orig, _ = corpus.make_config(config, n, size=size)
+    caps = [len(o) for o in orig]
+    got = pkg.decompress_batch(comp, caps)
+    for (res, code, out), o in zip(got, orig):
+        assert (res, code) == (1, 1) and out == o
+    caps2 = [len(o) + (i % 5) * 7 for i, o in enumerate(orig)]
+    assert check_batch(pkg, oracle, comp, caps2) == n
+
+
+def test_corrupt_truncated_and_small_buffers(gpu_lib, pkg, oracle, corpus):
+    rng = np.random.default_rng(99)
+    comp, orig, _ = corpus.make_config("C5", 66, size=20000)
+    streams, caps = [], []
+    for c, o in zip(comp, orig):
+        for m in helpers.mutations(c, rng, 8):
+            streams.append(m); caps.append(len(o) + 32)
+    n_ok = check_batch(pkg, oracle, streams, caps)
+    assert n_ok < len(streams)
+    small = [max(len(o) - 1 - i % 9, 0) for i, o in enumerate(orig)]
+    check_batch(pkg, oracle, comp, small)                       # valid streams, too little room: NEEDS_MORE_OUTPUT parity
+    check_batch(pkg, oracle, streams, [max(c - 40, 0) for c in caps], roomy=False)
+
+
+def test_empty_and_ragged_batches(gpu_lib, pkg, oracle):
+    assert pkg.decompress_batch([], []) == []
+    x = bytes.fromhex("0b00805803")
+    streams = [b"", x, b"\x06", x[:2], x + b"junk", helpers.golden_fixture("zeros.compressed")]
+    caps = [0, 1, 0, 10, 1, 262144]
+    check_batch(pkg, oracle, streams, caps)
+
+
+def test_device_batch_and_checksums(gpu_lib, pkg, oracle, corpus):
+    """Device-resident packed API (the path bench.py times) + the on-device checksum used at full size."""
+    import torch
+    comp, orig, _ = corpus.make_config("C2", 512, size=65536)
+    reps = 8
+    blobs = comp * reps
+    in_bytes, in_off = corpus.pack(blobs)
+    out_off = np.arange(len(blobs) + 1, dtype=np.uint64) * np.uint64(65536)
+    d_in = torch.from_numpy(in_bytes.copy()).cuda()
+    d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
+    d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device="cuda")
+    d_out_off = torch.from_numpy(out_off.view(np.int64)).cuda()
+    d_len = torch.zeros(len(blobs), dtype=torch.int64, device="cuda")
+    d_codes = torch.zeros(len(blobs), dtype=torch.int32, device="cuda")
+    d_sums = torch.zeros(len(blobs), dtype=torch.int64, device="cuda")
+    before = pkg.kernel_launch_count()
+    pkg.decompress_batch_device(len(blobs), d_in, d_in_off, d_out, d_out_off, d_len, d_codes)
+    pkg.checksum_batch_device(len(blobs), d_out, d_out_off, d_len, d_sums)
+    torch.cuda.synchronize()
+    assert pkg.kernel_launch_count() == before + 2
+    assert bool((d_codes == 1).all()) and bool((d_len == 65536).all())
+    out = d_out.cpu().numpy()
+    assert out.tobytes() == b"".join(orig) * reps
+    want = np.array([pkg.checksum_reference(o) for o in orig] * reps, dtype=np.uint64)
+    assert np.array_equal(d_sums.cpu().numpy().view(np.uint64), want)
+
+
+def test_host_packed_batch_pipeline(gpu_lib, pkg, corpus):
+    """Host packed API with enough data to span several pipeline chunks."""
+    comp, orig, _ = corpus.make_config("C2", 256, size=65536)
+    reps = 40  # 10240 streams, 640 MiB of output
+    blobs = comp * reps
+    in_bytes, in_off = corpus.pack(blobs)
+    out_off = np.arange(len(blobs) + 1, dtype=np.uint64) * np.uint64(65536)
+    out = np.zeros(int(out_off[-1]), dtype=np.uint8)
+    out_len = np.zeros(len(blobs), dtype=np.uint64)
+    codes = np.zeros(len(blobs), dtype=np.int32)
+    pkg.decompress_batch_packed(in_bytes, in_off, out, out_off, out_len, codes)
+    assert (codes == 1).all() and (out_len == 65536).all()
+    ref = np.frombuffer(b"".join(orig), dtype=np.uint8)
+    assert np.array_equal(out.reshape(reps, -1), np.broadcast_to(ref, (reps, len(ref))))
+
+
+def test_streaming_api_buffer_matrix(gpu_lib, pkg):
+    """BrotliDecoderDecompressStream with the reference's buffer-size pairs
+    (src/bin/integration_tests.rs:439-463: (65536,65536), (1,65536)-like small chunks, ...)."""
+    for name, pairs in (("alice29.txt.compressed", [(65536, 65536), (4093, 70001), (50096, 1000)]),
+                        ("quickfox_repeated.compressed", [(1, 65536), (3, 3000), (58, 1)]),
+                        ("ukkonooa.compressed", [(1, 1), (3, 3), (1024, 1024)])):
+        data = helpers.golden_fixture(name)
+        e = MAN[name]
+        for in_chunk, out_chunk in pairs:
+            if name.startswith("quickfox_repeated") and out_chunk == 1:
+                out_chunk = 4096
+            st = pkg.DecoderState()
+            got, pos, r = [], 0, 2
+            for _ in range(10000000):
+                chunk = data[pos:pos + in_chunk]
+                r, used, out = st.decompress_stream(chunk, out_chunk)
+                pos += used
+                got.append(out)
+                if r == 1 or r == 0:
+                    break
+                if r == 2:
+                    assert pos < len(data), "decoder wants input past the end"
+            assert r == 1 and st.is_finished() and st.is_used()
+            assert hashlib.sha256(b"".join(got)).hexdigest() == e["original_sha256"], (name, in_chunk, out_chunk)
+            st.close()
+
+
+def test_streaming_errors_and_trailing_bytes(gpu_lib, pkg):
+    st = pkg.DecoderState()
+    bad = bytes.fromhex(helpers.inline_vectors()["vectors"][6]["input_hex"])
+    r, used, out = st.decompress_stream(bad, 0)  # c/main.c:55-77
+    assert r == 0 and st.error_code() == -8 and st.error_string() == "ERROR_FORMAT_CONTEXT_MAP_REPEAT"
+    st.close()
+    st = pkg.DecoderState()
+    r, used, out = st.decompress_stream(bytes.fromhex("1f0700f827fe43840000"), 64)  # src/bin/ffi_stream_tests.rs:77
+    assert r == 1 and out == b"\xff" * 8 and used == 9  # the 10th byte is not part of the stream
+    st.close()
+    st = pkg.DecoderState()  # large window needs the parameter on a streaming instance (src/ffi/mod.rs:127)
+    r, used, out = st.decompress_stream(helpers.golden_fixture("rnd_chunk.br"), 4096)
+    assert r == 0 and st.error_code() == -13
+    st.close()
+
+
+def test_decompressor_reader(gpu_lib, pkg):
+    """Decompressor<R>::read (src/reader.rs:299-350) incl. the trailing-garbage rule (:353-389)."""
+    name = "asyoulik.txt.compressed"
+    d = pkg.Decompressor(io.BytesIO(helpers.golden_fixture(name)), 4096)
+    out = d.read()
+    assert hashlib.sha256(out).hexdigest() == MAN[name]["original_sha256"]
+    assert d.read(10) == b""
+    d = pkg.Decompressor(io.BytesIO(bytes.fromhex("8f028068656c6c6f0a03") + b"trailing garbage"), 4096)
+    assert d.read(100) == b"hello\n"
+    with pytest.raises(ValueError):
+        d.read(100)
+    d = pkg.Decompressor(io.BytesIO(helpers.golden_fixture(name)[:1000]), 256)
+    with pytest.raises(ValueError):
+        d.read()
