@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=4096, help="unique compressed streams (tiled into distinct copies)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-seconds budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -361,7 +362,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
         }
-        line["cpu_baseline"] = cpu_baseline(args, corpus, comp[:min(n_unique, 2048)], orig[:min(n_unique, 2048)]) if world == 1 else None
+        line["cpu_baseline"] = cpu_baseline(args, corpus, comp[:min(n_unique, 2048)], orig[:min(n_unique, 2048)]) if world == 1 and not args.no_cpu else None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

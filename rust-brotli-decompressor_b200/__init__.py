@@ -16,7 +16,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrotli_b200.so")
+# BROTLI_B200_LIB selects another build of the same library (tuning experiments: warps per CTA etc.)
+LIB_PATH = os.environ.get("BROTLI_B200_LIB") or os.path.join(_HERE, "libbrotli_b200.so")
 
 RESULT_ERROR, RESULT_SUCCESS, RESULT_NEEDS_MORE_INPUT, RESULT_NEEDS_MORE_OUTPUT = 0, 1, 2, 3
 

@@ -13,10 +13,16 @@
 
 namespace brotli_b200 {
 
+// Shared memory of one CTA: the two read-only LUTs (static) + one WarpShared region with its table
+// storage per warp (dynamic, kWarpSharedBytes each).
+static_assert(sizeof(WarpShared) % 8 == 0, "table storage must stay 8-byte aligned");
+static_assert(kWarpSharedBytes > sizeof(WarpShared) + 2 * 2048, "per-warp region too small for any table");
+constexpr uint32_t kSharedTableEntries = (kWarpSharedBytes - sizeof(WarpShared)) / 2;
+
 __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_batch_kernel(BatchArgs a) {
   __shared__ uint2 s_cmd_lut[704];
   __shared__ __align__(16) uint8_t s_ctx_lut[2048];
-  __shared__ WarpScratch s_ws[kWarpsPerCta];
+  extern __shared__ __align__(16) uint8_t s_dyn[];
   for (uint32_t i = threadIdx.x; i < 704; i += blockDim.x) s_cmd_lut[i] = pack_cmd_lut(i);
   for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_ctx_lut[i] = tbl::kBrotliContextLookup[i];
   __syncthreads();
@@ -28,7 +34,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
   Decoder d;
   d.arena = a.arena + gwarp * ArenaLayout::kBytes;
   d.tables = (uint16_t*)(d.arena + ArenaLayout::kTables);
-  d.ws = &s_ws[warp];
+  d.sh = (WarpShared*)(s_dyn + (size_t)warp * kWarpSharedBytes);
+  d.ws = &d.sh->ws;
+  d.stab = (uint16_t*)(d.sh + 1);
+  d.stab_cap = kSharedTableEntries;
+  d.stab_used = 0;
   d.luts.cmd_lut = s_cmd_lut;
   d.luts.ctx_lut = s_ctx_lut;
   d.luts.dictionary = a.dictionary;
@@ -78,7 +88,8 @@ size_t arena_bytes_per_warp() { return ArenaLayout::kBytes; }
 
 int query_resident_ctas(int device) {
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brotli_decode_batch_kernel, kThreadsPerCta, 0) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(brotli_decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynamicSharedBytes) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brotli_decode_batch_kernel, kThreadsPerCta, kDynamicSharedBytes) != cudaSuccess) return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   if (per_sm < 1) per_sm = 1;
   return per_sm * sms;
@@ -87,7 +98,7 @@ int query_resident_ctas(int device) {
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
-  brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, 0, stream>>>(a);
+  brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, kDynamicSharedBytes, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -8,9 +8,20 @@
 
 namespace brotli_b200 {
 
-constexpr int kWarpsPerCta = 4;
+// One persistent CTA per SM; each warp owns kWarpSharedBytes of shared memory (scratch + promoted
+// prefix-code tables).  24 warps x 9 KiB + the two LUTs fill the 227 KB an sm_100 CTA may use, and
+// 768 threads leave 80 registers per thread for the command loop.
+#ifndef BROTLI_B200_WARPS_PER_CTA
+#define BROTLI_B200_WARPS_PER_CTA 24
+#endif
+#ifndef BROTLI_B200_WARP_SHARED_BYTES
+#define BROTLI_B200_WARP_SHARED_BYTES 9216
+#endif
+constexpr int kWarpsPerCta = BROTLI_B200_WARPS_PER_CTA;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-constexpr int kMinCtasPerSm = 8;  // 32 decoding warps per SM
+constexpr int kMinCtasPerSm = 1;
+constexpr uint32_t kWarpSharedBytes = BROTLI_B200_WARP_SHARED_BYTES;
+constexpr uint32_t kDynamicSharedBytes = kWarpsPerCta * kWarpSharedBytes;
 
 // One launch decodes streams [0, n) of a packed batch (see decode.h, "Packed layout").
 struct BatchArgs {

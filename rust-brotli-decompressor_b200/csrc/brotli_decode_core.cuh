@@ -30,6 +30,7 @@
 #if defined(BROTLI_B200_HOSTSIM)
 #include <string.h>
 #define BD_DEV inline
+#define BD_COLD static
 #define BD_CONST_TABLE static const
 struct uint2 { uint32_t x, y; };
 namespace brotli_b200 {
@@ -50,10 +51,19 @@ static inline uint32_t brev(uint32_t v) {
 }
 static inline uint32_t ldg32(const uint32_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint8_t ldg8(const uint8_t* p) { return *p; }
+// "shared memory" references are plain addresses on the host
+typedef uintptr_t sref_t;
+static inline sref_t to_sref(const void* p) { return (sref_t)p; }
+static inline uint32_t lds8(sref_t a) { return *(const uint8_t*)a; }
+static inline uint32_t lds16(sref_t a) { return *(const uint16_t*)a; }
+static inline uint32_t lds32(sref_t a) { return *(const uint32_t*)a; }
+static inline uint2 lds64(sref_t a) { return *(const uint2*)a; }
+static inline sref_t lds_ref(sref_t a) { return *(const sref_t*)a; }
 }  // namespace hw
 }  // namespace brotli_b200
 #else
 #define BD_DEV __device__ __forceinline__
+#define BD_COLD __device__ __noinline__  /* per-metablock / per-stream code: kept out of the command loop's register budget */
 #define BD_CONST_TABLE __device__ const
 namespace brotli_b200 {
 namespace hw {
@@ -65,6 +75,16 @@ BD_DEV uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return __f
 BD_DEV uint32_t brev(uint32_t v) { return __brev(v); }
 BD_DEV uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 BD_DEV uint8_t ldg8(const uint8_t* p) { return __ldg(p); }
+// 32-bit shared-state-space addresses: ld.shared with 32-bit address arithmetic instead of generic
+// 64-bit loads.  The asm statements are not volatile so the compiler may schedule them freely; every
+// address data-depends on bits read after the tables were written.
+typedef uint32_t sref_t;
+BD_DEV sref_t to_sref(const void* p) { return (sref_t)__cvta_generic_to_shared(p); }
+BD_DEV uint32_t lds8(sref_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint32_t lds16(sref_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint32_t lds32(sref_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint2 lds64(sref_t a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+BD_DEV sref_t lds_ref(sref_t a) { return lds32(a); }
 }  // namespace hw
 }  // namespace brotli_b200
 #endif
@@ -117,7 +137,10 @@ struct ArenaLayout {
   static constexpr size_t kBlockTypeTrees = kTreeOffDist + 1024;        // u16[3][632]
   static constexpr size_t kBlockLenTrees = kBlockTypeTrees + 2 * 3 * kMaxBlockTypeTable;  // u16[3][396]
   static constexpr size_t kCtxMapTree = kBlockLenTrees + 2 * 3 * kMaxBlockLenTable;       // u16[646]
-  static constexpr size_t kTables = (kCtxMapTree + 2 * kMaxCtxMapTable + 63) & ~size_t(63);
+  static constexpr size_t kPtrLit = (kCtxMapTree + 2 * kMaxCtxMapTable + 63) & ~size_t(63);  // const u16*[256]
+  static constexpr size_t kPtrCmd = kPtrLit + 256 * 8;                  // const u16*[256]
+  static constexpr size_t kPtrDist = kPtrCmd + 256 * 8;                 // const u16*[256]
+  static constexpr size_t kTables = (kPtrDist + 256 * 8 + 63) & ~size_t(63);
   static constexpr size_t kTableEntries = 256 * (size_t)(kMaxLitTable + kMaxCmdTable + kMaxDistTable);
   static constexpr size_t kBytes = (kTables + 2 * kTableEntries + 255) & ~size_t(255);
 };
@@ -130,6 +153,28 @@ struct WarpScratch {
   uint8_t cl_cl[18];      // code length code lengths
   uint8_t pad[2];
   uint8_t word[72];       // dictionary word staging (<= 5 + 24 + 8 bytes, + uppercase overrun)
+};
+
+// Per-warp region of shared memory: everything the command loop touches per symbol.  A metablock's
+// prefix-code tables are built in the global arena and then promoted here while they fit (insert&copy
+// and distance tables first -- every command needs them -- then literal tables); what does not fit
+// is decoded straight from the arena through the same generic pointers.
+struct WarpShared {
+  static constexpr uint32_t kLitMapBytes = 256;   // literal context map of <= 4 block types
+  static constexpr uint32_t kDistMapBytes = 64;   // distance context map of <= 16 block types
+  static constexpr uint32_t kLitPtrs = 32, kDistPtrs = 16, kCmdPtrs = 4, kDistLut = 64;
+  WarpScratch ws;
+  uint8_t lit_map[kLitMapBytes];
+  uint8_t dist_map[kDistMapBytes];
+  const uint16_t* lit_ptrs[kLitPtrs];
+  const uint16_t* dist_ptrs[kDistPtrs];
+  const uint16_t* cmd_ptrs[kCmdPtrs];
+  const uint16_t* cur_dist[4];  // distance tables of the current distance block type, by distance context
+  // shared-space mirrors used by process_commands_shared (valid when Decoder::all_shared)
+  hw::sref_t cur_dist_s[4];
+  hw::sref_t lit_s[kLitPtrs];
+  uint32_t dist_lut[kDistLut];  // distance symbol 16 + i -> (distance base << 5) | extra bits, see build_dist_lut
+  // uint16_t tables[] follow (size chosen at launch)
 };
 
 // Read-only lookup data shared by all warps of a CTA (shared memory on the GPU).
@@ -281,6 +326,18 @@ struct Decoder {
   uint16_t* tables;
   WarpScratch* ws;
   SharedLuts luts;
+  // shared-memory residency of the current metablock's tables
+  WarpShared* sh;
+  uint16_t* stab;                 // shared table storage
+  uint32_t stab_cap, stab_used;   // in entries
+  const uint8_t* map_lit;         // literal context map: sh->lit_map or the arena copy
+  const uint8_t* map_dist;
+  const uint16_t* const* lit_ptrs;   // tree index -> table
+  const uint16_t* const* cmd_ptrs;
+  const uint16_t* const* dist_ptrs;
+  uint32_t n_unpromoted;          // tables of this metablock left in the global arena
+  uint32_t all_shared;            // every table, map and pointer array of this metablock is in shared memory
+  uint32_t use_dist_lut;          // sh->dist_lut covers the whole distance alphabet
 
   BD_DEV uint8_t* ctx_map_lit() const { return arena + ArenaLayout::kCtxMapLit; }
   BD_DEV uint8_t* ctx_map_dist() const { return arena + ArenaLayout::kCtxMapDist; }
@@ -360,7 +417,7 @@ BD_DEV int build_table(Decoder& d, uint16_t* tab, uint32_t cap_entries, uint32_t
 // ReadHuffmanCode, src/decode.rs:868-1013 (+ :516-556, :565-658, :661-853).  Truncation is
 // detected by the caller through br.overrun(); reads past the end see zero bits, every loop
 // below still terminates and stays inside its arrays.
-BD_DEV int read_huffman_code(Decoder& d, uint32_t alphabet_size, uint32_t max_symbol, uint16_t* tab, uint32_t cap_entries,
+BD_COLD int read_huffman_code(Decoder& d, uint32_t alphabet_size, uint32_t max_symbol, uint16_t* tab, uint32_t cap_entries,
                              uint32_t& table_size) {
   BitReader& br = d.br;
   const uint32_t lane = hw::lane();
@@ -532,17 +589,17 @@ BD_DEV void read_block_switch(Decoder& d, int cat, uint32_t num_types, uint32_t&
 BD_DEV void prepare_literal_decoding(Decoder& d) {
   const uint32_t block_type = d.rbt_l1;
   d.ctx_slice = block_type << 6;
-  const uint8_t* map = d.ctx_map_lit() + d.ctx_slice;
+  const uint8_t* map = d.map_lit + d.ctx_slice;
   const uint32_t sample = map[0];
   bool same = true;
   for (uint32_t j = hw::lane(); j < 64; j += hw::kWarp) same = same && (map[j] == sample);
   d.trivial_ctx = hw::all(same) ? 1u : 0u;
-  d.lit_tree = d.tables + d.tree_off_lit()[sample];
+  d.lit_tree = d.lit_ptrs[sample];
   d.ctx_mode_off = (uint32_t)(d.ctx_modes()[block_type] & 3u) * 512u;
 }
 
 // InverseMoveToFrontTransform, src/decode.rs:1096-1128 (warp-uniform, serial)
-BD_DEV void inverse_move_to_front(Decoder& d, uint8_t* v, uint32_t n) {
+BD_COLD void inverse_move_to_front(Decoder& d, uint8_t* v, uint32_t n) {
   uint8_t* mtf = d.arena + ArenaLayout::kMtf;
   for (uint32_t i = hw::lane(); i < 256; i += hw::kWarp) mtf[i] = (uint8_t)i;
   hw::syncwarp();
@@ -557,7 +614,7 @@ BD_DEV void inverse_move_to_front(Decoder& d, uint8_t* v, uint32_t n) {
 }
 
 // DecodeContextMap, src/decode.rs:1272-1428
-BD_DEV int decode_context_map(Decoder& d, uint32_t map_size, uint8_t* map, uint32_t& num_htrees) {
+BD_COLD int decode_context_map(Decoder& d, uint32_t map_size, uint8_t* map, uint32_t& num_htrees) {
   BitReader& br = d.br;
   const uint32_t lane = hw::lane();
   num_htrees = read_varlen_uint8(br) + 1;
@@ -611,7 +668,7 @@ BD_DEV void warp_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
 }
 
 // Static dictionary word + transform (src/decode.rs:2597-2620, src/transform.rs:720-795) into ws.word.
-BD_DEV uint32_t build_dictionary_word(Decoder& d, uint32_t offset, uint32_t wlen, uint32_t transform_idx) {
+BD_COLD uint32_t build_dictionary_word(Decoder& d, uint32_t offset, uint32_t wlen, uint32_t transform_idx) {
   uint8_t* o = d.ws->word;
   const uint8_t* dict = d.luts.dictionary + offset;
   const uint8_t* prefix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[transform_idx * 3]];
@@ -645,12 +702,26 @@ BD_DEV uint32_t build_dictionary_word(Decoder& d, uint32_t offset, uint32_t wlen
   return idx;
 }
 
+// Distance tables of the current distance block type, indexed by the 2-bit distance context
+// (src/decode.rs:2186-2188: dist_htree_index = dist_context_map[slice + context]).
+BD_DEV void refresh_cur_dist(Decoder& d) {
+  if (hw::lane() < 4 || hw::kWarp == 1) {
+    for (uint32_t c = hw::kWarp == 1 ? 0 : hw::lane(); c < 4; c += hw::kWarp == 1 ? 1 : 4)
+    {
+      const uint16_t* t = d.dist_ptrs[d.map_dist[d.dist_slice + c]];
+      d.sh->cur_dist[c] = t;
+      d.sh->cur_dist_s[c] = hw::to_sref(t);
+    }
+  }
+  hw::syncwarp();
+}
+
 // ======================= distance (src/decode.rs:2017-2131) =======================
 template <bool FAST>
 BD_DEV int32_t read_distance(Decoder& d, uint32_t& push_to_ring) {
   BitReader& br = d.br;
-  const uint32_t tree_idx = d.ctx_map_dist()[d.dist_slice + d.dist_ctx];
-  const uint16_t* tree = d.tables + d.tree_off_dist()[tree_idx];
+  const uint32_t tree_idx = d.map_dist[d.dist_slice + d.dist_ctx];
+  const uint16_t* tree = d.dist_ptrs[tree_idx];
   uint32_t len;
   const uint32_t code = decode_symbol(tree, br.peek(), len);
   br.skip<FAST>(len);
@@ -696,7 +767,7 @@ BD_DEV int flush_event(Decoder& d) {  // WriteRingBuffer at pos >= ringbuffer_si
 }
 
 template <bool SAFE>
-BD_DEV int process_commands(Decoder& d) {
+BD_COLD int process_commands(Decoder& d) {
   BitReader& br = d.br;
   const uint32_t lane = hw::lane();
   constexpr bool FAST = !SAFE;
@@ -706,7 +777,7 @@ BD_DEV int process_commands(Decoder& d) {
       if (d.bl_c == 0) {  // DecodeCommandBlockSwitch, src/decode.rs:1609-1621
         if (d.nbt_c <= 1) return kNeedsMoreInput;  // reference quirk, src/decode.rs:2368-2373 with :1479-1481
         read_block_switch<FAST>(d, 1, d.nbt_c, d.rbt_c0, d.rbt_c1, d.bl_c);
-        d.cmd_tree = d.tables + d.tree_off_cmd()[d.rbt_c1];
+        d.cmd_tree = d.cmd_ptrs[d.rbt_c1];
       }
       // ReadCommandInternal, src/decode.rs:2134-2189
       uint32_t len;
@@ -764,8 +835,8 @@ BD_DEV int process_commands(Decoder& d) {
       if (i != 0) {  // context-dependent literals, src/decode.rs:2463-2551
         hw::syncwarp();
         uint32_t p1 = d.pos >= 1 ? d.out[d.pos - 1] : 0, p2 = d.pos >= 2 ? d.out[d.pos - 2] : 0;
-        const uint8_t* map = d.ctx_map_lit();
-        const uint32_t* toff = d.tree_off_lit();
+        const uint8_t* map = d.map_lit;
+        const uint16_t* const* lit_ptrs = d.lit_ptrs;
         do {
           if (FAST && !br.fast_ok(4)) { d.ins_rem = i; return kNeedSafe; }
           if (d.bl_l == 0) {
@@ -776,7 +847,7 @@ BD_DEV int process_commands(Decoder& d) {
             } else if (SAFE) { d.ins_rem = i; return kNeedsMoreInput; }
           }
           const uint32_t context = d.luts.ctx_lut[d.ctx_mode_off + p1] | d.luts.ctx_lut[d.ctx_mode_off + 256 + p2];
-          const uint16_t* tree = d.tables + toff[map[d.ctx_slice + context]];
+          const uint16_t* tree = lit_ptrs[map[d.ctx_slice + context]];
           uint32_t len;
           const uint32_t lit = decode_symbol(tree, br.peek(), len);
           br.skip<FAST>(len);
@@ -810,6 +881,7 @@ BD_DEV int process_commands(Decoder& d) {
       if (d.bl_d == 0 && d.nbt_d > 1) {  // DecodeDistanceBlockSwitch, src/decode.rs:1643-1658
         read_block_switch<FAST>(d, 2, d.nbt_d, d.rbt_d0, d.rbt_d1, d.bl_d);
         d.dist_slice = d.rbt_d1 << 2;
+        refresh_cur_dist(d);
       } else if (d.bl_d == 0 && SAFE) {
         return kNeedsMoreInput;
       }
@@ -877,6 +949,392 @@ BD_DEV int process_commands(Decoder& d) {
   }
 }
 
+// ======================= command loop, fast path =======================
+// The loop the kernel spends its time in.  All hot state is copied into locals (registers) and
+// written back on exit.  It handles whole commands whose input lies in whole words well inside the
+// stream and whose output stays clear of the capacity and of the emulated flush points; anything
+// else -- block switches, the tail of the stream, the last bytes of the output -- makes it write its
+// state back and return kNeedSafe, and process_commands<true> finishes that command.
+BD_COLD uint32_t emit_dictionary_word(Decoder& d, uint32_t pos, uint32_t word_id, uint32_t copy_len, int& err) {
+  const uint32_t lane = hw::lane();
+  const uint32_t shift = tbl::kBrotliDictSizeBitsByLength[copy_len];
+  const uint32_t word_idx = word_id & ((1u << shift) - 1u);
+  const uint32_t transform_idx = word_id >> shift;
+  if (transform_idx >= 121) { err = kErrTransform; return 0; }
+  const uint32_t offset = tbl::kBrotliDictOffsetsByLength[copy_len] + word_idx * copy_len;
+  uint32_t n;
+  hw::syncwarp();
+  if (transform_idx == 0) {
+    n = copy_len;
+    for (uint32_t i = lane; i < n; i += hw::kWarp) d.out[pos + i] = hw::ldg8(d.luts.dictionary + offset + i);
+  } else {
+    n = build_dictionary_word(d, offset, copy_len, transform_idx);
+    for (uint32_t i = lane; i < n; i += hw::kWarp) d.out[pos + i] = d.ws->word[i];
+  }
+  err = kSuccess;
+  return n;
+}
+
+BD_DEV int process_commands_fast(Decoder& d) {
+  const uint32_t lane = hw::lane();
+  BitReader br = d.br;
+  if (!br.fast_ok(3)) return kNeedSafe;
+  uint8_t* const out = d.out;
+  uint32_t pos = d.pos;
+  int32_t mlen = d.mlen;
+  int32_t d0 = d.d0, d1 = d.d1, d2 = d.d2, d3 = d.d3;
+  uint32_t bl_c = d.bl_c, bl_l = d.bl_l, bl_d = d.bl_d;
+  const uint16_t* const cmd_tree = d.cmd_tree;
+  const uint16_t* const lit_tree = d.lit_tree;
+  const uint32_t trivial_ctx = d.trivial_ctx;
+  const uint2* const cmd_lut = d.luts.cmd_lut;
+  const uint16_t* const* const cur_dist = d.sh->cur_dist;
+  const uint32_t max_backward = d.max_backward;
+  const uint32_t npostfix = d.npostfix, ndirect = d.ndirect;
+  const uint64_t lim64 = d.next_flush < d.cap ? d.next_flush : d.cap;
+  const uint32_t limit = lim64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)lim64;
+  // command in flight (only meaningful when we bail out in the middle of one)
+  uint32_t state = kCmdBegin, ins_rem = 0, copy_len = 0, implicit_dist = 0, dist_ctx = 0;
+  int ret;
+  for (;;) {
+    // ---- insert&copy symbol and its extra bits (ReadCommandInternal, src/decode.rs:2134-2189) ----
+    if (bl_c == 0) { ret = kNeedSafe; break; }
+    uint32_t len;
+    const uint32_t sym = decode_symbol(cmd_tree, br.peek(), len);
+    br.skip<true>(len);
+    const uint2 lut = cmd_lut[sym];
+    const uint32_t ie = (lut.x >> 16) & 0xFF, ce = lut.y >> 16;
+    uint32_t insert_len = lut.x & 0xFFFF;
+    if (ie) insert_len += br.read<true>(ie);
+    copy_len = lut.y & 0xFFFF;
+    if (ce) copy_len += br.read<true>(ce);
+    implicit_dist = (lut.x >> 26) & 1;
+    dist_ctx = (lut.x >> 24) & 3;
+    bl_c--;
+    mlen -= (int32_t)insert_len;
+    ins_rem = insert_len;
+    state = insert_len ? kCmdInner : kCmdPostLiterals;
+    // one guard per command: input words for the literals + distance + the next command's symbol,
+    // output room for the literals and the copy, and no literal block switch inside the run
+    if (br.k + 16u + (insert_len >> 1) > br.end_full || insert_len > bl_l ||
+        (uint64_t)pos + insert_len + (copy_len > 40 ? copy_len : 40) >= limit) { ret = kNeedSafe; break; }
+    // ---- literals (src/decode.rs:2391-2558) ----
+    if (insert_len) {
+      bl_l -= insert_len;
+      if (trivial_ctx) {
+        uint32_t i = 0;
+        do {
+          uint32_t l2;
+          const uint32_t lit = decode_symbol(lit_tree, br.peek(), l2);
+          br.skip<true>(l2);
+          if (lane == 0) out[pos + i] = (uint8_t)lit;
+        } while (++i != insert_len);
+      } else {
+        hw::syncwarp();
+        uint32_t p1 = pos >= 1 ? out[pos - 1] : 0, p2 = pos >= 2 ? out[pos - 2] : 0;
+        const uint8_t* const map = d.map_lit + d.ctx_slice;
+        const uint8_t* const ctx_lut = d.luts.ctx_lut + d.ctx_mode_off;
+        const uint16_t* const* const lit_ptrs = d.lit_ptrs;
+        uint32_t i = 0;
+        do {
+          const uint32_t context = ctx_lut[p1] | ctx_lut[256 + p2];
+          const uint16_t* tree = lit_ptrs[map[context]];
+          uint32_t l2;
+          const uint32_t lit = decode_symbol(tree, br.peek(), l2);
+          br.skip<true>(l2);
+          p2 = p1; p1 = lit;
+          if (lane == 0) out[pos + i] = (uint8_t)lit;
+        } while (++i != insert_len);
+      }
+      pos += insert_len;
+      ins_rem = 0;
+      state = kCmdPostLiterals;
+      if (mlen <= 0) { ret = kMetablockDone; break; }
+    }
+    // ---- distance (src/decode.rs:2066-2131) ----
+    int32_t dist = d0;
+    uint32_t push = 0;
+    if (!implicit_dist) {
+      if (bl_d == 0) { ret = kNeedSafe; break; }
+      bl_d--;
+      uint32_t l3;
+      const uint32_t code = decode_symbol(cur_dist[dist_ctx], br.peek(), l3);
+      br.skip<true>(l3);
+      push = 1;
+      if (code >= ndirect) {
+        const uint32_t distval = code - ndirect;
+        const uint32_t postfix = distval & ((1u << npostfix) - 1u);
+        const uint32_t hcode = distval >> npostfix;
+        const uint32_t nbits = (hcode >> 1) + 1;
+        const uint32_t extra = br.read<true>(nbits);
+        const uint32_t offset = ((2u + (hcode & 1u)) << nbits) - 4u;
+        dist = (int32_t)(((offset + extra) << npostfix) + postfix + ndirect - 15u);
+      } else if (code >= 16) {
+        dist = (int32_t)(code - 15u);
+      } else if (code == 0) {
+        push = 0;
+      } else if (code < 4) {
+        dist = code == 1 ? d1 : (code == 2 ? d2 : d3);
+      } else {  // last / second-to-last distance -3..+3, src/decode.rs:2017-2049
+        const uint32_t c = code - 4;
+        const int32_t base = c < 6 ? d0 : d1;
+        const uint32_t m = c < 6 ? c : c - 6;
+        const int32_t delta = (int32_t)(m >> 1) + 1;
+        dist = (m & 1) ? base + delta : base - delta;
+        if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
+      }
+    }
+    // ---- copy or static dictionary word (src/decode.rs:2583-2689) ----
+    const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+    if (dist > (int32_t)max_distance) {
+      if (dist > 0x7FFFFFFC) { ret = kErrDistance; break; }
+      if (copy_len < 4 || copy_len > 24) { ret = kErrDictionary; break; }
+      int err;
+      const uint32_t n = emit_dictionary_word(d, pos, (uint32_t)dist - max_distance - 1, copy_len, err);
+      if (err != kSuccess) { ret = err; break; }
+      pos += n;
+      mlen -= (int32_t)n;
+    } else {
+      if (dist <= 0) { ret = kErrUnreachable; break; }
+      if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
+      mlen -= (int32_t)copy_len;
+      warp_copy(out, pos, (uint32_t)dist, copy_len);
+      pos += copy_len;
+    }
+    state = kCmdBegin;
+    if (mlen <= 0) { ret = kMetablockDone; break; }
+  }
+  d.br = br;
+  d.pos = pos; d.mlen = mlen;
+  d.d0 = d0; d.d1 = d1; d.d2 = d2; d.d3 = d3;
+  d.bl_c = bl_c; d.bl_l = bl_l; d.bl_d = bl_d;
+  d.state = state; d.ins_rem = ins_rem; d.copy_len = copy_len; d.implicit_dist = implicit_dist; d.dist_ctx = dist_ctx;
+  return ret;
+}
+
+// ======================= command loop, shared-memory path =======================
+// Same contract as process_commands_fast, for metablocks whose tables all live in the warp's shared
+// memory (Decoder::all_shared, the common case): table and LUT reads are ld.shared with 32-bit
+// addresses, the rare second-level lookup is out of line, distance symbols go through dist_lut.
+BD_COLD uint32_t second_level_shared(hw::sref_t tab, uint32_t e, uint32_t bits) {
+  const uint32_t wbits = (e & 15u) - kRootBits;
+  const uint32_t e2 = hw::lds16(tab + (((e >> 4) + ((bits >> kRootBits) & ((1u << wbits) - 1u))) << 1));
+  return e2 + kRootBits;  // symbol << 4 | total length (<= 15)
+}
+
+BD_DEV uint32_t decode_symbol_shared(hw::sref_t tab, uint32_t bits, uint32_t& len) {
+  uint32_t e = hw::lds16(tab + ((bits & 0xFFu) << 1));
+  if ((e & 15u) > kRootBits) e = second_level_shared(tab, e, bits);
+  len = e & 15u;
+  return e >> 4;
+}
+
+#if defined(BROTLI_B200_HOSTSIM)
+#define BD_LIKELY(x) (x)
+#define BD_UNLIKELY(x) (x)
+#else
+#define BD_LIKELY(x) __builtin_expect(!!(x), 1)
+#define BD_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
+
+BD_DEV int process_commands_shared(Decoder& d) {
+  const uint32_t lane = hw::lane();
+  BitReader br = d.br;
+  if (!br.fast_ok(3)) return kNeedSafe;
+  uint8_t* const out = d.out;
+  uint32_t pos = d.pos;
+  int32_t mlen = d.mlen;
+  int32_t d0 = d.d0, d1 = d.d1, d2 = d.d2, d3 = d.d3;
+  uint32_t bl_c = d.bl_c, bl_l = d.bl_l, bl_d = d.bl_d;
+  const hw::sref_t cmd_tree = hw::to_sref(d.cmd_tree);
+  const hw::sref_t lit_tree = hw::to_sref(d.lit_tree);
+  const hw::sref_t cmd_lut = hw::to_sref(d.luts.cmd_lut);
+  const hw::sref_t cur_dist = hw::to_sref(d.sh->cur_dist_s);
+  const hw::sref_t dist_lut = hw::to_sref(d.sh->dist_lut);
+  const uint32_t trivial_ctx = d.trivial_ctx;
+  const uint32_t use_dist_lut = d.use_dist_lut;
+  const uint32_t max_backward = d.max_backward;
+  const uint32_t npostfix = d.npostfix, ndirect = d.ndirect;
+  uint64_t lim64 = d.next_flush < d.cap ? d.next_flush : d.cap;
+  if (lim64 > 0xF0000000ull) lim64 = 0xF0000000ull;  // keeps pos + insert_len + copy_len inside 32 bits
+  const uint32_t limit = (uint32_t)lim64;
+  const uint32_t k_end = br.end_full;
+  uint32_t insert_len = 0, copy_len = 0, cmd_bits = 0;  // cmd_bits: implicit-distance flag (bit 26) and distance context (bits 24-25)
+  // Short backreference copies are split in two: the byte is loaded when the command is decoded and
+  // stored when the NEXT copy (or anything that reads the output) comes up, so the load's round
+  // trip to L2/HBM overlaps the decode of the following command instead of stalling the warp.
+  uint8_t* pend_ptr = out;
+  uint32_t pend_val = 0;
+  bool pend = false;
+#define BD_FLUSH_PENDING() do { if (pend) { *pend_ptr = (uint8_t)pend_val; pend = false; } } while (0)
+  int ret;
+  for (;;) {
+    // ---- insert&copy symbol and its extra bits (ReadCommandInternal, src/decode.rs:2134-2189) ----
+    if (BD_UNLIKELY(bl_c == 0)) goto bail_begin;
+    {
+      uint32_t len;
+      const uint32_t sym = decode_symbol_shared(cmd_tree, br.peek(), len);
+      br.skip<true>(len);
+      const uint2 lut = hw::lds64(cmd_lut + (sym << 3));
+      cmd_bits = lut.x;
+      insert_len = lut.x & 0xFFFF;
+      copy_len = lut.y & 0xFFFF;
+      if (BD_UNLIKELY((lut.x & 0xFF0000u) | (lut.y >> 16))) {
+        if (lut.x & 0xFF0000u) insert_len += br.read<true>((lut.x >> 16) & 0xFF);
+        if (lut.y >> 16) copy_len += br.read<true>(lut.y >> 16);
+      }
+    }
+    bl_c--;
+    mlen -= (int32_t)insert_len;
+    // one guard per command: input words for the literals + distance + the next command's symbol,
+    // output room for the literals and the copy, and no literal block switch inside the run
+    if (BD_UNLIKELY(br.k + 16u + (insert_len >> 1) > k_end || insert_len > bl_l ||
+                    pos + insert_len + (copy_len > 40 ? copy_len : 40) >= limit))
+      goto bail_command;
+    // ---- literals (src/decode.rs:2391-2558) ----
+    if (insert_len) {
+      bl_l -= insert_len;
+      if (BD_LIKELY(trivial_ctx)) {
+        uint32_t i = 0;
+#pragma unroll 1
+        do {
+          uint32_t l2;
+          const uint32_t lit = decode_symbol_shared(lit_tree, br.peek(), l2);
+          br.skip<true>(l2);
+          if (lane == 0) out[pos + i] = (uint8_t)lit;
+        } while (++i != insert_len);
+      } else {
+        BD_FLUSH_PENDING();
+        hw::syncwarp();
+        uint32_t p1 = pos >= 1 ? out[pos - 1] : 0, p2 = pos >= 2 ? out[pos - 2] : 0;
+        const hw::sref_t map = hw::to_sref(d.map_lit + d.ctx_slice);
+        const hw::sref_t ctx_lut = hw::to_sref(d.luts.ctx_lut + d.ctx_mode_off);
+        const hw::sref_t lit_s = hw::to_sref(d.sh->lit_s);
+        uint32_t i = 0;
+#pragma unroll 1
+        do {
+          const uint32_t context = hw::lds8(ctx_lut + p1) | hw::lds8(ctx_lut + 256 + p2);
+          const hw::sref_t tree = hw::lds_ref(lit_s + hw::lds8(map + context) * (uint32_t)sizeof(hw::sref_t));
+          uint32_t l2;
+          const uint32_t lit = decode_symbol_shared(tree, br.peek(), l2);
+          br.skip<true>(l2);
+          p2 = p1; p1 = lit;
+          if (lane == 0) out[pos + i] = (uint8_t)lit;
+        } while (++i != insert_len);
+      }
+      pos += insert_len;
+      insert_len = 0;
+      if (BD_UNLIKELY(mlen <= 0)) goto done_after_literals;
+    }
+    // ---- distance (src/decode.rs:2066-2131) ----
+    {
+      int32_t dist = d0;
+      uint32_t push = 0;
+      if (!(cmd_bits & (1u << 26))) {
+        if (BD_UNLIKELY(bl_d == 0)) goto bail_command;
+        bl_d--;
+        const hw::sref_t tree = hw::lds_ref(cur_dist + ((cmd_bits >> 24) & 3u) * (uint32_t)sizeof(hw::sref_t));
+        const uint32_t bits = br.peek();
+        uint32_t l3;
+        const uint32_t code = decode_symbol_shared(tree, bits, l3);
+        push = 1;
+        if (code >= 16) {
+          uint32_t base, nbits;
+          if (BD_LIKELY(use_dist_lut)) {
+            const uint32_t e = hw::lds32(dist_lut + ((code - 16u) << 2));
+            nbits = e & 31u; base = e >> 5;
+          } else if (code >= ndirect) {
+            const uint32_t distval = code - ndirect;
+            const uint32_t hcode = distval >> npostfix;
+            nbits = (hcode >> 1) + 1;
+            base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & ((1u << npostfix) - 1u)) + ndirect - 15u;
+          } else {
+            nbits = 0; base = code - 15u;
+          }
+          if (BD_LIKELY(l3 + nbits <= 32)) {  // symbol and extra bits from the one 32-bit peek
+            const uint32_t extra = (bits >> l3) & ((1u << nbits) - 1u);
+            br.skip<true>(l3 + nbits);
+            dist = (int32_t)(base + (extra << npostfix));
+          } else {
+            br.skip<true>(l3);
+            dist = (int32_t)(base + (br.read<true>(nbits) << npostfix));
+          }
+        } else {
+          br.skip<true>(l3);
+          if (code == 0) {
+            push = 0;
+          } else if (code < 4) {
+            dist = code == 1 ? d1 : (code == 2 ? d2 : d3);
+          } else {  // last / second-to-last distance -3..+3, src/decode.rs:2017-2049
+            const uint32_t c = code - 4;
+            const int32_t b = c < 6 ? d0 : d1;
+            const uint32_t m = c < 6 ? c : c - 6;
+            const int32_t delta = (int32_t)(m >> 1) + 1;
+            dist = (m & 1) ? b + delta : b - delta;
+            if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
+          }
+        }
+      }
+      // ---- copy or static dictionary word (src/decode.rs:2583-2689) ----
+      const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+      if (BD_UNLIKELY((uint32_t)dist > max_distance)) {  // also catches dist <= 0 (impossible for symbols < max_symbol)
+        if (dist <= 0) { ret = kErrUnreachable; goto fail; }
+        if (dist > 0x7FFFFFFC) { ret = kErrDistance; goto fail; }
+        if (copy_len < 4 || copy_len > 24) { ret = kErrDictionary; goto fail; }
+        int err;
+        const uint32_t n = emit_dictionary_word(d, pos, (uint32_t)dist - max_distance - 1, copy_len, err);
+        if (err != kSuccess) { ret = err; goto fail; }
+        pos += n;
+        mlen -= (int32_t)n;
+      } else {
+        if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
+        mlen -= (int32_t)copy_len;
+        BD_FLUSH_PENDING();
+        hw::syncwarp();  // literal and copy stores issued so far are visible to the loads below
+        if (BD_LIKELY(copy_len <= hw::kWarp && (uint32_t)dist >= copy_len)) {  // one byte per lane, no overlap
+          if (lane < copy_len) {
+            pend_ptr = out + (pos + lane);
+            pend_val = *(pend_ptr - (uint32_t)dist);
+            pend = true;
+          }
+        } else {
+          warp_copy(out, pos, (uint32_t)dist, copy_len);
+        }
+        pos += copy_len;
+      }
+    }
+    if (BD_UNLIKELY(mlen <= 0)) goto done_after_copy;
+  }
+bail_begin:  // before reading a command
+  d.state = kCmdBegin; d.ins_rem = 0;
+  ret = kNeedSafe;
+  goto writeback;
+bail_command:  // command read; literals (if any) and the distance are still to come
+  d.state = insert_len ? kCmdInner : kCmdPostLiterals; d.ins_rem = insert_len;
+  ret = kNeedSafe;
+  goto writeback;
+done_after_literals:
+  d.state = kCmdPostLiterals; d.ins_rem = 0;
+  ret = kMetablockDone;
+  goto writeback;
+done_after_copy:
+  d.state = kCmdBegin; d.ins_rem = 0;
+  ret = kMetablockDone;
+  goto writeback;
+fail:
+  d.state = kCmdPostLiterals; d.ins_rem = 0;
+writeback:
+  BD_FLUSH_PENDING();
+  hw::syncwarp();
+#undef BD_FLUSH_PENDING
+  d.br = br;
+  d.pos = pos; d.mlen = mlen;
+  d.d0 = d0; d.d1 = d1; d.d2 = d2; d.d3 = d3;
+  d.bl_c = bl_c; d.bl_l = bl_l; d.bl_d = bl_d;
+  d.copy_len = copy_len; d.implicit_dist = (cmd_bits >> 26) & 1; d.dist_ctx = (cmd_bits >> 24) & 3;
+  return ret;
+}
+
 // ======================= metablock header (src/decode.rs:243-372, :3046-3288) =======================
 BD_DEV int read_block_split_header(Decoder& d, int cat, uint32_t& num_types, uint32_t& block_length) {
   num_types = read_varlen_uint8(d.br) + 1;
@@ -901,21 +1359,61 @@ BD_DEV uint32_t max_distance_symbol(uint32_t ndirect, uint32_t npostfix) {
   return bound + diff + postfix;
 }
 
-BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint32_t max_symbol, uint32_t* tree_off, uint32_t& next_off) {
+// Distance symbols >= 16 as a lookup: dist = (lut >> 5) + (extra << NPOSTFIX) with (lut & 31) extra
+// bits -- the closed form of src/decode.rs:2100-2128 tabulated per metablock (NPOSTFIX / NDIRECT are
+// metablock parameters).  Only used when the whole alphabet fits the table and every base fits 27 bits.
+BD_DEV void build_dist_lut(Decoder& d) {
+  bool ok = d.dist_alphabet <= 16 + WarpShared::kDistLut;
+  if (ok) {
+    for (uint32_t i = hw::lane(); i < WarpShared::kDistLut; i += hw::kWarp) {
+      const uint32_t code = 16 + i;
+      uint32_t base = code - 15u, nbits = 0;
+      if (code >= d.ndirect) {
+        const uint32_t distval = code - d.ndirect;
+        const uint32_t postfix = distval & ((1u << d.npostfix) - 1u);
+        const uint32_t hcode = distval >> d.npostfix;
+        nbits = (hcode >> 1) + 1;
+        const uint64_t b = ((uint64_t)(((2u + (hcode & 1u)) << nbits) - 4u) << d.npostfix) + postfix + d.ndirect - 15u;
+        if (code < d.dist_alphabet && (b >> 27) != 0) ok = false;
+        base = (uint32_t)b;
+      }
+      d.sh->dist_lut[i] = (base << 5) | (nbits & 31u);
+    }
+  }
+  d.use_dist_lut = hw::all(ok) ? 1u : 0u;
+}
+
+// HuffmanTreeGroupDecode, src/decode.rs:1130-1219.  Each table is built in the global arena; while
+// it fits (keeping `reserve` entries free for the groups that follow) it is then copied into the
+// warp's shared-memory table storage and ptrs[i] points there instead.
+BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint32_t max_symbol, uint32_t* tree_off, uint32_t& next_off,
+                           const uint16_t** ptrs, uint32_t reserve) {
+  const uint32_t lane = hw::lane();
   for (uint32_t i = 0; i < ntrees; i++) {
     uint32_t tsize = 0;
     const uint32_t room = (uint32_t)(ArenaLayout::kTableEntries - next_off);
-    int r = read_huffman_code(d, alphabet, max_symbol, d.tables + next_off, room, tsize);
+    uint16_t* gtab = d.tables + next_off;
+    int r = read_huffman_code(d, alphabet, max_symbol, gtab, room, tsize);
     if (r != kSuccess) return r;
     tree_off[i] = next_off;
     next_off += tsize;
+    const uint16_t* where = gtab;
+    if (d.stab_used + tsize + reserve <= d.stab_cap) {
+      uint16_t* stab = d.stab + d.stab_used;
+      for (uint32_t j = lane; j < tsize; j += hw::kWarp) stab[j] = gtab[j];
+      d.stab_used += tsize;
+      where = stab;
+    } else {
+      d.n_unpromoted++;
+    }
+    ptrs[i] = where;
   }
   hw::syncwarp();
   return kSuccess;
 }
 
 // Everything between MLEN and the first command of a compressed metablock.
-BD_DEV int read_compressed_metablock_header(Decoder& d) {
+BD_COLD int read_compressed_metablock_header(Decoder& d) {
   BitReader& br = d.br;
   int r;
   if ((r = read_block_split_header(d, 0, d.nbt_l, d.bl_l)) != kSuccess) return r;
@@ -935,14 +1433,44 @@ BD_DEV int read_compressed_metablock_header(Decoder& d) {
   d.dist_max_symbol = d.large_window ? max_distance_symbol(num_direct_codes, d.npostfix) : d.dist_alphabet;
   if ((r = decode_context_map(d, d.nbt_d << 2, d.ctx_map_dist(), d.n_dist_trees)) != kSuccess) return r;
   if (br.overrun()) return kNeedsMoreInput;
+  // where this metablock's lookup structures live: shared memory when small enough, else the arena
+  WarpShared* sh = d.sh;
+  const uint16_t** lit_ptrs = d.n_lit_trees <= WarpShared::kLitPtrs ? sh->lit_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrLit);
+  const uint16_t** cmd_ptrs = d.nbt_c <= WarpShared::kCmdPtrs ? sh->cmd_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrCmd);
+  const uint16_t** dist_ptrs = d.n_dist_trees <= WarpShared::kDistPtrs ? sh->dist_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrDist);
+  d.lit_ptrs = lit_ptrs; d.cmd_ptrs = cmd_ptrs; d.dist_ptrs = dist_ptrs;
+  d.map_lit = d.ctx_map_lit(); d.map_dist = d.ctx_map_dist();
+  const uint32_t lane = hw::lane();
+  if ((d.nbt_l << 6) <= WarpShared::kLitMapBytes) {
+    for (uint32_t i = lane; i < (d.nbt_l << 6); i += hw::kWarp) sh->lit_map[i] = d.ctx_map_lit()[i];
+    d.map_lit = sh->lit_map;
+  }
+  if ((d.nbt_d << 2) <= WarpShared::kDistMapBytes) {
+    for (uint32_t i = lane; i < (d.nbt_d << 2); i += hw::kWarp) sh->dist_map[i] = d.ctx_map_dist()[i];
+    d.map_dist = sh->dist_map;
+  }
+  d.stab_used = 0;
+  d.n_unpromoted = 0;
+  const uint32_t reserve_dist = (d.n_dist_trees < 8 ? d.n_dist_trees : 8u) * 256u;
+  const uint32_t reserve_cmd = (d.nbt_c < 2 ? d.nbt_c : 2u) * 1024u;
   uint32_t next_off = 0;
-  if ((r = read_tree_group(d, d.n_lit_trees, 256, 256, d.tree_off_lit(), next_off)) != kSuccess) return r;
-  if ((r = read_tree_group(d, d.nbt_c, 704, 704, d.tree_off_cmd(), next_off)) != kSuccess) return r;
-  if ((r = read_tree_group(d, d.n_dist_trees, d.dist_alphabet, d.dist_max_symbol, d.tree_off_dist(), next_off)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.n_lit_trees, 256, 256, d.tree_off_lit(), next_off, lit_ptrs, reserve_cmd + reserve_dist)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.nbt_c, 704, 704, d.tree_off_cmd(), next_off, cmd_ptrs, reserve_dist)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.n_dist_trees, d.dist_alphabet, d.dist_max_symbol, d.tree_off_dist(), next_off, dist_ptrs, 0)) != kSuccess) return r;
   if (br.overrun()) return kNeedsMoreInput;
+  hw::syncwarp();
   prepare_literal_decoding(d);
   d.dist_slice = 0;
-  d.cmd_tree = d.tables + d.tree_off_cmd()[0];
+  refresh_cur_dist(d);
+  d.cmd_tree = d.cmd_ptrs[0];
+  // shared-space mirrors for process_commands_shared
+  d.all_shared = d.n_unpromoted == 0 && d.map_lit == sh->lit_map && d.map_dist == sh->dist_map && lit_ptrs == sh->lit_ptrs &&
+                 cmd_ptrs == sh->cmd_ptrs && dist_ptrs == sh->dist_ptrs;
+  if (d.all_shared) {
+    for (uint32_t i = lane; i < d.n_lit_trees; i += hw::kWarp) sh->lit_s[i] = hw::to_sref(lit_ptrs[i]);
+  }
+  build_dist_lut(d);
+  hw::syncwarp();
   d.state = kCmdBegin;
   return kSuccess;
 }
@@ -963,7 +1491,7 @@ BD_DEV void allocate_ring_emulation(Decoder& d, uint32_t is_last, uint32_t is_un
 }
 
 // CopyUncompressedBlockToOutput, src/decode.rs:1754-1806
-BD_DEV int copy_uncompressed(Decoder& d) {
+BD_COLD int copy_uncompressed(Decoder& d) {
   const uint32_t lane = hw::lane();
   uint64_t in_pos = d.br.byte_pos();
   const uint64_t in_size = d.br.size();
@@ -1093,7 +1621,7 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
           if (result == kSuccess && br.overrun()) result = kNeedsMoreInput;
           if (result != kSuccess) break;
           for (;;) {  // ProcessCommands / SafeProcessCommands, src/decode.rs:3289-3298
-            result = process_commands<false>(d);
+            result = d.all_shared ? process_commands_shared(d) : process_commands_fast(d);
             if (result == kNeedSafe) result = process_commands<true>(d);
             if (result != kRetryFast) break;
           }

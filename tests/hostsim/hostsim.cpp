@@ -12,14 +12,27 @@
 
 extern "C" const uint8_t kBrotliDictionaryData[];
 
+static uint32_t g_last_stab_used, g_last_all_shared, g_last_unpromoted;
+// shared-table occupancy of the last metablock decoded (sizing experiments for kWarpSharedBytes)
+extern "C" void hostsim_last_table_stats(uint32_t* stab_used, uint32_t* all_shared, uint32_t* unpromoted) {
+  *stab_used = g_last_stab_used; *all_shared = g_last_all_shared; *unpromoted = g_last_unpromoted;
+}
+
 extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, uint64_t* decoded) {
   using namespace brotli_b200;
   static std::vector<uint2> cmd_lut;
   if (cmd_lut.empty()) { cmd_lut.resize(704); for (uint32_t i = 0; i < 704; i++) cmd_lut[i] = pack_cmd_lut(i); }
   std::vector<uint8_t> arena(ArenaLayout::kBytes);
-  WarpScratch ws;
+  // "shared memory" of the simulated warp: WarpShared followed by table storage (same carve-up as the kernel)
+  const uint32_t stab_entries = 4096;
+  std::vector<uint64_t> shmem((sizeof(WarpShared) + 2 * stab_entries + 7) / 8);
+  WarpShared* sh = (WarpShared*)shmem.data();
+  WarpScratch& ws = sh->ws;
   Decoder d;
   memset(&d, 0, sizeof(d));
+  d.sh = sh;
+  d.stab = (uint16_t*)(sh + 1);
+  d.stab_cap = stab_entries;
   d.arena = arena.data();
   d.tables = (uint16_t*)(arena.data() + ArenaLayout::kTables);
   d.ws = &ws;
@@ -27,5 +40,7 @@ extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, s
   d.luts.ctx_lut = tbl::kBrotliContextLookup;
   d.luts.dictionary = kBrotliDictionaryData;
   uint64_t used = 0;
-  return decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used);
+  int rc = decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used);
+  g_last_stab_used = d.stab_used; g_last_all_shared = d.all_shared; g_last_unpromoted = d.n_unpromoted;
+  return rc;
 }

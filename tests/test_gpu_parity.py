@@ -196,7 +196,11 @@ def test_streaming_errors_and_trailing_bytes(gpu_lib, pkg):
     st.close()
     st = pkg.DecoderState()
     r, used, out = st.decompress_stream(bytes.fromhex("1f0700f827fe43840000"), 64)  # src/bin/ffi_stream_tests.rs:77
-    assert r == 1 and out == b"\xff" * 8 and used == 9  # the 10th byte is not part of the stream
+    assert r == 1 and out == b"\xff" * 8 and used == 10 and st.is_used()
+    st.close()
+    st = pkg.DecoderState()  # bytes after the end of the stream are left unconsumed (src/ffi/mod.rs:452-453)
+    r, used, out = st.decompress_stream(bytes.fromhex("8f028068656c6c6f0a03") + b"trailing garbage", 64)
+    assert r == 1 and out == b"hello\n" and used == 10
     st.close()
     st = pkg.DecoderState()  # large window needs the parameter on a streaming instance (src/ffi/mod.rs:127)
     r, used, out = st.decompress_stream(helpers.golden_fixture("rnd_chunk.br"), 4096)
