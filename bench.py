@@ -116,9 +116,8 @@ def tile_indices(n_total, n_unique, seed=0xB2000000):
 
 def shard(n_total, world, rank):
     """Contiguous per-GPU slice; streams are equal-sized here so an even count split is byte-balanced."""
-    lo = n_total * rank // world
-    hi = n_total * (rank + 1) // world
-    return lo, hi
+    sharding = importlib.import_module("rust-brotli-decompressor_b200.sharding")
+    return sharding.even_split(n_total, world, rank)
 
 
 def run_reference(args, rank, world):
