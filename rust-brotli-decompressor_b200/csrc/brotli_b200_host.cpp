@@ -94,6 +94,13 @@ struct DeviceCtx {
   bool ready = false;
   int device = -1;
   int ctas = 0;
+  int lane_ctas = 0;           // 0: lane kernel disabled (BROTLI_B200_LANE=0): every stream takes the exact kernel
+  int lane_warps = 0;          // warps per CTA of the lane kernel
+  uint32_t lane_slot_bytes = 0;
+  uint8_t* lane_arena = nullptr;
+  uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
+  uint32_t* bail_count = nullptr;
+  DevBuf bail_list;
   uint8_t* arena = nullptr;
   uint8_t* dictionary = nullptr;
   uint32_t* ticket = nullptr;
@@ -149,6 +156,27 @@ DeviceCtx* acquire_ctx() {
     set_error(std::string("brotli_b200: device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
+  const char* lane_env = getenv("BROTLI_B200_LANE");
+  if (!(lane_env && lane_env[0] == '0')) {
+    const char* warps_env = getenv("BROTLI_B200_LANE_WARPS");
+    c->lane_warps = warps_env ? atoi(warps_env) : brotli_b200::kLaneWarpsPerCta;
+    c->lane_ctas = brotli_b200::query_lane_resident_ctas(dev, c->lane_warps);
+    if (c->lane_ctas <= 0) { set_error("brotli_b200: occupancy query of the lane kernel failed"); return nullptr; }
+    c->lane_slot_bytes = brotli_b200::lane_slot_bytes(c->lane_warps);
+    const size_t lane_bytes = (size_t)c->lane_ctas * c->lane_warps * 32 * brotli_b200::lane_arena_bytes_per_lane();
+    if (cudaMalloc((void**)&c->lane_arena, lane_bytes) != cudaSuccess) {
+      set_error(std::string("brotli_b200: lane arena allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    if (cudaMalloc((void**)&c->xdict, brotli_b200::xdict_bytes()) != cudaSuccess ||
+        brotli_b200::launch_build_xdict(c->dictionary, c->xdict, c->s_compute) != cudaSuccess ||
+        cudaStreamSynchronize(c->s_compute) != cudaSuccess) {
+      set_error(std::string("brotli_b200: expanded dictionary build failed: ") + cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    g_launches.fetch_add(1);
+    c->bail_count = c->ticket + 16;  // same 256-byte allocation as the tickets
+  }
   c->ready = true;
   return c;
 }
@@ -163,9 +191,24 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   a.in = d_in; a.in_off = d_in_off; a.out = d_out; a.out_off = d_out_off; a.out_len = d_out_len; a.codes = d_codes;
   a.in_used = d_in_used;
   a.order = nullptr; a.ticket = c->ticket; a.arena = c->arena; a.dictionary = c->dictionary;
-  a.n = (uint32_t)n; a.large_window = large_window;
+  a.n = (uint32_t)n; a.large_window = large_window; a.n_ptr = nullptr;
   std::lock_guard<std::mutex> lock(c->launch_mu);
   if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
+  if (c->lane_ctas > 0) {
+    // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
+    CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
+    brotli_b200::LaneArgs la;
+    la.arena = c->lane_arena; la.bail_count = c->bail_count; la.bail_list = (uint32_t*)c->bail_list.p;
+    la.slot_bytes = c->lane_slot_bytes; la.xdict = c->xdict;
+    // small batches: fewer streams per warp, spread over all resident warps
+    const size_t total_warps = (size_t)c->lane_ctas * c->lane_warps;
+    const size_t per_warp = (n + total_warps - 1) / total_warps;
+    la.chunk = per_warp >= 32 ? 32u : (uint32_t)per_warp;
+    CU_TRY(brotli_b200::launch_decode_lane(a, la, c->lane_ctas, c->lane_warps, stream));
+    g_launches.fetch_add(1);
+    // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
+    a.order = la.bail_list; a.n_ptr = la.bail_count; a.ticket = c->ticket + 8;
+  }
   CU_TRY(brotli_b200::launch_decode_batch(a, c->ctas, stream));
   CU_TRY(cudaEventRecord(c->ev_arena, stream));
   c->arena_busy = true;
@@ -562,6 +605,10 @@ void BrotliB200Shutdown(void) {
     if (!c->ready) continue;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     cudaFree(c->arena); cudaFree(c->dictionary); cudaFree(c->ticket);
+    if (c->lane_arena) cudaFree(c->lane_arena);
+    if (c->xdict) cudaFree(c->xdict);
+    c->xdict = nullptr;
+    c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
     cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); cudaEventDestroy(c->ev_arena); c->arena_busy = false;

@@ -43,11 +43,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
   d.luts.ctx_lut = s_ctx_lut;
   d.luts.dictionary = a.dictionary;
 
+  const uint32_t n = a.n_ptr ? *a.n_ptr : a.n;
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= a.n) break;
+    if (t >= n) break;
     const uint32_t i = a.order ? a.order[t] : t;
     const uint64_t in0 = a.in_off[i], in1 = a.in_off[i + 1];
     const uint64_t out0 = a.out_off[i], out1 = a.out_off[i + 1];

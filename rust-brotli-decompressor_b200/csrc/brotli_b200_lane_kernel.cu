@@ -1,0 +1,158 @@
+// brotli_b200_lane_kernel.cu -- brotli_decode_lane_kernel: one stream per lane, 32 streams per warp
+// (see brotli_decode_lane.cuh).  Streams this optimistic path gives up are appended to a bail list and
+// decoded afterwards by the exact warp-per-stream kernel (brotli_b200_kernels.cu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "brotli_b200_runtime.h"
+#include "brotli_decode_lane.cuh"
+
+namespace brotli_b200 {
+
+// One persistent CTA per SM.  Static shared memory: the command LUT and the literal-context LUT, read by
+// all lanes.  Dynamic shared memory: one private slot per lane (slot header + root tables).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(BatchArgs a, LaneArgs la) {
+  __shared__ uint2 s_cmd_lut[704];
+  __shared__ __align__(16) uint8_t s_ctx_lut[2048];
+  __shared__ uint32_t s_word_info[25];
+  __shared__ uint32_t s_transform_info[BROTLI_NUM_TRANSFORMS];
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  for (uint32_t i = threadIdx.x; i < 704; i += blockDim.x) s_cmd_lut[i] = pack_cmd_lut(i);
+  for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_ctx_lut[i] = tbl::kBrotliContextLookup[i];
+  {
+    const lane::XDictLayout x = lane::xdict_layout();
+    for (uint32_t i = threadIdx.x; i < 25; i += blockDim.x) s_word_info[i] = lane::pack_word_info(x, i);
+    for (uint32_t i = threadIdx.x; i < BROTLI_NUM_TRANSFORMS; i += blockDim.x) s_transform_info[i] = lane::pack_transform_info(i);
+  }
+  __syncthreads();
+
+  const uint32_t lane_id = threadIdx.x & 31u;
+  const uint64_t glane = (uint64_t)blockIdx.x * (WARPS * 32) + threadIdx.x;
+  uint8_t* const arena = la.arena + glane * lane::ArenaLayout::kBytes;
+
+  lane::LaneCtx c;
+  c.slot = hw::to_sref(s_dyn + (size_t)threadIdx.x * la.slot_bytes);
+  c.stab = c.slot + lane::kSlotHeaderBytes;
+  c.E = (la.slot_bytes - lane::kSlotHeaderBytes) / 2;
+  c.gtab = (uint16_t*)(arena + lane::ArenaLayout::kTab);
+  c.cold_off = (uint32_t*)(arena + lane::ArenaLayout::kColdOff);
+  c.ctx_lit = arena + lane::ArenaLayout::kCtxLit;
+  c.ctx_dist = arena + lane::ArenaLayout::kCtxDist;
+  c.ctx_modes = arena + lane::ArenaLayout::kCtxModes;
+  c.cmd_lut = hw::to_sref(s_cmd_lut);
+  c.ctx_lut = hw::to_sref(s_ctx_lut);
+  c.dictionary = a.dictionary;
+  c.xdict = la.xdict;
+  c.word_info = hw::to_sref(s_word_info);
+  c.transform_info = hw::to_sref(s_transform_info);
+
+  const uint32_t chunk = la.chunk;  // streams a warp takes per ticket (32 unless the batch is small)
+  for (;;) {
+    uint32_t base = 0;
+    if (lane_id == 0) base = atomicAdd(a.ticket, chunk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= a.n) break;
+    const uint32_t t = base + lane_id;
+    const bool active = lane_id < chunk && t < a.n;
+    uint32_t i = 0;
+    uint64_t in0 = 0, in1 = 0, out0 = 0, out1 = 0;
+    if (active) {
+      i = a.order ? a.order[t] : t;
+      in0 = a.in_off[i]; in1 = a.in_off[i + 1];
+      out0 = a.out_off[i]; out1 = a.out_off[i + 1];
+    }
+    uint64_t decoded = 0, used = 0;
+    // the whole warp decodes together: one stream per lane, one prefix-code symbol per lane and iteration
+    const uint32_t r = lane::decode_streams(c, active, a.in + in0, in1 - in0, a.out + out0, out1 - out0, &decoded, &used);
+    if (active) {
+      if (r == lane::kStDone) {
+        a.out_len[i] = decoded;
+        a.codes[i] = kSuccess;
+        if (a.in_used) a.in_used[i] = used;
+      } else {
+        la.bail_list[atomicAdd(la.bail_count, 1u)] = i;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// One thread per (word, transform): fills the expanded dictionary (see xdict_layout) once per device.
+__global__ void brotli_build_xdict_kernel(const uint8_t* dictionary, uint8_t* xdict) {
+  const lane::XDictLayout x = lane::xdict_layout();
+  const uint32_t len = BROTLI_MIN_DICTIONARY_WORD_LENGTH + blockIdx.y;
+  const uint32_t n = BROTLI_NUM_TRANSFORMS << lane::dict_size_bits(len);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t idx = e / BROTLI_NUM_TRANSFORMS, t = e % BROTLI_NUM_TRANSFORMS;
+    lane::build_xdict_entry(xdict + x.base[len] + (size_t)e * lane::xdict_stride(len),
+                            dictionary + tbl::kBrotliDictOffsetsByLength[len] + idx * len, len, t);
+  }
+}
+
+size_t xdict_bytes() { return (size_t)lane::xdict_layout().total + 64; }
+
+cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream) {
+  brotli_build_xdict_kernel<<<dim3(64, BROTLI_MAX_DICTIONARY_WORD_LENGTH - BROTLI_MIN_DICTIONARY_WORD_LENGTH + 1), 256, 0, stream>>>(dictionary, xdict);
+  return cudaGetLastError();
+}
+
+namespace {
+template <int WARPS>
+int lane_occupancy(uint32_t dyn) {
+  int per_sm = 0;
+  if (cudaFuncSetAttribute(brotli_decode_lane_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brotli_decode_lane_kernel<WARPS>, WARPS * 32, dyn) != cudaSuccess) return -1;
+  return per_sm;
+}
+}  // namespace
+
+size_t lane_arena_bytes_per_lane() { return lane::ArenaLayout::kBytes; }
+
+// Slot size for `warps` warps per CTA: what is left of the SM's shared memory, an odd number of 32-bit
+// words so that equal offsets in different lanes' slots fall into different banks.
+uint32_t lane_slot_bytes(int warps) {
+  const uint32_t static_bytes = 704 * 8 + 2048 + 4 * (25 + BROTLI_NUM_TRANSFORMS) + 1024 + 128;  // the LUTs + the runtime's reserve
+  uint32_t per_lane = (232448u - static_bytes) / (uint32_t)(warps * 32);
+  uint32_t words = per_lane / 4;
+  if ((words & 1u) == 0) words--;
+  return words * 4;
+}
+
+int query_lane_resident_ctas(int device, int warps) {
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  const uint32_t dyn = lane_slot_bytes(warps) * (uint32_t)(warps * 32);
+  int per_sm = -1;
+  switch (warps) {
+    case 2: per_sm = lane_occupancy<2>(dyn); break;
+    case 4: per_sm = lane_occupancy<4>(dyn); break;
+    case 6: per_sm = lane_occupancy<6>(dyn); break;
+    case 8: per_sm = lane_occupancy<8>(dyn); break;
+    case 12: per_sm = lane_occupancy<12>(dyn); break;
+    case 16: per_sm = lane_occupancy<16>(dyn); break;
+    default: return -1;
+  }
+  if (per_sm < 1) return -1;
+  return per_sm * sms;
+}
+
+cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  const uint32_t dyn = la.slot_bytes * (uint32_t)(warps * 32);
+  switch (warps) {
+    case 2: brotli_decode_lane_kernel<2><<<ctas, 64, dyn, stream>>>(a, la); break;
+    case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
+    case 6: brotli_decode_lane_kernel<6><<<ctas, 192, dyn, stream>>>(a, la); break;
+    case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;
+    case 12: brotli_decode_lane_kernel<12><<<ctas, 384, dyn, stream>>>(a, la); break;
+    case 16: brotli_decode_lane_kernel<16><<<ctas, 512, dyn, stream>>>(a, la); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace brotli_b200

@@ -23,6 +23,13 @@ constexpr int kMinCtasPerSm = 1;
 constexpr uint32_t kWarpSharedBytes = BROTLI_B200_WARP_SHARED_BYTES;
 constexpr uint32_t kDynamicSharedBytes = kWarpsPerCta * kWarpSharedBytes;
 
+// Lane kernel (brotli_b200_lane_kernel.cu): one stream per lane, one persistent CTA per SM; the SM's
+// shared memory is split into one private table slot per lane, so fewer warps mean wider root tables.
+#ifndef BROTLI_B200_LANE_WARPS_PER_CTA
+#define BROTLI_B200_LANE_WARPS_PER_CTA 8
+#endif
+constexpr int kLaneWarpsPerCta = BROTLI_B200_LANE_WARPS_PER_CTA;
+
 // One launch decodes streams [0, n) of a packed batch (see decode.h, "Packed layout").
 struct BatchArgs {
   const uint8_t* in;
@@ -38,11 +45,28 @@ struct BatchArgs {
   const uint8_t* dictionary;  // RFC 7932 static dictionary in device memory
   uint32_t n;
   uint32_t large_window;    // accept the large-window header (one-shot: 1, src/state.rs:394)
+  const uint32_t* n_ptr;    // optional: the stream count lives in device memory (fallback pass over a bail list)
+};
+
+// Extra arguments of the lane kernel.
+struct LaneArgs {
+  uint8_t* arena;        // resident lanes * lane_arena_bytes_per_lane()
+  uint32_t* bail_count;  // device counter, reset by the launcher
+  uint32_t* bail_list;   // [n] stream indices the lane kernel gave up; decoded next by the exact kernel
+  const uint8_t* xdict;  // expanded static dictionary, xdict_bytes(), filled by launch_build_xdict
+  uint32_t slot_bytes;   // shared-memory slot per lane
+  uint32_t chunk;        // streams a warp takes per ticket (1..32)
 };
 
 size_t arena_bytes_per_warp();
 int query_resident_ctas(int device);
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream);
+size_t lane_arena_bytes_per_lane();
+uint32_t lane_slot_bytes(int warps);
+size_t xdict_bytes();
+cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream);
+int query_lane_resident_ctas(int device, int warps);
+cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream);
 cudaError_t launch_checksum_batch(uint32_t n, const uint8_t* bytes, const uint64_t* off, const uint64_t* len, uint64_t* sums,
                                   cudaStream_t stream);
 

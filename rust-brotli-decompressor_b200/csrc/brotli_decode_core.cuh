@@ -63,7 +63,7 @@ static inline sref_t lds_ref(sref_t a) { return *(const sref_t*)a; }
 }  // namespace brotli_b200
 #else
 #define BD_DEV __device__ __forceinline__
-#define BD_COLD __device__ __noinline__  /* per-metablock / per-stream code: kept out of the command loop's register budget */
+#define BD_COLD static __device__ __noinline__  /* per-metablock / per-stream code: kept out of the command loop's register budget */
 #define BD_CONST_TABLE __device__ const
 namespace brotli_b200 {
 namespace hw {

@@ -1,0 +1,1056 @@
+// brotli_decode_lane.cuh -- one stream per LANE: 32 independent streams per warp (sm_100a).
+//
+// The warp-per-stream decoder (brotli_decode_core.cuh) issues the serial prefix-code chain once per
+// warp, so a B200 is limited by instruction issue long before HBM.  A batch of many independent
+// streams has a better mapping: every lane owns a whole stream, so one issued instruction advances 32
+// bit windows / table lookups / output cursors at once.  What makes that work on the SM:
+//
+//   * unified symbol loop -- each iteration every lane decodes ONE prefix-code symbol of whatever kind
+//     its stream needs next (insert&copy command, literal, distance).  The expensive common part (peek,
+//     root-table load, bit skip, refill) is convergent; only the short per-kind tails diverge.
+//   * per-lane prefix-code tables with a SMALL root level in shared memory (a private slot per lane;
+//     32 random addresses over 32 banks cost ~3 wavefronts) and the rarely used second level in a
+//     per-lane global arena (L1/L2).  Root widths are chosen per metablock so all roots fit the slot.
+//   * output through a 4-byte write combiner: literals and copies are appended to a partial word in a
+//     register and leave as aligned 32-bit stores; backreference sources are read as aligned words and
+//     re-aligned with a funnel shift.  Loads after stores of the SAME thread are ordered by the
+//     hardware, so no warp synchronisation is needed anywhere.
+//
+// This path is OPTIMISTIC (like a fast path in front of the reference's "safe" path): it decodes
+// well-formed streams with compressed metablocks and a regular window.  Anything else -- corrupt or
+// truncated input, too small an output region, uncompressed / metadata metablocks, large-window
+// headers, table sets larger than the arena -- makes the lane give its stream up ("bail"); the host
+// runs exactly those streams through brotli_decode_batch_kernel, which owns the reference's
+// error-code and decoded_size semantics.  Every validity check of the reference is still made here;
+// a failed check bails instead of reporting a code.
+//
+// Reference path restated (file:line under /root/reference):
+//   DecodeWindowBits src/decode.rs:152-187, DecodeMetaBlockLength :243-372, DecodeVarLenUint8 :193-241,
+//   ReadHuffmanCode :868-1013 (+ :516-556, :565-658, :661-731, :801-853), table shape after
+//   src/huffman/mod.rs:273-471 (canonical codes, bit-reversed keys; the root width is ours),
+//   DecodeContextMap :1272-1428, InverseMoveToFrontTransform :1096-1128, DecodeBlockTypeAndLength
+//   :1469-1524, PrepareLiteralDecoding :1554-1570, ReadCommandInternal :2134-2189, ReadDistanceInternal
+//   :2066-2131, TakeDistanceFromRingBuffer :2017-2049, ProcessCommandsInternal :2330-2744, dictionary
+//   :2593-2640 + src/transform.rs:720-795, METABLOCK_DONE :3345-3381.
+#pragma once
+#include "brotli_decode_core.cuh"
+
+#ifndef BD_NS
+#define BD_NS brotli_b200
+#endif
+namespace BD_NS {
+namespace lane {
+
+// ---- per-lane storage geometry ----
+constexpr uint32_t kSlotHeaderBytes = 32;   // cur_dist[4]: {root virtual index, second-level base} per distance context
+constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
+constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
+constexpr uint32_t kTreeIdBlock = 0;        // ids 0..2 block-type trees, 3..5 block-length trees
+constexpr uint32_t kTreeIdCtxMap = 6;       // temporary tree of a context map
+constexpr uint32_t kTreeIdGroups = 7;       // literal, command, distance trees follow
+constexpr uint32_t kMaxTreeIds = kTreeIdGroups + 3 * 256;
+constexpr uint32_t kBlockRootBits = 6;
+
+struct ArenaLayout {
+  static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
+  static constexpr size_t kColdOff = kTab + 2 * (size_t)kGlobalTab;   // u32[kMaxTreeIds]
+  static constexpr size_t kCtxLit = kColdOff + 4 * (size_t)kMaxTreeIds;  // u8[64 * kMaxBlockTypes]
+  static constexpr size_t kCtxDist = kCtxLit + 64 * (size_t)kMaxBlockTypes;  // u8[4 * kMaxBlockTypes]
+  static constexpr size_t kCtxModes = kCtxDist + 4 * (size_t)kMaxBlockTypes;  // u8[kMaxBlockTypes]
+  static constexpr size_t kBytes = (kCtxModes + kMaxBlockTypes + 255) & ~size_t(255);
+};
+
+enum : int { kLaneOk = 0, kLaneDone = 1, kLaneBail = 2 };
+enum : uint32_t { kSymCmd = 0, kSymLit = 1, kSymDist = 2 };  // also the block category order of the decoder (lit=0,cmd=1,dist=2 in the reference)
+
+#if defined(BROTLI_B200_HOSTSIM)
+static inline void sts16(hw::sref_t a, uint32_t v) { *(uint16_t*)a = (uint16_t)v; }
+static inline void sts32(hw::sref_t a, uint32_t v) { *(uint32_t*)a = v; }
+static inline uint32_t vlds16(hw::sref_t a) { return *(const uint16_t*)a; }
+static inline uint32_t vlds32(hw::sref_t a) { return *(const uint32_t*)a; }
+static inline uint2 vlds64(hw::sref_t a) { return *(const uint2*)a; }
+static inline uint32_t vlds8(hw::sref_t a) { return *(const uint8_t*)a; }
+static inline uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) {
+  if (s >= 32) return hi;
+  return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+static inline void warp_sync() {}
+static inline bool warp_any(bool p) { return p; }
+#else
+// volatile: these loads follow stores to the same slot (table fill) made through asm as well
+BD_DEV void sts16(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+BD_DEV void sts32(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BD_DEV uint32_t vlds16(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint32_t vlds32(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint32_t vlds8(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BD_DEV uint2 vlds64(hw::sref_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+BD_DEV uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
+BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
+BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
+BD_DEV void warp_sync() { __syncwarp(); }
+BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 lanes take part
+#endif
+
+BD_DEV uint32_t mask_bits(uint32_t n) { return (1u << n) - 1u; }  // n <= 31
+
+// Constant per-lane context (where this lane's storage lives).
+struct LaneCtx {
+  hw::sref_t slot;       // shared: kSlotHeaderBytes header, then E u16 table entries
+  hw::sref_t stab;       // slot + kSlotHeaderBytes
+  uint32_t E;            // entries of virtual table space that live in the shared slot
+  uint16_t* gtab;        // arena: virtual entries E .. E + kGlobalTab
+  uint32_t* cold_off;    // arena: second-level base (virtual index) per tree id
+  uint8_t* ctx_lit;
+  uint8_t* ctx_dist;
+  uint8_t* ctx_modes;
+  hw::sref_t cmd_lut;    // shared: uint2[704], pack_cmd_lut
+  hw::sref_t ctx_lut;    // shared: u8[2048]
+  const uint8_t* dictionary;  // RFC 7932 dictionary (source of the expanded table)
+  const uint8_t* xdict;  // expanded static dictionary (every word under every transform), see xdict_layout
+  hw::sref_t word_info;       // shared: u32[25], pack_word_info
+  hw::sref_t transform_info;  // shared: u32[121], pack_transform_info
+};
+
+// Decoder state of one lane's stream.  Lives in local memory for the per-metablock (cold) code; the
+// command loop works on register copies.
+struct Lane {
+  // bit window: 96 bits of look-ahead over aligned words of the input
+  const uint32_t* w;
+  uint32_t lo, hi, nx, k, bp;
+  uint32_t k_max;        // last word holding stream bytes; loads never go past it
+  uint64_t end_bit;      // 8 * (lead + size), relative to the aligned base
+  uint32_t lead;
+  // output write combiner; positions are biased by (out & 3) so that word boundaries are absolute
+  uint8_t* out_al;
+  uint32_t posb, acc, bias, capb;
+  // stream / metablock
+  uint32_t wbits, max_backward, is_last;
+  int32_t mlen;
+  int32_t d0, d1, d2, d3;
+  uint32_t bl[3], nbt[3], rb[6];   // category order: 0 literal, 1 command, 2 distance (reference order)
+  uint32_t npostfix, ndirect, dist_alphabet;
+  uint32_t n_lit, n_dist;
+  uint32_t rbits[3], root[3], tid0[3];  // per group (0 literal, 1 command, 2 distance): root width, root base, first tree id
+  uint32_t trivial_lo, trivial_hi;      // bit i: literal block type i uses one tree for all 64 contexts
+  uint32_t trivial, lit_tree, ctx_mode_off, ctx_slice, cmd_tree, dist_slice;
+  uint32_t cold_next;    // next free virtual index of the arena part of the table space
+
+  BD_DEV uint32_t peek() const { return hw::funnelshift_r(lo, hi, bp); }
+  BD_DEV void skip(uint32_t n) {
+    bp += n;
+    if (bp >= 32) {
+      lo = hi; hi = nx; k++;
+      const uint32_t kk = k + 2 < k_max ? k + 2 : k_max;
+      nx = hw::ldg32(w + kk);
+      bp -= 32;
+    }
+  }
+  BD_DEV uint32_t read(uint32_t n) {  // n <= 25
+    const uint32_t v = peek() & mask_bits(n);
+    skip(n);
+    return v;
+  }
+  BD_DEV bool overrun() const { return (uint64_t)k * 32 + bp > end_bit; }
+  BD_DEV uint32_t pos() const { return posb - bias; }
+};
+
+// ---- virtual table space ----
+BD_DEV uint32_t tab_load(const LaneCtx& c, uint32_t v) {
+  return v < c.E ? vlds16(c.stab + (v << 1)) : (uint32_t)c.gtab[v - c.E];
+}
+BD_DEV void tab_store(const LaneCtx& c, uint32_t v, uint32_t e) {
+  if (v < c.E) sts16(c.stab + (v << 1), e); else c.gtab[v - c.E] = (uint16_t)e;
+}
+
+// One symbol of the tree whose root (2^rbits entries) starts at virtual index root_v.
+// Entry = symbol << 4 | code length; length > rbits marks a pointer: value = offset of the second-level
+// table from cold_off[tid], length - rbits = its index width.
+BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+  const uint32_t bits = L.peek();
+  uint32_t e = tab_load(c, root_v + (bits & mask_bits(rbits)));
+  uint32_t len = e & 15u;
+  if (len > rbits) {
+    e = tab_load(c, c.cold_off[tid] + (e >> 4) + ((bits >> rbits) & mask_bits(len - rbits)));
+    len = e & 15u;
+  }
+  L.skip(len);
+  return e >> 4;
+}
+
+// ---- output write combiner ----
+BD_DEV void store_word(uint8_t* out_al, uint32_t bias, uint32_t wpos, uint32_t word) {
+  if (BD_UNLIKELY(wpos < bias)) {  // first word of an unaligned region: bytes below the region are not ours
+    for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
+  } else {
+    st32(out_al + wpos, word);
+  }
+}
+// v holds exactly n (1..4) valid low bytes, the rest is zero
+BD_DEV void append(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc, uint32_t v, uint32_t n) {
+  const uint32_t a = posb & 3u, sh = a * 8u;
+  const uint32_t word = acc | (v << sh);
+  if (a + n >= 4) {
+    store_word(out_al, bias, posb & ~3u, word);
+    acc = funnelshift_rc(v, 0u, 32u - sh);
+  } else {
+    acc = word;
+  }
+  posb += n;
+}
+BD_DEV void flush_partial(uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_t acc) {
+  const uint32_t a = posb & 3u, wpos = posb & ~3u;
+  for (uint32_t j = 0; j < a; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(acc >> (8 * j));
+}
+BD_DEV uint32_t reload_partial(const uint8_t* out_al, uint32_t posb) {
+  const uint32_t a = posb & 3u;
+  return a ? ld32(out_al + (posb & ~3u)) & mask_bits(8 * a) : 0u;
+}
+// Last two output bytes (p1 = newest), zero before the start of the stream: the literal context.
+BD_DEV void last_two(const uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_t acc, uint32_t& p1, uint32_t& p2) {
+  const uint32_t a = posb & 3u;
+  uint32_t x;  // the four bytes before posb, newest in the top byte
+  if (a >= 2) {
+    x = acc << (32 - 8 * a);
+  } else {
+    const uint32_t wpos = posb & ~3u;
+    const uint32_t prev = wpos >= 4 ? ld32(out_al + wpos - 4) : 0u;
+    x = a ? (acc << 24) | (prev >> 8) : prev;
+  }
+  const uint32_t have = posb - bias;
+  p1 = have >= 1 ? x >> 24 : 0u;
+  p2 = have >= 2 ? (x >> 16) & 0xFFu : 0u;
+}
+
+// ======================= per-metablock (cold) code =======================
+
+// DecodeVarLenUint8, src/decode.rs:193-241
+BD_DEV uint32_t read_varlen8(Lane& L) {
+  if (L.read(1) == 0) return 0;
+  const uint32_t n = L.read(3);
+  if (n == 0) return 1;
+  return (1u << n) + L.read(n);
+}
+
+BD_DEV uint32_t bit_width(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++; } return r; }  // Log2Floor of src/decode.rs:502-509
+
+// Fill the lookup structure of one prefix code from its symbols sorted by (length, value).
+// count[l] = symbols of length l.  Root of 2^rbits entries at root_v; longer codes go to second-level
+// tables allocated from L.cold_next.  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
+BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const uint16_t* count, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+  uint16_t rem[16];
+  for (uint32_t l = 0; l < 16; l++) rem[l] = count[l];
+  const uint32_t cold_base = L.cold_next;
+  c.cold_off[tid] = cold_base;
+  uint32_t code = 0, idx = 0;
+  uint32_t cur_prefix = 0xFFFFFFFFu, sub_w = 0, sub_v = 0;
+  for (uint32_t l = 1; l <= 15; l++) {
+    for (uint32_t j = count[l]; j != 0; j--) {
+      const uint32_t sym = sorted[idx++];
+      const uint32_t rev = hw::brev(code) >> (32 - l);
+      const uint32_t e = (sym << 4) | l;
+      if (l <= rbits) {
+        for (uint32_t t = rev; t < (1u << rbits); t += 1u << l) tab_store(c, root_v + t, e);
+      } else {
+        const uint32_t prefix = code >> (l - rbits);
+        if (prefix != cur_prefix) {  // first code under a new root slot: size its second-level table (NextTableBitSize, :181-193)
+          cur_prefix = prefix;
+          int32_t left = 1 << (l - rbits);
+          uint32_t ll = l;
+          while (ll < 15) {
+            left -= (int32_t)rem[ll];
+            if (left <= 0) break;
+            ll++; left <<= 1;
+          }
+          sub_w = ll - rbits;
+          sub_v = L.cold_next;
+          const uint32_t off = sub_v - cold_base;
+          if (off > 4095u || sub_v + (1u << sub_w) > c.E + kGlobalTab) return kLaneBail;
+          L.cold_next += 1u << sub_w;
+          tab_store(c, root_v + (rev & mask_bits(rbits)), (off << 4) | (rbits + sub_w));
+        }
+        for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) tab_store(c, sub_v + t, e);
+      }
+      code++;
+      rem[l]--;
+    }
+    code <<= 1;
+  }
+  return kLaneOk;
+}
+
+// ReadHuffmanCode, src/decode.rs:868-1013: one prefix-code description -> lookup structure.
+BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+  uint16_t sorted[704];
+  uint16_t count[16];
+  for (uint32_t l = 0; l < 16; l++) count[l] = 0;
+  const uint32_t hskip = L.read(2);
+  if (hskip == 1) {  // simple code: NSYM 1..4 explicit symbols (ReadSimpleHuffmanSymbols, :516-556)
+    const uint32_t nsym = L.read(2) + 1;
+    const uint32_t max_bits = bit_width(alphabet_size - 1);
+    uint32_t s[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < nsym; i++) {
+      s[i] = L.read(max_bits);
+      if (s[i] >= max_symbol) return kLaneBail;
+    }
+    for (uint32_t i = 0; i + 1 < nsym; i++)
+      for (uint32_t k = i + 1; k < nsym; k++) if (s[i] == s[k]) return kLaneBail;
+    if (nsym == 1) {
+      c.cold_off[tid] = L.cold_next;
+      for (uint32_t t = 0; t < (1u << rbits); t++) tab_store(c, root_v + t, s[0] << 4);
+      return kLaneOk;
+    }
+    // canonical codes sorted by (length, value) reproduce BrotliBuildSimpleHuffmanTable (src/huffman/mod.rs:390-471)
+    uint32_t len[4] = {1, 1, 0, 0};
+    if (nsym == 3) { len[1] = 2; len[2] = 2; }
+    if (nsym == 4) {
+      if (L.read(1)) { len[0] = 1; len[1] = 2; len[2] = 3; len[3] = 3; } else { len[0] = len[1] = len[2] = len[3] = 2; }
+    }
+    uint32_t n = 0;
+    for (uint32_t l = 1; l <= 3; l++) {
+      const uint32_t first = n;
+      for (uint32_t i = 0; i < nsym; i++) if (len[i] == l) {
+        uint32_t q = n++;
+        while (q > first && sorted[q - 1] > s[i]) { sorted[q] = sorted[q - 1]; q--; }
+        sorted[q] = (uint16_t)s[i];
+        count[l]++;
+      }
+    }
+    return fill_table(c, L, sorted, count, root_v, rbits, tid);
+  }
+  // complex code: code-length code lengths (ReadCodeLengthCodeLengths, :801-853)
+  uint8_t cl_cl[18];
+  for (uint32_t i = 0; i < 18; i++) cl_cl[i] = 0;
+  uint32_t space = 32, num_codes = 0;
+  for (uint32_t i = hskip; i < 18; i++) {
+    const uint32_t ix = L.peek() & 15u;
+    // kCodeLengthPrefixLength / kCodeLengthPrefixValue (src/decode.rs:59-61) packed four bits per entry
+    const uint32_t plen = (uint32_t)(0x4222322242223222ull >> (ix * 4)) & 15u;
+    const uint32_t v = (uint32_t)(0x5340234013402340ull >> (ix * 4)) & 15u;
+    L.skip(plen);
+    cl_cl[tbl::kCodeLengthCodeOrder[i]] = (uint8_t)v;
+    if (v != 0) {
+      space -= 32u >> v;
+      num_codes++;
+      if (space - 1u >= 32u) break;  // space is 0 or wrapped
+    }
+  }
+  if (!(num_codes == 1 || space == 0)) return kLaneBail;
+  // 5-bit lookup of the code-length code (BrotliBuildCodeLengthsHuffmanTable, src/huffman/mod.rs:196-271)
+  uint8_t cl_tab[32];  // symbol << 3 | length
+  if (num_codes == 1) {
+    uint32_t only = 0;
+    for (uint32_t i = 0; i < 18; i++) if (cl_cl[i]) only = i;
+    for (uint32_t t = 0; t < 32; t++) cl_tab[t] = (uint8_t)(only << 3);
+  } else {
+    uint32_t code = 0;
+    for (uint32_t l = 1; l <= 5; l++) {
+      for (uint32_t sy = 0; sy < 18; sy++) if (cl_cl[sy] == l) {
+        const uint32_t rev = hw::brev(code) >> (32 - l);
+        for (uint32_t t = rev; t < 32; t += 1u << l) cl_tab[t] = (uint8_t)((sy << 3) | l);
+        code++;
+      }
+      code <<= 1;
+    }
+  }
+  // symbol code lengths with repeat codes (ReadSymbolCodeLengths, :661-731; Process*CodeLength :565-658)
+  uint8_t cl[704];
+  uint32_t symbol = 0, prev_len = 8, repeat = 0, repeat_len = 0;
+  space = 32768;
+  if (max_symbol > 704) return kLaneBail;
+  while (symbol < max_symbol && space > 0) {
+    const uint32_t p = cl_tab[L.peek() & 31u];
+    L.skip(p & 7u);
+    const uint32_t code_len = p >> 3;
+    if (code_len < 16) {
+      repeat = 0;
+      cl[symbol] = (uint8_t)code_len;
+      if (code_len != 0) {
+        prev_len = code_len;
+        space -= 32768u >> code_len;
+        count[code_len]++;
+      }
+      symbol++;
+    } else {
+      const uint32_t extra_bits = code_len - 14;
+      uint32_t delta = L.read(extra_bits);
+      const uint32_t new_len = code_len == 16 ? prev_len : 0;
+      if (repeat_len != new_len) { repeat = 0; repeat_len = new_len; }
+      const uint32_t old_repeat = repeat;
+      if (repeat > 0) { repeat -= 2; repeat <<= extra_bits; }
+      repeat += delta + 3;
+      delta = repeat - old_repeat;
+      if (symbol + delta > max_symbol) { space = 0xFFFFF; break; }
+      for (uint32_t j = 0; j < delta; j++) cl[symbol + j] = (uint8_t)repeat_len;
+      symbol += delta;
+      if (repeat_len != 0) {
+        space -= delta << (15 - repeat_len);
+        count[repeat_len] = (uint16_t)(count[repeat_len] + delta);
+      }
+    }
+  }
+  if (space != 0) return kLaneBail;
+  uint16_t offs[16];
+  uint32_t o = 0;
+  for (uint32_t l = 1; l <= 15; l++) { offs[l] = (uint16_t)o; o += count[l]; }
+  for (uint32_t sy = 0; sy < symbol; sy++) {
+    const uint32_t l = cl[sy];
+    if (l) sorted[offs[l]++] = (uint16_t)sy;
+  }
+  return fill_table(c, L, sorted, count, root_v, rbits, tid);
+}
+
+// A tree that lives wholly in the arena part of the table space (block-switch and context-map codes).
+BD_DEV int read_arena_tree(const LaneCtx& c, Lane& L, uint32_t alphabet, uint32_t tid, uint32_t& root_v) {
+  root_v = L.cold_next;
+  if (root_v + (1u << kBlockRootBits) > c.E + kGlobalTab) return kLaneBail;
+  L.cold_next += 1u << kBlockRootBits;
+  return read_huffman_code(c, L, alphabet, alphabet, root_v, kBlockRootBits, tid);
+}
+
+// ReadBlockLength, src/decode.rs:1016-1026
+BD_DEV uint32_t read_block_length(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t tid) {
+  const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits, tid);
+  if (code >= 26) return 0;  // cannot happen for a 26-symbol alphabet
+  return tbl::kBrotliBlockLengthOffset[code] + L.read(tbl::kBrotliBlockLengthNBits[code]);
+}
+
+// DecodeContextMap, src/decode.rs:1272-1428 (+ InverseMoveToFrontTransform :1096-1128)
+BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_t& ntrees, uint8_t* map) {
+  ntrees = read_varlen8(L) + 1;
+  if (ntrees <= 1) {
+    for (uint32_t i = 0; i < size; i++) map[i] = 0;
+    return kLaneOk;
+  }
+  uint32_t rle_max = 0;
+  const uint32_t b5 = L.peek() & 31u;
+  if (b5 & 1u) { rle_max = (b5 >> 1) + 1; L.skip(5); } else { L.skip(1); }
+  const uint32_t saved_cold = L.cold_next;
+  uint32_t root_v;
+  if (read_arena_tree(c, L, ntrees + rle_max, kTreeIdCtxMap, root_v) != kLaneOk) return kLaneBail;
+  uint32_t i = 0;
+  while (i < size) {
+    const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits, kTreeIdCtxMap);
+    if (code == 0) { map[i++] = 0; continue; }
+    if (code > rle_max) { map[i++] = (uint8_t)(code - rle_max); continue; }
+    uint32_t reps = (1u << code) + L.read(code);
+    if (i + reps > size) return kLaneBail;
+    do { map[i++] = 0; } while (--reps);
+    if (L.overrun()) return kLaneBail;
+  }
+  L.cold_next = saved_cold;  // the map's own code is not needed any more
+  if (L.read(1)) {
+    uint8_t mtf[256];
+    for (uint32_t j = 0; j < 256; j++) mtf[j] = (uint8_t)j;
+    for (uint32_t j = 0; j < size; j++) {
+      uint32_t index = map[j];
+      const uint8_t value = mtf[index];
+      map[j] = value;
+      for (; index > 0; index--) mtf[index] = mtf[index - 1];
+      mtf[0] = value;
+    }
+  }
+  return kLaneOk;
+}
+
+// Virtual root index of tree i of group g.
+BD_DEV uint32_t tree_root(const Lane& L, uint32_t g, uint32_t i) { return L.root[g] + (i << L.rbits[g]); }
+
+// Distance-context -> {root, second-level base} of the current distance block type, kept in the shared slot.
+BD_DEV void refresh_cur_dist(const LaneCtx& c, const Lane& L) {
+  for (uint32_t ctx = 0; ctx < 4; ctx++) {
+    const uint32_t t = c.ctx_dist[L.dist_slice + ctx];
+    sts32(c.slot + ctx * 8, tree_root(L, 2, t));
+    sts32(c.slot + ctx * 8 + 4, c.cold_off[L.tid0[2] + t]);
+  }
+}
+
+// PrepareLiteralDecoding, src/decode.rs:1554-1570
+BD_DEV void prepare_literal(const LaneCtx& c, Lane& L) {
+  const uint32_t bt = L.rb[1];
+  L.ctx_slice = bt << 6;
+  L.trivial = ((bt < 32 ? L.trivial_lo >> bt : L.trivial_hi >> (bt - 32)) & 1u);
+  L.lit_tree = c.ctx_lit[L.ctx_slice];
+  L.ctx_mode_off = (uint32_t)(c.ctx_modes[bt] & 3u) * 512u;
+}
+
+// DecodeBlockTypeAndLength + Decode{Literal,Command,Distance}BlockSwitch, src/decode.rs:1469-1658.
+// cat: 0 literal, 1 command, 2 distance.
+BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, uint32_t type_root, uint32_t len_root) {
+  const uint32_t nbt = L.nbt[cat];
+  if (nbt < 2) return kLaneBail;  // the counter of a single block type can only run out in a corrupt stream
+  uint32_t bt = decode_generic(c, L, type_root, kBlockRootBits, kTreeIdBlock + cat);
+  L.bl[cat] = read_block_length(c, L, len_root, kTreeIdBlock + 3 + cat);
+  uint32_t* rb = &L.rb[2 * cat];
+  if (bt == 1) bt = rb[1] + 1;
+  else if (bt == 0) bt = rb[0];
+  else bt -= 2;
+  if (bt >= nbt) bt -= nbt;
+  if (bt >= nbt) return kLaneBail;
+  rb[0] = rb[1]; rb[1] = bt;
+  if (cat == 0) prepare_literal(c, L);
+  else if (cat == 1) L.cmd_tree = bt;
+  else { L.dist_slice = bt << 2; refresh_cur_dist(c, L); }
+  return L.overrun() ? kLaneBail : kLaneOk;
+}
+
+struct BlockTrees { uint32_t type_root[3], len_root[3]; };
+
+// Metablock header up to the first command: src/decode.rs:2980-3288.
+BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
+  const uint32_t is_last = L.read(1);
+  L.is_last = is_last;
+  L.mlen = 0;
+  if (is_last && L.read(1)) return kLaneDone;  // ISLASTEMPTY
+  const uint32_t nib = L.read(2);
+  if (nib == 3) return kLaneBail;  // metadata block
+  const uint32_t nn = nib + 4;
+  uint32_t v = 0;
+  for (uint32_t i = 0; i < nn; i++) {
+    const uint32_t b = L.read(4);
+    if (i + 1 == nn && nn > 4 && b == 0) return kLaneBail;
+    v |= b << (i * 4);
+  }
+  if (!is_last && L.read(1)) return kLaneBail;  // uncompressed metablock
+  L.mlen = (int32_t)v + 1;
+  L.cold_next = c.E;
+  // block types and lengths per category (HUFFMAN_CODE_0..3, :3046-3140)
+  for (uint32_t k = 0; k < 3; k++) {
+    L.nbt[k] = read_varlen8(L) + 1;
+    L.bl[k] = 1u << 24;
+    L.rb[2 * k] = 1; L.rb[2 * k + 1] = 0;
+    bt.type_root[k] = bt.len_root[k] = 0;
+    if (L.nbt[k] >= 2) {
+      if (L.nbt[k] > kMaxBlockTypes) return kLaneBail;
+      if (read_arena_tree(c, L, L.nbt[k] + 2, kTreeIdBlock + k, bt.type_root[k]) != kLaneOk) return kLaneBail;
+      if (read_arena_tree(c, L, 26, kTreeIdBlock + 3 + k, bt.len_root[k]) != kLaneOk) return kLaneBail;
+      L.bl[k] = read_block_length(c, L, bt.len_root[k], kTreeIdBlock + 3 + k);
+    }
+    if (L.overrun()) return kLaneBail;
+  }
+  const uint32_t pb = L.read(6);
+  L.npostfix = pb & 3u;
+  L.ndirect = 16u + ((pb >> 2) << L.npostfix);
+  for (uint32_t i = 0; i < L.nbt[0]; i++) c.ctx_modes[i] = (uint8_t)L.read(2);  // ReadContextModes, :1991-2015
+  if (decode_context_map(c, L, L.nbt[0] << 6, L.n_lit, c.ctx_lit) != kLaneOk) return kLaneBail;
+  // DetectTrivialLiteralBlockTypes, :1525-1553
+  L.trivial_lo = L.trivial_hi = 0;
+  for (uint32_t i = 0; i < L.nbt[0]; i++) {
+    const uint8_t* m = c.ctx_lit + (i << 6);
+    uint32_t diff = 0;
+    for (uint32_t j = 1; j < 64; j++) diff |= (uint32_t)(m[j] ^ m[0]);
+    if (diff == 0) { if (i < 32) L.trivial_lo |= 1u << i; else L.trivial_hi |= 1u << (i - 32); }
+  }
+  if (decode_context_map(c, L, L.nbt[2] << 2, L.n_dist, c.ctx_dist) != kLaneOk) return kLaneBail;
+  if (L.overrun()) return kLaneBail;
+  L.dist_alphabet = L.ndirect + (48u << L.npostfix);  // 16 + NDIRECT + (24 << (NPOSTFIX + 1)), :3189-3194
+  // Root widths: as wide as the shared slot allows.  Group sizes in entries: n << rbits.
+  const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
+  uint32_t rb[3] = {8, 8, 7};
+  const uint32_t rmin[3] = {5, 5, 4};
+  for (;;) {
+    const uint32_t sz[3] = {ntrees[0] << rb[0], ntrees[1] << rb[1], ntrees[2] << rb[2]};
+    if (sz[0] + sz[1] + sz[2] <= c.E) break;
+    uint32_t g = 3, best = 0;
+    for (uint32_t i = 0; i < 3; i++) if (rb[i] > rmin[i] && sz[i] >= best) { best = sz[i]; g = i; }
+    if (g == 3) break;
+    rb[g]--;
+  }
+  // Groups are placed command, literal, distance from the bottom of the slot; a group that does not
+  // fit any more goes to the arena as a whole (with narrow roots to bound the space).
+  uint32_t next_shared = 0;
+  const uint32_t order[3] = {1, 0, 2};
+  for (uint32_t oi = 0; oi < 3; oi++) {
+    const uint32_t g = order[oi];
+    uint32_t sz = ntrees[g] << rb[g];
+    if (next_shared + sz <= c.E) {
+      L.root[g] = next_shared;
+      next_shared += sz;
+    } else {
+      rb[g] = rmin[g];
+      sz = ntrees[g] << rb[g];
+      if (L.cold_next + sz > c.E + kGlobalTab) return kLaneBail;
+      L.root[g] = L.cold_next;
+      L.cold_next += sz;
+    }
+    L.rbits[g] = rb[g];
+  }
+  L.tid0[0] = kTreeIdGroups;
+  L.tid0[1] = L.tid0[0] + L.n_lit;
+  L.tid0[2] = L.tid0[1] + L.nbt[1];
+  // HuffmanTreeGroupDecode x3, :1130-1219
+  const uint32_t alpha[3] = {256, 704, L.dist_alphabet};
+  for (uint32_t g = 0; g < 3; g++) {
+    for (uint32_t i = 0; i < ntrees[g]; i++) {
+      if (read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g], L.tid0[g] + i) != kLaneOk) return kLaneBail;
+      if (L.overrun()) return kLaneBail;
+    }
+  }
+  prepare_literal(c, L);
+  L.cmd_tree = 0;
+  L.dist_slice = 0;
+  refresh_cur_dist(c, L);
+  return kLaneOk;
+}
+
+// ======================= expanded static dictionary =======================
+// Every (word, transform) pair of the RFC 7932 dictionary is materialised once per device, so a
+// dictionary reference in the command loop is a plain word copy from a table instead of byte-serial
+// transform logic (src/transform.rs:720-795) running with one active lane.  Entry of word `idx` of length
+// L under transform t: xdict + xdict_base(L) + (idx * 121 + t) * xdict_stride(L), holding the
+// prefix | transformed word | suffix bytes (at most L + 13), zero padded.
+#if defined(BROTLI_B200_HOSTSIM)
+#define BD_HD inline
+#else
+#define BD_HD __host__ __device__ __forceinline__
+#endif
+BD_HD uint32_t xdict_stride(uint32_t len) { return (len + 16u) & ~3u; }
+// kBrotliDictSizeBitsByLength (src/dictionary/mod.rs:3-18) for lengths 4..24, four bits per entry, so that the
+// layout is computable on the host as well (tests/hostsim checks it against the generated table)
+BD_HD uint32_t dict_size_bits(uint32_t len) {
+  if (len < 4 || len > 24) return 0;
+  return len < 20 ? (uint32_t)(0x7877899AAAAABBAAull >> ((len - 4) * 4)) & 15u : (0x55667u >> ((len - 20) * 4)) & 15u;
+}
+struct XDictLayout {
+  uint32_t base[25];
+  uint32_t total;
+};
+BD_HD XDictLayout xdict_layout() {
+  XDictLayout x;
+  uint32_t off = 0;
+  for (uint32_t l = 0; l < 25; l++) {
+    x.base[l] = off;
+    if (l >= BROTLI_MIN_DICTIONARY_WORD_LENGTH) off += (BROTLI_NUM_TRANSFORMS << dict_size_bits(l)) * xdict_stride(l);
+  }
+  x.total = off;
+  return x;
+}
+// word info [len]: (xdict_base(len) / 4) << 4 | size bits;  transform info [t]: prefix length | suffix length << 4 | type << 8
+BD_DEV uint32_t pack_word_info(const XDictLayout& x, uint32_t len) {
+  return ((x.base[len] >> 2) << 4) | dict_size_bits(len);
+}
+BD_DEV uint32_t pack_transform_info(uint32_t t) {
+  const uint8_t* prefix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[t * 3]];
+  const uint8_t* suffix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[t * 3 + 2]];
+  uint32_t plen = 0, slen = 0;
+  while (prefix[plen]) plen++;
+  while (suffix[slen]) slen++;
+  return plen | (slen << 4) | ((uint32_t)tbl::kBrotliTransforms[t * 3 + 1] << 8);
+}
+// Bytes of the word itself that survive transform `type` (omit-first / omit-last).
+BD_DEV uint32_t transformed_word_length(uint32_t len, uint32_t type) {
+  uint32_t skip = type < tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 ? 0u : type - (tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 - 1);
+  if (skip > len) skip = len;
+  int32_t wl = (int32_t)(len - skip);
+  if (type <= tbl::BROTLI_TRANSFORM_OMIT_LAST_9) wl -= (int32_t)type;
+  return wl > 0 ? (uint32_t)wl : 0u;
+}
+// TransformDictionaryWord, src/transform.rs:743-795 (+ ToUpperCase :720-741): writes one table entry.
+BD_DEV uint32_t build_xdict_entry(uint8_t* dst, const uint8_t* word, uint32_t len, uint32_t t) {
+  const uint8_t* prefix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[t * 3]];
+  const uint32_t type = tbl::kBrotliTransforms[t * 3 + 1];
+  const uint8_t* suffix = &tbl::kBrotliPrefixSuffix[tbl::kBrotliTransforms[t * 3 + 2]];
+  uint32_t n = 0;
+  while (*prefix) dst[n++] = *prefix++;
+  uint32_t skip = type < tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 ? 0u : type - (tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 - 1);
+  if (skip > len) skip = len;
+  const uint32_t wlen = transformed_word_length(len, type);
+  word += skip;
+  uint32_t upper = (type == tbl::BROTLI_TRANSFORM_UPPERCASE_FIRST || type == tbl::BROTLI_TRANSFORM_UPPERCASE_ALL) ? 1u : 0u;
+  uint32_t i = 0;
+  while (i < wlen) {  // changes ToUpperCase would make past the word's end are never visible in the output
+    const uint32_t c0 = word[i];
+    if (c0 < 0xC0 || !upper) {
+      dst[n++] = (uint8_t)((upper && c0 >= 'a' && c0 <= 'z') ? c0 ^ 32u : c0);
+      i += 1;
+    } else if (c0 < 0xE0) {
+      dst[n++] = (uint8_t)c0;
+      if (i + 1 < wlen) dst[n++] = word[i + 1] ^ 32u;
+      i += 2;
+    } else {
+      dst[n++] = (uint8_t)c0;
+      if (i + 1 < wlen) dst[n++] = word[i + 1];
+      if (i + 2 < wlen) dst[n++] = word[i + 2] ^ 5u;
+      i += 3;
+    }
+    if (type == tbl::BROTLI_TRANSFORM_UPPERCASE_FIRST) upper = 0;
+  }
+  while (*suffix) dst[n++] = *suffix++;
+  for (uint32_t j = n; j < xdict_stride(len); j++) dst[j] = 0;
+  return n;
+}
+
+// ======================= the unified symbol loop =======================
+enum : uint32_t { kStIdle = 0, kStHeader = 1, kStCommands = 2, kStFinish = 3, kStDone = 4, kStBail = 5 };
+
+// One prefix-code symbol per iteration and lane; `kind` says which.  Restates ProcessCommandsInternal
+// (src/decode.rs:2330-2744) for one metablock.  The WHOLE WARP calls this together; lanes with
+// run == false only take part in the votes, and the vote at the top of every iteration is what keeps
+// the 32 streams in lock-step (without it, lanes drift apart and the warp serialises).
+// On return st is kStHeader (metablock complete) or kStBail for every lane that ran.
+BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
+  // register copies of the hot state
+  const uint32_t* w = nullptr;
+  uint32_t lo = 0, hi = 0, nx = 0, k = 0, bp = 0, k_max = 0;
+  uint8_t* out_al = nullptr;
+  uint32_t bias = 0, capb = 0, posb = 0, acc = 0;
+  int32_t mlen = 0;
+  int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+  uint32_t bl_l = 0, bl_c = 0, bl_d = 0;
+  uint32_t max_backward = 0, npostfix = 0, ndirect = 0;
+  uint32_t r_lit = 0, r_cmd = 0, r_dist = 0, root_lit = 0;
+  // tree of the current command block type / literal block type (trivial context map)
+  uint32_t cmd_tv = 0, cmd_cold = 0, lit_tv = 0, lit_cold = 0, trivial = 0;
+  hw::sref_t ctx_lut = 0;
+  const uint8_t* ctx_map = nullptr;
+  const uint32_t E = c.E;
+  const hw::sref_t stab = c.stab;
+  uint16_t* const gtab = c.gtab;
+
+#define LN_TREES()                                                                       \
+  do {                                                                                   \
+    cmd_tv = tree_root(L, 1, L.cmd_tree); cmd_cold = c.cold_off[L.tid0[1] + L.cmd_tree]; \
+    trivial = L.trivial;                                                                 \
+    lit_tv = tree_root(L, 0, L.lit_tree); lit_cold = c.cold_off[L.tid0[0] + L.lit_tree]; \
+    ctx_lut = c.ctx_lut + L.ctx_mode_off; ctx_map = c.ctx_lit + L.ctx_slice;             \
+  } while (0)
+
+  if (run) {
+    w = L.w; lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp; k_max = L.k_max;
+    out_al = L.out_al; bias = L.bias; capb = L.capb; posb = L.posb; acc = L.acc;
+    mlen = L.mlen;
+    d0 = L.d0; d1 = L.d1; d2 = L.d2; d3 = L.d3;
+    bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];
+    max_backward = L.max_backward; npostfix = L.npostfix; ndirect = L.ndirect;
+    r_lit = L.rbits[0]; r_cmd = L.rbits[1]; r_dist = L.rbits[2]; root_lit = L.root[0];
+    LN_TREES();
+  }
+  uint32_t kind = kSymCmd;
+  uint32_t tv = cmd_tv, tr = r_cmd, tcold = cmd_cold;
+  uint32_t ins = 0, copy_len = 0, cmd_bits = 0;
+  uint32_t p1 = 0, p2 = 0;
+
+#define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
+#define LN_SKIP(n)                                                     \
+  do {                                                                 \
+    bp += (n);                                                         \
+    if (bp >= 32) {                                                    \
+      lo = hi; hi = nx; k++;                                           \
+      const uint32_t kk_ = k + 2 < k_max ? k + 2 : k_max;              \
+      nx = hw::ldg32(w + kk_);                                         \
+      bp -= 32;                                                        \
+    }                                                                  \
+  } while (0)
+#define LN_SAVE()                                                                                   \
+  do {                                                                                              \
+    L.lo = lo; L.hi = hi; L.nx = nx; L.k = k; L.bp = bp; L.posb = posb; L.acc = acc; L.mlen = mlen;  \
+    L.d0 = d0; L.d1 = d1; L.d2 = d2; L.d3 = d3; L.bl[0] = bl_l; L.bl[1] = bl_c; L.bl[2] = bl_d;     \
+  } while (0)
+// literal tree for the next literal when the block type's context map is not trivial (:2500-2507)
+#define LN_CTX_TREE()                                                          \
+  do {                                                                         \
+    const uint32_t cx_ = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);      \
+    const uint32_t ti_ = ctx_map[cx_];                                         \
+    tv = root_lit + (ti_ << r_lit); tcold = c.cold_off[L.tid0[0] + ti_];       \
+  } while (0)
+#define LN_ENTER_LIT()                                                              \
+  do {                                                                              \
+    kind = kSymLit; tr = r_lit;                                                     \
+    if (trivial) { tv = lit_tv; tcold = lit_cold; }                                 \
+    else { last_two(out_al, bias, posb, acc, p1, p2); LN_CTX_TREE(); }              \
+  } while (0)
+#define LN_ENTER_DIST()                                                      \
+  do {                                                                       \
+    const uint2 cd_ = vlds64(c.slot + ((cmd_bits >> 24) & 3u) * 8u);         \
+    kind = kSymDist; tr = r_dist; tv = cd_.x; tcold = cd_.y;                 \
+  } while (0)
+#define LN_ENTER_CMD() do { kind = kSymCmd; tr = r_cmd; tv = cmd_tv; tcold = cmd_cold; } while (0)
+
+  while (warp_any(run)) {
+    if (run) {
+      uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
+      // ---- block switch when this kind's counter ran out (:2367-2372, :2413-2424, :2567-2571) ----
+      {
+        const uint32_t blv = kind == kSymCmd ? bl_c : (kind == kSymLit ? bl_l : bl_d);
+        if (BD_UNLIKELY(blv == 0)) {
+          const uint32_t cat = kind == kSymCmd ? 1u : (kind == kSymLit ? 0u : 2u);
+          LN_SAVE();
+          const int r = block_switch(c, L, cat, bt.type_root[cat], bt.len_root[cat]);
+          lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;
+          bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];
+          LN_TREES();
+          if (r != kLaneOk) ev = kStBail;
+          else if (kind == kSymCmd) LN_ENTER_CMD();
+          else if (kind == kSymLit) LN_ENTER_LIT();
+          else LN_ENTER_DIST();
+        }
+      }
+      if (ev == kStCommands) {
+        // ---- one symbol (DecodeSymbol, :377-391, over our table shape) ----
+        const uint32_t bits = LN_PEEK();
+        uint32_t e;
+        {
+          const uint32_t v = tv + (bits & mask_bits(tr));
+          e = v < E ? vlds16(stab + (v << 1)) : (uint32_t)gtab[v - E];
+        }
+        uint32_t len = e & 15u;
+        if (BD_UNLIKELY(len > tr)) {
+          const uint32_t v = tcold + (e >> 4) + ((bits >> tr) & mask_bits(len - tr));
+          e = v < E ? vlds16(stab + (v << 1)) : (uint32_t)gtab[v - E];
+          len = e & 15u;
+        }
+        const uint32_t sym = e >> 4;
+#ifdef BD_LANE_STATS
+        BD_LANE_STATS(kind, len, tr);
+#endif
+        bool do_copy = false;
+        int32_t dist = d0;
+        uint32_t push = 0;
+        if (kind == kSymLit) {
+          // ---- literal (:2391-2551) ----
+          LN_SKIP(len);
+          bl_l--;
+          append(out_al, bias, posb, acc, sym, 1);
+          if (--ins != 0) {
+            if (!trivial) { p2 = p1; p1 = sym; LN_CTX_TREE(); }
+          } else if (mlen <= 0) {
+            ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+          } else if (cmd_bits & (1u << 26)) {
+            do_copy = true;
+          } else {
+            LN_ENTER_DIST();
+          }
+        } else if (kind == kSymCmd) {
+          // ---- insert&copy command and its extra bits (ReadCommandInternal, :2134-2189) ----
+          const uint2 lut = vlds64(c.cmd_lut + (sym << 3));
+          cmd_bits = lut.x;
+          ins = lut.x & 0xFFFFu;
+          copy_len = lut.y & 0xFFFFu;
+          const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
+          if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
+            const uint32_t x = bits >> len;
+            ins += x & mask_bits(ie);
+            copy_len += (x >> ie) & mask_bits(ce);
+            LN_SKIP(len + ie + ce);
+          } else {
+            LN_SKIP(len);
+            if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
+            if (ce) { copy_len += LN_PEEK() & mask_bits(ce); LN_SKIP(ce); }
+          }
+          bl_c--;
+          mlen -= (int32_t)ins;
+          // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
+          if (BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
+          else if (ins != 0) LN_ENTER_LIT();
+          else if (cmd_bits & (1u << 26)) do_copy = true;
+          else LN_ENTER_DIST();
+        } else {
+          // ---- distance (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049) ----
+          bl_d--;
+          do_copy = true;
+          push = 1;
+          if (sym >= 16) {
+            uint32_t base, nbits;
+            if (sym >= ndirect) {
+              const uint32_t distval = sym - ndirect;
+              const uint32_t hcode = distval >> npostfix;
+              nbits = (hcode >> 1) + 1;
+              base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
+            } else {
+              nbits = 0; base = sym - 15u;
+            }
+            uint32_t extra;
+            if (BD_LIKELY(len + nbits <= 32)) {
+              extra = (bits >> len) & mask_bits(nbits);
+              LN_SKIP(len + nbits);
+            } else {
+              LN_SKIP(len);
+              extra = LN_PEEK() & mask_bits(nbits);
+              LN_SKIP(nbits);
+            }
+            dist = (int32_t)(base + (extra << npostfix));
+          } else {
+            LN_SKIP(len);
+            if (sym == 0) {
+              push = 0;
+            } else if (sym < 4) {
+              dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
+            } else {
+              const uint32_t cc = sym - 4;
+              const int32_t b = cc < 6 ? d0 : d1;
+              const uint32_t m = cc < 6 ? cc : cc - 6;
+              const int32_t delta = (int32_t)(m >> 1) + 1;
+              dist = (m & 1) ? b + delta : b - delta;
+              if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
+            }
+          }
+        }
+        if (do_copy) {
+          // ---- copy or static dictionary word (:2583-2689) ----
+          const uint32_t pos = posb - bias;
+          const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+          const uint8_t* src = nullptr;  // aligned word holding the first source byte
+          uint32_t s8 = 0, n = 0;        // bit offset of that byte in its word; bytes to copy by words
+          if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
+            // static dictionary: the transformed word is an entry of the expanded table
+            if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
+              ev = kStBail;
+            } else {
+              const uint32_t wi = vlds32(c.word_info + copy_len * 4u);
+              const uint32_t shift = wi & 15u;
+              const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
+              const uint32_t t = word_id >> shift;
+              if (t >= BROTLI_NUM_TRANSFORMS) {
+                ev = kStBail;
+              } else {
+                const uint32_t ti = vlds32(c.transform_info + t * 4u);
+                n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
+                if (n > capb - posb) {
+                  ev = kStBail; n = 0;
+                } else {
+                  src = c.xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
+                  mlen -= (int32_t)n;
+                }
+              }
+            }
+          } else {
+            if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
+            if (BD_UNLIKELY(copy_len > capb - posb)) {
+              ev = kStBail;
+            } else {
+              mlen -= (int32_t)copy_len;
+              n = copy_len;
+              uint32_t ud = (uint32_t)dist;
+              if (BD_UNLIKELY(ud < 12)) {
+                // Short period: copy byte-wise until the period can be widened to >= 12 (a copy at distance d
+                // equals a copy at distance k*d once k*d bytes are out); the word loop does the rest.
+                const uint32_t wide = ud * ((11u + ud) / ud);
+                const uint32_t m = n < wide ? n : wide;
+                flush_partial(out_al, bias, posb, acc);
+                for (uint32_t i = 0; i < m; i++) out_al[posb + i] = out_al[posb + i - ud];
+                posb += m;
+                acc = reload_partial(out_al, posb);
+                n -= m;
+                ud = wide;
+              }
+              const uint32_t sp = posb - ud;
+              s8 = (sp & 3u) * 8u;
+              src = out_al + (sp & ~3u);
+            }
+          }
+          if (n != 0) {
+            // Word loop.  Everything below the current output word is in memory, and a distance >= 12 keeps
+            // every byte used from a loaded word (including the word carried into the next round) below it.
+            uint32_t w0 = ld32(src);
+            for (;;) {
+              const uint32_t m = n < 4 ? n : 4u;
+              uint32_t w1 = 0;
+              if (s8 + 8 * m > 32 || n > 4) w1 = ld32(src + 4);  // only words that hold source bytes are touched
+              uint32_t v = hw::funnelshift_r(w0, w1, s8);
+              if (m < 4) v &= mask_bits(8 * m);
+              append(out_al, bias, posb, acc, v, m);
+              n -= m;
+              if (n == 0) break;
+              w0 = w1;
+              src += 4;
+            }
+          }
+          if (ev == kStCommands) {
+            if (mlen <= 0) ev = kStHeader; else LN_ENTER_CMD();
+          }
+        }
+      }
+      if (ev != kStCommands) {
+        run = false;
+        st = ev;
+        LN_SAVE();
+      }
+    }
+  }
+#undef LN_PEEK
+#undef LN_SKIP
+#undef LN_SAVE
+#undef LN_TREES
+#undef LN_CTX_TREE
+#undef LN_ENTER_LIT
+#undef LN_ENTER_DIST
+#undef LN_ENTER_CMD
+}
+
+// Stream header: bit window and output cursor set-up, DecodeWindowBits (src/decode.rs:152-187).
+BD_DEV uint32_t stream_begin(Lane& L, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap) {
+  if (in_size == 0 || in_size >= ((uint64_t)1 << 31)) return kStBail;
+  const uintptr_t ia = (uintptr_t)in;
+  L.lead = (uint32_t)(ia & 3u);
+  L.w = (const uint32_t*)(ia - L.lead);
+  L.end_bit = 8 * ((uint64_t)L.lead + in_size);
+  L.k_max = (uint32_t)((L.lead + in_size - 1) >> 2);
+  L.k = 0;
+  L.bp = 8 * L.lead;
+  L.lo = hw::ldg32(L.w);
+  L.hi = hw::ldg32(L.w + (1 < L.k_max ? 1 : L.k_max));
+  L.nx = hw::ldg32(L.w + (2 < L.k_max ? 2 : L.k_max));
+  const uintptr_t oa = (uintptr_t)out;
+  L.bias = (uint32_t)(oa & 3u);
+  L.out_al = out - L.bias;
+  const uint64_t cap = out_cap > 0xF0000000ull ? 0xF0000000ull : out_cap;
+  L.capb = (uint32_t)cap + L.bias;
+  L.posb = L.bias;
+  L.acc = 0;
+  L.d0 = 4; L.d1 = 11; L.d2 = 15; L.d3 = 16;
+  L.mlen = 0; L.is_last = 0;
+  if (L.read(1) == 0) {
+    L.wbits = 16;
+  } else {
+    uint32_t n = L.read(3);
+    if (n != 0) {
+      L.wbits = 17 + n;
+    } else {
+      n = L.read(3);
+      if (n == 1) return kStBail;  // large-window marker (or invalid)
+      L.wbits = n != 0 ? 8 + n : 17;
+    }
+  }
+  L.max_backward = (1u << L.wbits) - 16;
+  return kStHeader;
+}
+
+// After the last metablock: final padding must be zero (src/decode.rs:3365-3373); flush the write combiner.
+BD_DEV uint32_t stream_finish(Lane& L, uint64_t* decoded, uint64_t* used) {
+  const uint32_t pad = (8u - (L.bp & 7u)) & 7u;
+  if (pad && L.read(pad) != 0) return kStBail;
+  if (L.overrun()) return kStBail;
+  flush_partial(L.out_al, L.bias, L.posb, L.acc);
+  *decoded = L.pos();
+  const uint64_t bitpos = (uint64_t)L.k * 32 + L.bp;
+  *used = ((bitpos + 7) >> 3) - L.lead;
+  return kStDone;
+}
+
+// One stream per lane, the whole warp together (lanes without a stream pass active == false).
+// Returns kStDone (decoded; sizes written) or kStBail (hand the stream to the exact kernel).
+BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap,
+                               uint64_t* decoded, uint64_t* used) {
+  Lane L;
+  BlockTrees bt;
+  uint32_t st = kStIdle;
+  if (active) st = stream_begin(L, in, in_size, out, out_cap);
+  for (;;) {
+    if (st == kStHeader) {
+      const int r = metablock_begin(c, L, bt);
+      st = r == kLaneOk ? kStCommands : (r == kLaneDone ? kStFinish : kStBail);
+    }
+    warp_sync();
+    if (!warp_any(st == kStCommands)) break;
+    run_commands(c, L, bt, st == kStCommands, st);
+    // METABLOCK_DONE, src/decode.rs:3345-3381: BLOCK_LENGTH_2 (:3356-3359) / truncated input
+    if (st == kStHeader && (L.mlen < 0 || L.overrun())) st = kStBail;
+    if (st == kStHeader && L.is_last) st = kStFinish;
+  }
+  if (st == kStFinish) st = stream_finish(L, decoded, used);
+  return st;
+}
+
+}  // namespace lane
+}  // namespace BD_NS

@@ -67,16 +67,39 @@ class HostSim:
     def __init__(self):
         d = os.path.join(ROOT, "tests", "hostsim")
         so = os.path.join(d, "libhostsim.so")
-        srcs = [os.path.join(d, "hostsim.cpp"), os.path.join(ROOT, "rust-brotli-decompressor_b200", "csrc", "brotli_decode_core.cuh"),
+        srcs = [os.path.join(d, "hostsim.cpp"), os.path.join(d, "hostsim_lane.cpp"),
+                os.path.join(ROOT, "rust-brotli-decompressor_b200", "csrc", "brotli_decode_core.cuh"),
+                os.path.join(ROOT, "rust-brotli-decompressor_b200", "csrc", "brotli_decode_lane.cuh"),
                 os.path.join(ROOT, "tables", "brotli_tables.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            _run(["g++", "-O2", "-g", "-shared", "-fPIC", "-o", so, srcs[0], os.path.join(ROOT, "tables", "brotli_dictionary.c"),
+            _run(["g++", "-O2", "-g", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", so, srcs[0], srcs[1], os.path.join(ROOT, "tables", "brotli_dictionary.c"),
                   '-DBROTLI_DICT_PATH="%s"' % os.path.join(ROOT, "tables", "brotli_dictionary.bin")])
         L = ctypes.CDLL(so)
         L.hostsim_decode.restype = ctypes.c_int
         L.hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_lane_decode.restype = ctypes.c_int
+        L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                          ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         self.lib = L
+
+    LANE_BAIL = 1000
+
+    def lane_decode(self, data, capacity, table_entries=430, misalign=0):
+        """Lane-per-stream (optimistic) path -> (code, bytes, input bytes used); code 1 = decoded, LANE_BAIL = the
+        path gave the stream up (the exact kernel decodes it on the device; bytes are then meaningless).
+        table_entries = u16 entries of the lane's shared-memory slot; misalign = output address modulo 4."""
+        data = bytes(data)
+        buf = ctypes.create_string_buffer(max(int(capacity), 1) + 72)
+        addr = ctypes.addressof(buf)
+        addr += (-addr) % 8 + misalign
+        off = addr - ctypes.addressof(buf)
+        n = ctypes.c_uint64(0)
+        used = ctypes.c_uint64(0)
+        code = self.lib.hostsim_lane_decode(data, len(data), addr, int(capacity), int(table_entries), ctypes.byref(n), ctypes.byref(used))
+        raw = buf.raw
+        assert raw[:off] == bytes(off) and raw[off + int(capacity):] == bytes(len(raw) - off - int(capacity)), "wrote outside the region"
+        return code, raw[off:off + n.value], used.value
 
     def decode(self, data, capacity, large_window=True):
         """-> (code, bytes): code is the BrotliDecoderErrorCode, bytes the reference's decoded_size prefix."""

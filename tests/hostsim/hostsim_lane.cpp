@@ -1,0 +1,58 @@
+// tests/hostsim/hostsim_lane.cpp -- TEST-ONLY host build of the lane-per-stream path of the CUDA decoder
+// (csrc/brotli_decode_lane.cuh).  A lane is scalar code, so the host build runs exactly the device logic
+// for one stream.  Returns 1 on success or 1000 when the optimistic path gives the stream up (the exact
+// kernel then decodes it on the device).  Not a fallback: never linked into the product.
+#define BROTLI_B200_HOSTSIM 1
+#include "../../rust-brotli-decompressor_b200/csrc/brotli_decode_lane.cuh"
+
+#include <stdlib.h>
+#include <vector>
+
+extern "C" const uint8_t kBrotliDictionaryData[];
+
+extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, uint32_t table_entries, uint64_t* decoded,
+                                   uint64_t* used) {
+  using namespace brotli_b200;
+  static std::vector<uint2> cmd_lut;
+  if (cmd_lut.empty()) { cmd_lut.resize(704); for (uint32_t i = 0; i < 704; i++) cmd_lut[i] = pack_cmd_lut(i); }
+  std::vector<uint64_t> arena((lane::ArenaLayout::kBytes + 7) / 8);
+  std::vector<uint64_t> slot((lane::kSlotHeaderBytes + 2 * (size_t)table_entries + 7) / 8 + 1);
+  uint8_t* a = (uint8_t*)arena.data();
+  lane::LaneCtx c;
+  c.slot = hw::to_sref(slot.data());
+  c.stab = c.slot + lane::kSlotHeaderBytes;
+  c.E = table_entries;
+  c.gtab = (uint16_t*)(a + lane::ArenaLayout::kTab);
+  c.cold_off = (uint32_t*)(a + lane::ArenaLayout::kColdOff);
+  c.ctx_lit = a + lane::ArenaLayout::kCtxLit;
+  c.ctx_dist = a + lane::ArenaLayout::kCtxDist;
+  c.ctx_modes = a + lane::ArenaLayout::kCtxModes;
+  c.cmd_lut = hw::to_sref(cmd_lut.data());
+  c.ctx_lut = hw::to_sref(tbl::kBrotliContextLookup);
+  c.dictionary = kBrotliDictionaryData;
+  // expanded dictionary and its two index tables (built by brotli_build_xdict_kernel on the device)
+  static std::vector<uint8_t> xdict;
+  static uint32_t word_info[25], transform_info[BROTLI_NUM_TRANSFORMS];
+  if (xdict.empty()) {
+    const lane::XDictLayout x = lane::xdict_layout();
+    xdict.resize(x.total + 64);
+    for (uint32_t len = 0; len < 25; len++) {
+      if (lane::dict_size_bits(len) != (len >= 4 ? tbl::kBrotliDictSizeBitsByLength[len] : 0u)) abort();
+      word_info[len] = lane::pack_word_info(x, len);
+    }
+    for (uint32_t t = 0; t < BROTLI_NUM_TRANSFORMS; t++) transform_info[t] = lane::pack_transform_info(t);
+    for (uint32_t len = BROTLI_MIN_DICTIONARY_WORD_LENGTH; len <= BROTLI_MAX_DICTIONARY_WORD_LENGTH; len++)
+      for (uint32_t idx = 0; idx < (1u << tbl::kBrotliDictSizeBitsByLength[len]); idx++)
+        for (uint32_t t = 0; t < BROTLI_NUM_TRANSFORMS; t++)
+          lane::build_xdict_entry(xdict.data() + x.base[len] + (size_t)(idx * BROTLI_NUM_TRANSFORMS + t) * lane::xdict_stride(len),
+                                  kBrotliDictionaryData + tbl::kBrotliDictOffsetsByLength[len] + idx * len, len, t);
+  }
+  c.xdict = xdict.data();
+  c.word_info = hw::to_sref(word_info);
+  c.transform_info = hw::to_sref(transform_info);
+  uint64_t d = 0, u = 0;
+  const uint32_t r = lane::decode_streams(c, true, in, in_size, out, cap, &d, &u);
+  *decoded = d;
+  if (used) *used = u;
+  return r == lane::kStDone ? 1 : 1000;
+}
