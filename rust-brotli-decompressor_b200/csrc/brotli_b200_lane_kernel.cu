@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   c.stab = c.slot + lane::kSlotHeaderBytes;
   c.E = (la.slot_bytes - lane::kSlotHeaderBytes) / 2;
   c.gtab = (uint16_t*)(arena + lane::ArenaLayout::kTab);
-  c.cold_off = (uint32_t*)(arena + lane::ArenaLayout::kColdOff);
   c.ctx_lit = arena + lane::ArenaLayout::kCtxLit;
   c.ctx_dist = arena + lane::ArenaLayout::kCtxDist;
   c.ctx_modes = arena + lane::ArenaLayout::kCtxModes;

@@ -5,16 +5,22 @@
 // streams has a better mapping: every lane owns a whole stream, so one issued instruction advances 32
 // bit windows / table lookups / output cursors at once.  What makes that work on the SM:
 //
-//   * unified symbol loop -- each iteration every lane decodes ONE prefix-code symbol of whatever kind
-//     its stream needs next (insert&copy command, literal, distance).  The expensive common part (peek,
-//     root-table load, bit skip, refill) is convergent; only the short per-kind tails diverge.
+//   * phased rounds -- the warp runs rounds of fixed phases: [command symbol] [retire the copy issued last
+//     round] [literal symbol, up to kMaxLitPhases times] [distance symbol + issue the copy's loads].  Each
+//     phase's code is issued once per round for all lanes that are at that point of their stream, so a
+//     lane normally completes one whole insert-and-copy command per round; warp votes at the phase
+//     boundaries keep the 32 streams converged.
+//   * nothing on a round's critical path waits for L2/HBM: backreference (and dictionary) source words
+//     are loaded at the end of a round and consumed after the next round's command decode; a symbol whose
+//     code is longer than the root table requests its second-level entry and the lane simply retries
+//     that phase next round with the entry in a register.
 //   * per-lane prefix-code tables with a SMALL root level in shared memory (a private slot per lane;
-//     32 random addresses over 32 banks cost ~3 wavefronts) and the rarely used second level in a
-//     per-lane global arena (L1/L2).  Root widths are chosen per metablock so all roots fit the slot.
+//     32 random addresses over 32 banks cost ~3 wavefronts) and the second level in a per-lane global
+//     arena.  Root widths are chosen per metablock so all roots fit the slot.
 //   * output through a 4-byte write combiner: literals and copies are appended to a partial word in a
-//     register and leave as aligned 32-bit stores; backreference sources are read as aligned words and
-//     re-aligned with a funnel shift.  Loads after stores of the SAME thread are ordered by the
-//     hardware, so no warp synchronisation is needed anywhere.
+//     register and leave as aligned 32-bit stores; copy sources are read as aligned words and re-aligned
+//     with funnel shifts.  Loads after stores of the SAME thread are ordered by the hardware, so no
+//     synchronisation is needed for the data.
 //
 // This path is OPTIMISTIC (like a fast path in front of the reference's "safe" path): it decodes
 // well-formed streams with compressed metablocks and a regular window.  Anything else -- corrupt or
@@ -42,26 +48,24 @@ namespace BD_NS {
 namespace lane {
 
 // ---- per-lane storage geometry ----
-constexpr uint32_t kSlotHeaderBytes = 32;   // cur_dist[4]: {root virtual index, second-level base} per distance context
+// shared slot: cur_dist[4] (root of the distance tree per distance context), the 64-entry literal context
+// map of the current literal block type, then E u16 table entries
+constexpr uint32_t kSlotCtxMap = 16;
+constexpr uint32_t kSlotHeaderBytes = 16 + 64;
 constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
-constexpr uint32_t kTreeIdBlock = 0;        // ids 0..2 block-type trees, 3..5 block-length trees
-constexpr uint32_t kTreeIdCtxMap = 6;       // temporary tree of a context map
-constexpr uint32_t kTreeIdGroups = 7;       // literal, command, distance trees follow
-constexpr uint32_t kMaxTreeIds = kTreeIdGroups + 3 * 256;
 constexpr uint32_t kBlockRootBits = 6;
+constexpr uint32_t kMaxLitPhases = 3;       // literal symbols a lane can decode per round
 
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
-  static constexpr size_t kColdOff = kTab + 2 * (size_t)kGlobalTab;   // u32[kMaxTreeIds]
-  static constexpr size_t kCtxLit = kColdOff + 4 * (size_t)kMaxTreeIds;  // u8[64 * kMaxBlockTypes]
+  static constexpr size_t kCtxLit = kTab + 2 * (size_t)kGlobalTab;    // u8[64 * kMaxBlockTypes]
   static constexpr size_t kCtxDist = kCtxLit + 64 * (size_t)kMaxBlockTypes;  // u8[4 * kMaxBlockTypes]
   static constexpr size_t kCtxModes = kCtxDist + 4 * (size_t)kMaxBlockTypes;  // u8[kMaxBlockTypes]
   static constexpr size_t kBytes = (kCtxModes + kMaxBlockTypes + 255) & ~size_t(255);
 };
 
 enum : int { kLaneOk = 0, kLaneDone = 1, kLaneBail = 2 };
-enum : uint32_t { kSymCmd = 0, kSymLit = 1, kSymDist = 2 };  // also the block category order of the decoder (lit=0,cmd=1,dist=2 in the reference)
 
 #if defined(BROTLI_B200_HOSTSIM)
 static inline void sts16(hw::sref_t a, uint32_t v) { *(uint16_t*)a = (uint16_t)v; }
@@ -73,6 +77,9 @@ static inline uint32_t vlds8(hw::sref_t a) { return *(const uint8_t*)a; }
 static inline uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) {
   if (s >= 32) return hi;
   return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+static inline uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high word of (hi:lo) << s, s in 0..31
+  s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
 static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
@@ -87,6 +94,7 @@ BD_DEV uint32_t vlds32(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u32 %
 BD_DEV uint32_t vlds8(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BD_DEV uint2 vlds64(hw::sref_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 BD_DEV uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
+BD_DEV uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
 BD_DEV void warp_sync() { __syncwarp(); }
@@ -101,7 +109,6 @@ struct LaneCtx {
   hw::sref_t stab;       // slot + kSlotHeaderBytes
   uint32_t E;            // entries of virtual table space that live in the shared slot
   uint16_t* gtab;        // arena: virtual entries E .. E + kGlobalTab
-  uint32_t* cold_off;    // arena: second-level base (virtual index) per tree id
   uint8_t* ctx_lit;
   uint8_t* ctx_dist;
   uint8_t* ctx_modes;
@@ -132,7 +139,7 @@ struct Lane {
   uint32_t bl[3], nbt[3], rb[6];   // category order: 0 literal, 1 command, 2 distance (reference order)
   uint32_t npostfix, ndirect, dist_alphabet;
   uint32_t n_lit, n_dist;
-  uint32_t rbits[3], root[3], tid0[3];  // per group (0 literal, 1 command, 2 distance): root width, root base, first tree id
+  uint32_t rbits[3], root[3];  // per group (0 literal, 1 command, 2 distance): root width, root base (virtual index)
   uint32_t trivial_lo, trivial_hi;      // bit i: literal block type i uses one tree for all 64 contexts
   uint32_t trivial, lit_tree, ctx_mode_off, ctx_slice, cmd_tree, dist_slice;
   uint32_t cold_next;    // next free virtual index of the arena part of the table space
@@ -165,14 +172,14 @@ BD_DEV void tab_store(const LaneCtx& c, uint32_t v, uint32_t e) {
 }
 
 // One symbol of the tree whose root (2^rbits entries) starts at virtual index root_v.
-// Entry = symbol << 4 | code length; length > rbits marks a pointer: value = offset of the second-level
-// table from cold_off[tid], length - rbits = its index width.
-BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+// Entry = symbol << 4 | code length; length > rbits marks a pointer: its second-level table starts at
+// virtual index E + 2 * value and is indexed by the next (length - rbits) bits.
+BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t rbits) {
   const uint32_t bits = L.peek();
   uint32_t e = tab_load(c, root_v + (bits & mask_bits(rbits)));
   uint32_t len = e & 15u;
   if (len > rbits) {
-    e = tab_load(c, c.cold_off[tid] + (e >> 4) + ((bits >> rbits) & mask_bits(len - rbits)));
+    e = c.gtab[((e >> 4) << 1) + ((bits >> rbits) & mask_bits(len - rbits))];
     len = e & 15u;
   }
   L.skip(len);
@@ -196,6 +203,24 @@ BD_DEV void append(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc
     acc = funnelshift_rc(v, 0u, 32u - sh);
   } else {
     acc = word;
+  }
+  posb += n;
+}
+// v_hi:v_lo holds exactly n (1..8) valid low bytes, the rest is zero
+BD_DEV void append8(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc, uint32_t v_lo, uint32_t v_hi, uint32_t n) {
+  const uint32_t a = posb & 3u, sh = a * 8u, wpos = posb & ~3u;
+  const uint32_t x0 = acc | (v_lo << sh);
+  const uint32_t x1 = funnelshift_l(v_lo, v_hi, sh);
+  const uint32_t t = a + n;
+  if (t >= 8) {
+    store_word(out_al, bias, wpos, x0);
+    st32(out_al + wpos + 4, x1);
+    acc = funnelshift_rc(v_hi, 0u, 32u - sh);
+  } else if (t >= 4) {
+    store_word(out_al, bias, wpos, x0);
+    acc = x1;
+  } else {
+    acc = x0;
   }
   posb += n;
 }
@@ -237,12 +262,10 @@ BD_DEV uint32_t bit_width(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++
 
 // Fill the lookup structure of one prefix code from its symbols sorted by (length, value).
 // count[l] = symbols of length l.  Root of 2^rbits entries at root_v; longer codes go to second-level
-// tables allocated from L.cold_next.  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
-BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const uint16_t* count, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+// tables allocated from L.cold_next (always in the arena).  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
+BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const uint16_t* count, uint32_t root_v, uint32_t rbits) {
   uint16_t rem[16];
   for (uint32_t l = 0; l < 16; l++) rem[l] = count[l];
-  const uint32_t cold_base = L.cold_next;
-  c.cold_off[tid] = cold_base;
   uint32_t code = 0, idx = 0;
   uint32_t cur_prefix = 0xFFFFFFFFu, sub_w = 0, sub_v = 0;
   for (uint32_t l = 1; l <= 15; l++) {
@@ -264,13 +287,12 @@ BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const u
             ll++; left <<= 1;
           }
           sub_w = ll - rbits;
-          sub_v = L.cold_next;
-          const uint32_t off = sub_v - cold_base;
-          if (off > 4095u || sub_v + (1u << sub_w) > c.E + kGlobalTab) return kLaneBail;
+          sub_v = L.cold_next - c.E;  // index into the arena part; every allocation there is even-sized
+          if (sub_v + (1u << sub_w) > kGlobalTab) return kLaneBail;
           L.cold_next += 1u << sub_w;
-          tab_store(c, root_v + (rev & mask_bits(rbits)), (off << 4) | (rbits + sub_w));
+          tab_store(c, root_v + (rev & mask_bits(rbits)), ((sub_v >> 1) << 4) | (rbits + sub_w));
         }
-        for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) tab_store(c, sub_v + t, e);
+        for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) c.gtab[sub_v + t] = (uint16_t)e;
       }
       code++;
       rem[l]--;
@@ -281,7 +303,7 @@ BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const u
 }
 
 // ReadHuffmanCode, src/decode.rs:868-1013: one prefix-code description -> lookup structure.
-BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits, uint32_t tid) {
+BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits) {
   uint16_t sorted[704];
   uint16_t count[16];
   for (uint32_t l = 0; l < 16; l++) count[l] = 0;
@@ -297,7 +319,6 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
     for (uint32_t i = 0; i + 1 < nsym; i++)
       for (uint32_t k = i + 1; k < nsym; k++) if (s[i] == s[k]) return kLaneBail;
     if (nsym == 1) {
-      c.cold_off[tid] = L.cold_next;
       for (uint32_t t = 0; t < (1u << rbits); t++) tab_store(c, root_v + t, s[0] << 4);
       return kLaneOk;
     }
@@ -317,7 +338,7 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
         count[l]++;
       }
     }
-    return fill_table(c, L, sorted, count, root_v, rbits, tid);
+    return fill_table(c, L, sorted, count, root_v, rbits);
   }
   // complex code: code-length code lengths (ReadCodeLengthCodeLengths, :801-853)
   uint8_t cl_cl[18];
@@ -398,20 +419,20 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
     const uint32_t l = cl[sy];
     if (l) sorted[offs[l]++] = (uint16_t)sy;
   }
-  return fill_table(c, L, sorted, count, root_v, rbits, tid);
+  return fill_table(c, L, sorted, count, root_v, rbits);
 }
 
 // A tree that lives wholly in the arena part of the table space (block-switch and context-map codes).
-BD_DEV int read_arena_tree(const LaneCtx& c, Lane& L, uint32_t alphabet, uint32_t tid, uint32_t& root_v) {
+BD_DEV int read_arena_tree(const LaneCtx& c, Lane& L, uint32_t alphabet, uint32_t& root_v) {
   root_v = L.cold_next;
   if (root_v + (1u << kBlockRootBits) > c.E + kGlobalTab) return kLaneBail;
   L.cold_next += 1u << kBlockRootBits;
-  return read_huffman_code(c, L, alphabet, alphabet, root_v, kBlockRootBits, tid);
+  return read_huffman_code(c, L, alphabet, alphabet, root_v, kBlockRootBits);
 }
 
 // ReadBlockLength, src/decode.rs:1016-1026
-BD_DEV uint32_t read_block_length(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t tid) {
-  const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits, tid);
+BD_DEV uint32_t read_block_length(const LaneCtx& c, Lane& L, uint32_t root_v) {
+  const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits);
   if (code >= 26) return 0;  // cannot happen for a 26-symbol alphabet
   return tbl::kBrotliBlockLengthOffset[code] + L.read(tbl::kBrotliBlockLengthNBits[code]);
 }
@@ -428,10 +449,10 @@ BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_
   if (b5 & 1u) { rle_max = (b5 >> 1) + 1; L.skip(5); } else { L.skip(1); }
   const uint32_t saved_cold = L.cold_next;
   uint32_t root_v;
-  if (read_arena_tree(c, L, ntrees + rle_max, kTreeIdCtxMap, root_v) != kLaneOk) return kLaneBail;
+  if (read_arena_tree(c, L, ntrees + rle_max, root_v) != kLaneOk) return kLaneBail;
   uint32_t i = 0;
   while (i < size) {
-    const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits, kTreeIdCtxMap);
+    const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits);
     if (code == 0) { map[i++] = 0; continue; }
     if (code > rle_max) { map[i++] = (uint8_t)(code - rle_max); continue; }
     uint32_t reps = (1u << code) + L.read(code);
@@ -457,12 +478,11 @@ BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_
 // Virtual root index of tree i of group g.
 BD_DEV uint32_t tree_root(const Lane& L, uint32_t g, uint32_t i) { return L.root[g] + (i << L.rbits[g]); }
 
-// Distance-context -> {root, second-level base} of the current distance block type, kept in the shared slot.
+// Distance-context -> root of its tree for the current distance block type, kept in the shared slot.
 BD_DEV void refresh_cur_dist(const LaneCtx& c, const Lane& L) {
   for (uint32_t ctx = 0; ctx < 4; ctx++) {
     const uint32_t t = c.ctx_dist[L.dist_slice + ctx];
-    sts32(c.slot + ctx * 8, tree_root(L, 2, t));
-    sts32(c.slot + ctx * 8 + 4, c.cold_off[L.tid0[2] + t]);
+    sts32(c.slot + ctx * 4, tree_root(L, 2, t));
   }
 }
 
@@ -473,6 +493,9 @@ BD_DEV void prepare_literal(const LaneCtx& c, Lane& L) {
   L.trivial = ((bt < 32 ? L.trivial_lo >> bt : L.trivial_hi >> (bt - 32)) & 1u);
   L.lit_tree = c.ctx_lit[L.ctx_slice];
   L.ctx_mode_off = (uint32_t)(c.ctx_modes[bt] & 3u) * 512u;
+  if (!L.trivial) {  // the command loop reads the block type's context map from the shared slot
+    for (uint32_t j = 0; j < 64; j += 4) sts32(c.slot + kSlotCtxMap + j, ld32(c.ctx_lit + L.ctx_slice + j));
+  }
 }
 
 // DecodeBlockTypeAndLength + Decode{Literal,Command,Distance}BlockSwitch, src/decode.rs:1469-1658.
@@ -480,8 +503,8 @@ BD_DEV void prepare_literal(const LaneCtx& c, Lane& L) {
 BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, uint32_t type_root, uint32_t len_root) {
   const uint32_t nbt = L.nbt[cat];
   if (nbt < 2) return kLaneBail;  // the counter of a single block type can only run out in a corrupt stream
-  uint32_t bt = decode_generic(c, L, type_root, kBlockRootBits, kTreeIdBlock + cat);
-  L.bl[cat] = read_block_length(c, L, len_root, kTreeIdBlock + 3 + cat);
+  uint32_t bt = decode_generic(c, L, type_root, kBlockRootBits);
+  L.bl[cat] = read_block_length(c, L, len_root);
   uint32_t* rb = &L.rb[2 * cat];
   if (bt == 1) bt = rb[1] + 1;
   else if (bt == 0) bt = rb[0];
@@ -523,9 +546,9 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     bt.type_root[k] = bt.len_root[k] = 0;
     if (L.nbt[k] >= 2) {
       if (L.nbt[k] > kMaxBlockTypes) return kLaneBail;
-      if (read_arena_tree(c, L, L.nbt[k] + 2, kTreeIdBlock + k, bt.type_root[k]) != kLaneOk) return kLaneBail;
-      if (read_arena_tree(c, L, 26, kTreeIdBlock + 3 + k, bt.len_root[k]) != kLaneOk) return kLaneBail;
-      L.bl[k] = read_block_length(c, L, bt.len_root[k], kTreeIdBlock + 3 + k);
+      if (read_arena_tree(c, L, L.nbt[k] + 2, bt.type_root[k]) != kLaneOk) return kLaneBail;
+      if (read_arena_tree(c, L, 26, bt.len_root[k]) != kLaneOk) return kLaneBail;
+      L.bl[k] = read_block_length(c, L, bt.len_root[k]);
     }
     if (L.overrun()) return kLaneBail;
   }
@@ -576,17 +599,17 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     }
     L.rbits[g] = rb[g];
   }
-  L.tid0[0] = kTreeIdGroups;
-  L.tid0[1] = L.tid0[0] + L.n_lit;
-  L.tid0[2] = L.tid0[1] + L.nbt[1];
   // HuffmanTreeGroupDecode x3, :1130-1219
   const uint32_t alpha[3] = {256, 704, L.dist_alphabet};
   for (uint32_t g = 0; g < 3; g++) {
     for (uint32_t i = 0; i < ntrees[g]; i++) {
-      if (read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g], L.tid0[g] + i) != kLaneOk) return kLaneBail;
+      if (read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g]) != kLaneOk) return kLaneBail;
       if (L.overrun()) return kLaneBail;
     }
   }
+#ifdef BD_LANE_MB_STATS
+  BD_LANE_MB_STATS(c, L);
+#endif
   prepare_literal(c, L);
   L.cmd_tree = 0;
   L.dist_slice = 0;
@@ -681,14 +704,13 @@ BD_DEV uint32_t build_xdict_entry(uint8_t* dst, const uint8_t* word, uint32_t le
   return n;
 }
 
-// ======================= the unified symbol loop =======================
+// ======================= the command loop: phased rounds =======================
 enum : uint32_t { kStIdle = 0, kStHeader = 1, kStCommands = 2, kStFinish = 3, kStDone = 4, kStBail = 5 };
+enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a lane's stream needs next
 
-// One prefix-code symbol per iteration and lane; `kind` says which.  Restates ProcessCommandsInternal
-// (src/decode.rs:2330-2744) for one metablock.  The WHOLE WARP calls this together; lanes with
-// run == false only take part in the votes, and the vote at the top of every iteration is what keeps
-// the 32 streams in lock-step (without it, lanes drift apart and the warp serialises).
-// On return st is kStHeader (metablock complete) or kStBail for every lane that ran.
+// Restates ProcessCommandsInternal (src/decode.rs:2330-2744) for one metablock.  The WHOLE WARP calls
+// this together; lanes with run == false only take part in the votes.  On return st is kStHeader
+// (metablock complete) or kStBail for every lane that ran.
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
   // register copies of the hot state
   const uint32_t* w = nullptr;
@@ -700,20 +722,18 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t bl_l = 0, bl_c = 0, bl_d = 0;
   uint32_t max_backward = 0, npostfix = 0, ndirect = 0;
   uint32_t r_lit = 0, r_cmd = 0, r_dist = 0, root_lit = 0;
-  // tree of the current command block type / literal block type (trivial context map)
-  uint32_t cmd_tv = 0, cmd_cold = 0, lit_tv = 0, lit_cold = 0, trivial = 0;
+  uint32_t cmd_tv = 0, lit_tv = 0, trivial = 0;  // trees of the current command / literal block type
   hw::sref_t ctx_lut = 0;
-  const uint8_t* ctx_map = nullptr;
   const uint32_t E = c.E;
   const hw::sref_t stab = c.stab;
-  uint16_t* const gtab = c.gtab;
+  const uint16_t* const gtab = c.gtab;
 
-#define LN_TREES()                                                                       \
-  do {                                                                                   \
-    cmd_tv = tree_root(L, 1, L.cmd_tree); cmd_cold = c.cold_off[L.tid0[1] + L.cmd_tree]; \
-    trivial = L.trivial;                                                                 \
-    lit_tv = tree_root(L, 0, L.lit_tree); lit_cold = c.cold_off[L.tid0[0] + L.lit_tree]; \
-    ctx_lut = c.ctx_lut + L.ctx_mode_off; ctx_map = c.ctx_lit + L.ctx_slice;             \
+#define LN_TREES()                                                          \
+  do {                                                                      \
+    cmd_tv = tree_root(L, 1, L.cmd_tree);                                   \
+    trivial = L.trivial;                                                    \
+    lit_tv = tree_root(L, 0, L.lit_tree);                                   \
+    ctx_lut = c.ctx_lut + L.ctx_mode_off;                                   \
   } while (0)
 
   if (run) {
@@ -726,10 +746,17 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     r_lit = L.rbits[0]; r_cmd = L.rbits[1]; r_dist = L.rbits[2]; root_lit = L.root[0];
     LN_TREES();
   }
-  uint32_t kind = kSymCmd;
-  uint32_t tv = cmd_tv, tr = r_cmd, tcold = cmd_cold;
+  uint32_t ph = kPhCmd;
   uint32_t ins = 0, copy_len = 0, cmd_bits = 0;
   uint32_t p1 = 0, p2 = 0;
+  bool ctx_fresh = false;     // p1/p2 hold the last two output bytes (non-trivial literal contexts)
+  // copy chunk in flight: up to 8 source bytes in three aligned words, shifted by pend_s8 bits
+  uint32_t pw0 = 0, pw1 = 0, pw2 = 0, pend_n = 0, pend_s8 = 0;
+  const uint8_t* csrc = nullptr;  // next aligned source word of a copy longer than one chunk
+  uint32_t crem = 0;              // its remaining bytes
+  // second-level table entry requested in an earlier round for the symbol this lane is waiting to decode
+  uint32_t de = 0;
+  bool dhave = false;
 
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
 #define LN_SKIP(n)                                                     \
@@ -747,82 +774,72 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     L.lo = lo; L.hi = hi; L.nx = nx; L.k = k; L.bp = bp; L.posb = posb; L.acc = acc; L.mlen = mlen;  \
     L.d0 = d0; L.d1 = d1; L.d2 = d2; L.d3 = d3; L.bl[0] = bl_l; L.bl[1] = bl_c; L.bl[2] = bl_d;     \
   } while (0)
-// literal tree for the next literal when the block type's context map is not trivial (:2500-2507)
-#define LN_CTX_TREE()                                                          \
-  do {                                                                         \
-    const uint32_t cx_ = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);      \
-    const uint32_t ti_ = ctx_map[cx_];                                         \
-    tv = root_lit + (ti_ << r_lit); tcold = c.cold_off[L.tid0[0] + ti_];       \
+// block switch of category CAT (0 literal, 1 command, 2 distance); rare, so the state takes a round trip
+// through local memory (:2367-2372, :2413-2424, :2567-2571)
+#define LN_BLOCK_SWITCH(CAT)                                                          \
+  do {                                                                                \
+    LN_SAVE();                                                                        \
+    const int r_ = block_switch(c, L, CAT, bt.type_root[CAT], bt.len_root[CAT]);      \
+    lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;                              \
+    bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];                                   \
+    LN_TREES();                                                                       \
+    ctx_fresh = false;                                                                \
+    if (r_ != kLaneOk) ev = kStBail;                                                  \
   } while (0)
-#define LN_ENTER_LIT()                                                              \
-  do {                                                                              \
-    kind = kSymLit; tr = r_lit;                                                     \
-    if (trivial) { tv = lit_tv; tcold = lit_cold; }                                 \
-    else { last_two(out_al, bias, posb, acc, p1, p2); LN_CTX_TREE(); }              \
+// One symbol of the tree rooted at TV (root width TR): sets BITS (the 32-bit peek), LEN and SYM, or -- when
+// the code is longer than the root -- requests the second-level entry and sets WAIT: the lane retries
+// this phase next round with the entry in `de` (DecodeSymbol, :377-391, over our table shape).
+#define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
+  do {                                                                                           \
+    BITS = LN_PEEK();                                                                            \
+    uint32_t e_;                                                                                 \
+    if (BD_UNLIKELY(dhave)) {                                                                    \
+      e_ = de; dhave = false;                                                                    \
+    } else {                                                                                     \
+      const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                         \
+      e_ = v_ < E ? vlds16(stab + (v_ << 1)) : (uint32_t)gtab[v_ - E];                           \
+      if (BD_UNLIKELY((e_ & 15u) > (TR))) {                                                      \
+        de = gtab[((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits((e_ & 15u) - (TR)))];           \
+        dhave = true; WAIT = true;                                                               \
+      }                                                                                          \
+    }                                                                                            \
+    LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
-#define LN_ENTER_DIST()                                                      \
-  do {                                                                       \
-    const uint2 cd_ = vlds64(c.slot + ((cmd_bits >> 24) & 3u) * 8u);         \
-    kind = kSymDist; tr = r_dist; tv = cd_.x; tcold = cd_.y;                 \
+// loads of the next copy chunk: min(crem, 8) bytes starting pend_s8 bits into the aligned word at csrc;
+// only words that hold source bytes are touched
+#define LN_ISSUE_CHUNK()                                                   \
+  do {                                                                     \
+    pend_n = crem < 8 ? crem : 8u;                                         \
+    crem -= pend_n;                                                        \
+    const uint32_t end_ = pend_s8 + 8 * pend_n;                            \
+    pw0 = ld32(csrc);                                                      \
+    pw1 = end_ > 32 ? ld32(csrc + 4) : 0u;                                 \
+    pw2 = end_ > 64 ? ld32(csrc + 8) : 0u;                                 \
+    csrc += 8;                                                             \
   } while (0)
-#define LN_ENTER_CMD() do { kind = kSymCmd; tr = r_cmd; tv = cmd_tv; tcold = cmd_cold; } while (0)
+// append the chunk in flight to the output
+#define LN_RETIRE_CHUNK()                                                  \
+  do {                                                                     \
+    uint32_t v_lo_ = hw::funnelshift_r(pw0, pw1, pend_s8);                 \
+    uint32_t v_hi_ = hw::funnelshift_r(pw1, pw2, pend_s8);                 \
+    if (pend_n < 4) v_lo_ &= mask_bits(8 * pend_n);                        \
+    if (pend_n <= 4) v_hi_ = 0;                                            \
+    else if (pend_n < 8) v_hi_ &= mask_bits(8 * (pend_n - 4));             \
+    append8(out_al, bias, posb, acc, v_lo_, v_hi_, pend_n);                \
+    pend_n = 0;                                                            \
+  } while (0)
 
   while (warp_any(run)) {
-    if (run) {
-      uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
-      // ---- block switch when this kind's counter ran out (:2367-2372, :2413-2424, :2567-2571) ----
-      {
-        const uint32_t blv = kind == kSymCmd ? bl_c : (kind == kSymLit ? bl_l : bl_d);
-        if (BD_UNLIKELY(blv == 0)) {
-          const uint32_t cat = kind == kSymCmd ? 1u : (kind == kSymLit ? 0u : 2u);
-          LN_SAVE();
-          const int r = block_switch(c, L, cat, bt.type_root[cat], bt.len_root[cat]);
-          lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;
-          bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];
-          LN_TREES();
-          if (r != kLaneOk) ev = kStBail;
-          else if (kind == kSymCmd) LN_ENTER_CMD();
-          else if (kind == kSymLit) LN_ENTER_LIT();
-          else LN_ENTER_DIST();
-        }
-      }
+    uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
+
+    // ---- phase A: insert&copy command and its extra bits (ReadCommandInternal, :2134-2189) ----
+    if (run && ph == kPhCmd) {
+      if (BD_UNLIKELY(bl_c == 0)) LN_BLOCK_SWITCH(1);
       if (ev == kStCommands) {
-        // ---- one symbol (DecodeSymbol, :377-391, over our table shape) ----
-        const uint32_t bits = LN_PEEK();
-        uint32_t e;
-        {
-          const uint32_t v = tv + (bits & mask_bits(tr));
-          e = v < E ? vlds16(stab + (v << 1)) : (uint32_t)gtab[v - E];
-        }
-        uint32_t len = e & 15u;
-        if (BD_UNLIKELY(len > tr)) {
-          const uint32_t v = tcold + (e >> 4) + ((bits >> tr) & mask_bits(len - tr));
-          e = v < E ? vlds16(stab + (v << 1)) : (uint32_t)gtab[v - E];
-          len = e & 15u;
-        }
-        const uint32_t sym = e >> 4;
-#ifdef BD_LANE_STATS
-        BD_LANE_STATS(kind, len, tr);
-#endif
-        bool do_copy = false;
-        int32_t dist = d0;
-        uint32_t push = 0;
-        if (kind == kSymLit) {
-          // ---- literal (:2391-2551) ----
-          LN_SKIP(len);
-          bl_l--;
-          append(out_al, bias, posb, acc, sym, 1);
-          if (--ins != 0) {
-            if (!trivial) { p2 = p1; p1 = sym; LN_CTX_TREE(); }
-          } else if (mlen <= 0) {
-            ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
-          } else if (cmd_bits & (1u << 26)) {
-            do_copy = true;
-          } else {
-            LN_ENTER_DIST();
-          }
-        } else if (kind == kSymCmd) {
-          // ---- insert&copy command and its extra bits (ReadCommandInternal, :2134-2189) ----
+        uint32_t bits, len, sym;
+        bool wait = false;
+        LN_DECODE(cmd_tv, r_cmd, bits, len, sym, wait);
+        if (!wait) {
           const uint2 lut = vlds64(c.cmd_lut + (sym << 3));
           cmd_bits = lut.x;
           ins = lut.x & 0xFFFFu;
@@ -840,142 +857,191 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           }
           bl_c--;
           mlen -= (int32_t)ins;
-          // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
-          if (BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
-          else if (ins != 0) LN_ENTER_LIT();
-          else if (cmd_bits & (1u << 26)) do_copy = true;
-          else LN_ENTER_DIST();
-        } else {
-          // ---- distance (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049) ----
-          bl_d--;
-          do_copy = true;
-          push = 1;
-          if (sym >= 16) {
-            uint32_t base, nbits;
-            if (sym >= ndirect) {
-              const uint32_t distval = sym - ndirect;
-              const uint32_t hcode = distval >> npostfix;
-              nbits = (hcode >> 1) + 1;
-              base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
-            } else {
-              nbits = 0; base = sym - 15u;
+          ph = ins != 0 ? kPhLit : kPhDist;
+          ctx_fresh = false;
+        }
+      }
+    }
+    warp_sync();
+
+    // ---- phase P: retire the copy chunk issued in an earlier round; keep a long copy going ----
+    if (run && pend_n != 0) {
+      LN_RETIRE_CHUNK();
+      if (crem != 0) {
+        LN_ISSUE_CHUNK();
+        if (crem == 0) ph = kPhCmd;  // last chunk in flight: the next command can be decoded meanwhile
+      }
+    }
+    // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
+    if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
+
+    // ---- phase B: literals (:2391-2551), up to kMaxLitPhases per round ----
+    for (uint32_t rep = 0; rep < kMaxLitPhases; rep++) {
+      if (!warp_any(run && ph == kPhLit && ev == kStCommands)) break;
+      if (run && ph == kPhLit && ev == kStCommands) {
+        if (BD_UNLIKELY(bl_l == 0)) LN_BLOCK_SWITCH(0);
+        if (ev == kStCommands) {
+          uint32_t tv = lit_tv;
+          if (!trivial) {  // tree by the context of the last two bytes (:2500-2507)
+            if (!ctx_fresh) { last_two(out_al, bias, posb, acc, p1, p2); ctx_fresh = true; }
+            const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
+            tv = root_lit + (vlds8(c.slot + kSlotCtxMap + cx) << r_lit);
+          }
+          uint32_t bits, len, sym;
+          bool wait = false;
+          LN_DECODE(tv, r_lit, bits, len, sym, wait);
+          if (!wait) {
+            LN_SKIP(len);
+            bl_l--;
+            append(out_al, bias, posb, acc, sym, 1);
+            p2 = p1; p1 = sym;
+            if (--ins == 0) {
+              if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+              else ph = kPhDist;
             }
-            uint32_t extra;
-            if (BD_LIKELY(len + nbits <= 32)) {
-              extra = (bits >> len) & mask_bits(nbits);
-              LN_SKIP(len + nbits);
+          }
+        }
+      }
+    }
+    warp_sync();
+
+    // ---- phase C: distance (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049),
+    //      then the copy or static dictionary word (:2583-2689) whose source loads are issued here ----
+    if (run && ph == kPhDist && ev == kStCommands) {
+      int32_t dist = d0;
+      uint32_t push = 0;
+      bool wait = false;
+      if (!(cmd_bits & (1u << 26))) {  // explicit distance symbol
+        if (BD_UNLIKELY(bl_d == 0)) LN_BLOCK_SWITCH(2);
+        if (ev == kStCommands) {
+          const uint32_t tv = vlds32(c.slot + ((cmd_bits >> 24) & 3u) * 4u);
+          uint32_t bits, len, sym;
+          LN_DECODE(tv, r_dist, bits, len, sym, wait);
+          if (!wait) {
+            bl_d--;
+            push = 1;
+            if (sym >= 16) {
+              uint32_t base, nbits;
+              if (sym >= ndirect) {
+                const uint32_t distval = sym - ndirect;
+                const uint32_t hcode = distval >> npostfix;
+                nbits = (hcode >> 1) + 1;
+                base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
+              } else {
+                nbits = 0; base = sym - 15u;
+              }
+              uint32_t extra;
+              if (BD_LIKELY(len + nbits <= 32)) {
+                extra = (bits >> len) & mask_bits(nbits);
+                LN_SKIP(len + nbits);
+              } else {
+                LN_SKIP(len);
+                extra = LN_PEEK() & mask_bits(nbits);
+                LN_SKIP(nbits);
+              }
+              dist = (int32_t)(base + (extra << npostfix));
             } else {
               LN_SKIP(len);
-              extra = LN_PEEK() & mask_bits(nbits);
-              LN_SKIP(nbits);
-            }
-            dist = (int32_t)(base + (extra << npostfix));
-          } else {
-            LN_SKIP(len);
-            if (sym == 0) {
-              push = 0;
-            } else if (sym < 4) {
-              dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
-            } else {
-              const uint32_t cc = sym - 4;
-              const int32_t b = cc < 6 ? d0 : d1;
-              const uint32_t m = cc < 6 ? cc : cc - 6;
-              const int32_t delta = (int32_t)(m >> 1) + 1;
-              dist = (m & 1) ? b + delta : b - delta;
-              if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
+              if (sym == 0) {
+                push = 0;
+              } else if (sym < 4) {
+                dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
+              } else {
+                const uint32_t cc = sym - 4;
+                const int32_t b = cc < 6 ? d0 : d1;
+                const uint32_t m = cc < 6 ? cc : cc - 6;
+                const int32_t delta = (int32_t)(m >> 1) + 1;
+                dist = (m & 1) ? b + delta : b - delta;
+                if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
+              }
             }
           }
         }
-        if (do_copy) {
-          // ---- copy or static dictionary word (:2583-2689) ----
-          const uint32_t pos = posb - bias;
-          const uint32_t max_distance = pos < max_backward ? pos : max_backward;
-          const uint8_t* src = nullptr;  // aligned word holding the first source byte
-          uint32_t s8 = 0, n = 0;        // bit offset of that byte in its word; bytes to copy by words
-          if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
-            // static dictionary: the transformed word is an entry of the expanded table
-            if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
+      }
+      if (!wait && ev == kStCommands) {
+        const uint32_t pos = posb - bias;
+        const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+        crem = 0;
+        if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
+          // static dictionary: the transformed word is an entry of the expanded table
+          if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
+            ev = kStBail;
+          } else {
+            const uint32_t wi = vlds32(c.word_info + copy_len * 4u);
+            const uint32_t shift = wi & 15u;
+            const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
+            const uint32_t t = word_id >> shift;
+            if (t >= BROTLI_NUM_TRANSFORMS) {
               ev = kStBail;
             } else {
-              const uint32_t wi = vlds32(c.word_info + copy_len * 4u);
-              const uint32_t shift = wi & 15u;
-              const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
-              const uint32_t t = word_id >> shift;
-              if (t >= BROTLI_NUM_TRANSFORMS) {
+              const uint32_t ti = vlds32(c.transform_info + t * 4u);
+              const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
+              if (n > capb - posb) {
                 ev = kStBail;
               } else {
-                const uint32_t ti = vlds32(c.transform_info + t * 4u);
-                n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
-                if (n > capb - posb) {
-                  ev = kStBail; n = 0;
-                } else {
-                  src = c.xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
-                  mlen -= (int32_t)n;
-                }
+                csrc = c.xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
+                pend_s8 = 0;
+                crem = n;
+                mlen -= (int32_t)n;
               }
             }
+          }
+        } else {
+          if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
+          if (BD_UNLIKELY(copy_len > capb - posb)) {
+            ev = kStBail;
           } else {
-            if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
-            if (BD_UNLIKELY(copy_len > capb - posb)) {
-              ev = kStBail;
-            } else {
-              mlen -= (int32_t)copy_len;
-              n = copy_len;
-              uint32_t ud = (uint32_t)dist;
-              if (BD_UNLIKELY(ud < 12)) {
-                // Short period: copy byte-wise until the period can be widened to >= 12 (a copy at distance d
-                // equals a copy at distance k*d once k*d bytes are out); the word loop does the rest.
-                const uint32_t wide = ud * ((11u + ud) / ud);
-                const uint32_t m = n < wide ? n : wide;
-                flush_partial(out_al, bias, posb, acc);
-                for (uint32_t i = 0; i < m; i++) out_al[posb + i] = out_al[posb + i - ud];
-                posb += m;
-                acc = reload_partial(out_al, posb);
-                n -= m;
-                ud = wide;
-              }
-              const uint32_t sp = posb - ud;
-              s8 = (sp & 3u) * 8u;
-              src = out_al + (sp & ~3u);
+            mlen -= (int32_t)copy_len;
+            crem = copy_len;
+            uint32_t ud = (uint32_t)dist;
+            if (BD_UNLIKELY(ud < 12)) {
+              // Short period: copy byte-wise until the period can be widened to >= 12 (a copy at distance d
+              // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
+              const uint32_t wide = ud * ((11u + ud) / ud);
+              const uint32_t m = crem < wide ? crem : wide;
+              flush_partial(out_al, bias, posb, acc);
+              for (uint32_t i = 0; i < m; i++) out_al[posb + i] = out_al[posb + i - ud];
+              posb += m;
+              acc = reload_partial(out_al, posb);
+              crem -= m;
+              ud = wide;
             }
+            // Everything below the current output word is in memory, and a distance >= 12 keeps the eight
+            // source bytes of every chunk below that word at the time the chunk is loaded.
+            const uint32_t sp = posb - ud;
+            pend_s8 = (sp & 3u) * 8u;
+            csrc = out_al + (sp & ~3u);
           }
-          if (n != 0) {
-            // Word loop.  Everything below the current output word is in memory, and a distance >= 12 keeps
-            // every byte used from a loaded word (including the word carried into the next round) below it.
-            uint32_t w0 = ld32(src);
-            for (;;) {
-              const uint32_t m = n < 4 ? n : 4u;
-              uint32_t w1 = 0;
-              if (s8 + 8 * m > 32 || n > 4) w1 = ld32(src + 4);  // only words that hold source bytes are touched
-              uint32_t v = hw::funnelshift_r(w0, w1, s8);
-              if (m < 4) v &= mask_bits(8 * m);
-              append(out_al, bias, posb, acc, v, m);
-              n -= m;
-              if (n == 0) break;
-              w0 = w1;
-              src += 4;
+        }
+        if (ev == kStCommands) {
+          if (crem != 0) LN_ISSUE_CHUNK();
+          if (mlen <= 0) {
+            // end of the metablock: drain the copy now
+            while (pend_n != 0) {
+              LN_RETIRE_CHUNK();
+              if (crem != 0) LN_ISSUE_CHUNK();
             }
-          }
-          if (ev == kStCommands) {
-            if (mlen <= 0) ev = kStHeader; else LN_ENTER_CMD();
+            ev = kStHeader;
+          } else {
+            ph = crem != 0 ? kPhCopy : kPhCmd;
           }
         }
       }
-      if (ev != kStCommands) {
-        run = false;
-        st = ev;
-        LN_SAVE();
-      }
+    }
+    if (run && ev != kStCommands) {
+      run = false;
+      st = ev;
+      LN_SAVE();
     }
   }
 #undef LN_PEEK
 #undef LN_SKIP
 #undef LN_SAVE
 #undef LN_TREES
-#undef LN_CTX_TREE
-#undef LN_ENTER_LIT
-#undef LN_ENTER_DIST
-#undef LN_ENTER_CMD
+#undef LN_BLOCK_SWITCH
+#undef LN_DECODE
+#undef LN_ISSUE_CHUNK
+#undef LN_RETIRE_CHUNK
 }
 
 // Stream header: bit window and output cursor set-up, DecodeWindowBits (src/decode.rs:152-187).

@@ -23,7 +23,6 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
   c.stab = c.slot + lane::kSlotHeaderBytes;
   c.E = table_entries;
   c.gtab = (uint16_t*)(a + lane::ArenaLayout::kTab);
-  c.cold_off = (uint32_t*)(a + lane::ArenaLayout::kColdOff);
   c.ctx_lit = a + lane::ArenaLayout::kCtxLit;
   c.ctx_dist = a + lane::ArenaLayout::kCtxDist;
   c.ctx_modes = a + lane::ArenaLayout::kCtxModes;
