@@ -32,7 +32,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   uint8_t* const arena = la.arena + glane * lane::ArenaLayout::kBytes;
 
   lane::LaneCtx c;
-  c.slot = hw::to_sref(s_dyn + (size_t)threadIdx.x * la.slot_bytes);
+  // dynamic shared memory: the input rings of all lanes (two 16-byte blocks each, block-interleaved so that
+  // lanes spread over the banks), then one table slot per lane
+  c.ring = hw::to_sref(s_dyn + (size_t)threadIdx.x * 16);
+  c.ring_stride = WARPS * 32 * 16;
+  c.hist = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 32 + (size_t)threadIdx.x * 32);  // 32-byte output history ring
+  c.stage = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 64 + (size_t)threadIdx.x * 48);  // cp.async landing zone
+  c.slot = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 112 + (size_t)threadIdx.x * la.slot_bytes);
   c.stab = c.slot + lane::kSlotHeaderBytes;
   c.E = (la.slot_bytes - lane::kSlotHeaderBytes) / 2;
   c.gtab = (uint16_t*)(arena + lane::ArenaLayout::kTab);
@@ -112,7 +118,7 @@ size_t lane_arena_bytes_per_lane() { return lane::ArenaLayout::kBytes; }
 // words so that equal offsets in different lanes' slots fall into different banks.
 uint32_t lane_slot_bytes(int warps) {
   const uint32_t static_bytes = 704 * 8 + 2048 + 4 * (25 + BROTLI_NUM_TRANSFORMS) + 1024 + 128;  // the LUTs + the runtime's reserve
-  uint32_t per_lane = (232448u - static_bytes) / (uint32_t)(warps * 32);
+  uint32_t per_lane = (232448u - static_bytes) / (uint32_t)(warps * 32) - 112u;  // 112: the lane's input ring (32), output history ring (32) and cp.async landing zone (48)
   uint32_t words = per_lane / 4;
   if ((words & 1u) == 0) words--;
   return words * 4;
@@ -121,7 +127,7 @@ uint32_t lane_slot_bytes(int warps) {
 int query_lane_resident_ctas(int device, int warps) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-  const uint32_t dyn = lane_slot_bytes(warps) * (uint32_t)(warps * 32);
+  const uint32_t dyn = (lane_slot_bytes(warps) + 112u) * (uint32_t)(warps * 32);
   int per_sm = -1;
   switch (warps) {
     case 2: per_sm = lane_occupancy<2>(dyn); break;
@@ -141,7 +147,7 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
-  const uint32_t dyn = la.slot_bytes * (uint32_t)(warps * 32);
+  const uint32_t dyn = (la.slot_bytes + 112u) * (uint32_t)(warps * 32);
   switch (warps) {
     case 2: brotli_decode_lane_kernel<2><<<ctas, 64, dyn, stream>>>(a, la); break;
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;

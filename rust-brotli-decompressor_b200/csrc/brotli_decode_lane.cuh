@@ -55,7 +55,10 @@ constexpr uint32_t kSlotHeaderBytes = 16 + 64;
 constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
 constexpr uint32_t kBlockRootBits = 6;
-constexpr uint32_t kMaxLitPhases = 3;       // literal symbols a lane can decode per round
+#ifndef BD_LANE_LIT_PHASES
+#define BD_LANE_LIT_PHASES 3
+#endif
+constexpr uint32_t kMaxLitPhases = BD_LANE_LIT_PHASES;  // literal symbols a lane can decode per round
 
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
@@ -85,6 +88,16 @@ static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); re
 static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
 static inline void warp_sync() {}
 static inline bool warp_any(bool p) { return p; }
+#define BD_PIN32(x) ((void)0)
+#define BD_PIN64(x) ((void)0)
+static inline void ld32_if(bool cond, const uint8_t* p, uint32_t& dst) { if (cond) memcpy(&dst, p, 4); }
+static inline void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) { if (cond) dst = *p; }
+// asynchronous 16-byte copy global -> "shared": immediate on the host
+static inline void cp_async16(hw::sref_t dst, const uint8_t* src) { memcpy((void*)dst, src, 16); }
+static inline void cp_async16_if(bool cond, hw::sref_t dst, const void* src) { if (cond) memcpy((void*)dst, src, 16); }
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_all_but_latest() {}
+static inline void cp_async_wait_all() {}
 #else
 // volatile: these loads follow stores to the same slot (table fill) made through asm as well
 BD_DEV void sts16(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
@@ -97,7 +110,35 @@ BD_DEV uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __
 BD_DEV uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
+// LDGSTS: the input stream reaches shared memory without passing through a register, so nothing in the
+// decode loop ever waits on (or moves) an in-flight global load of compressed bytes
+BD_DEV void cp_async16(hw::sref_t dst, const uint8_t* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+BD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// predicated 16-byte copy (stays predicated: no branch, see ld16_if).  .cg: served by L2, where this thread's
+// earlier stores are, never by a possibly stale L1 line.
+BD_DEV void cp_async16_if(bool cond, hw::sref_t dst, const void* src) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}" ::"r"((uint32_t)cond), "r"(dst), "l"(src) : "memory");
+}
+// NOTE: the hardware counts committed groups per WARP (one dependency counter), so commits and waits with a
+// nonzero count are only placed where the whole warp is converged.
+BD_DEV void cp_async_wait_all_but_latest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+BD_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 BD_DEV void warp_sync() { __syncwarp(); }
+// Pin a loop-invariant copy in a register: without this the compiler re-reads such values from the
+// (address-taken) structs in local memory every round, and with the L1 full of streaming data each of
+// those "free" reloads is an L2 round trip on the round's critical path.
+// Predicated global loads that stay predicated (no branch).  ptxas tracks outstanding loads per control-flow
+// path; a load issued inside an if-block is waited for where that block rejoins the main path, which would
+// put the whole L2/HBM latency back on the round's critical path.  Without a branch there is no such join,
+// and the wait moves to the first real use (a round later).
+BD_DEV void ld32_if(bool cond, const uint8_t* p, uint32_t& dst) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.u32 %0, [%2];\n\t}" : "+r"(dst) : "r"((uint32_t)cond), "l"(p) : "memory");
+}
+BD_DEV void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.u16 %0, [%2];\n\t}" : "+r"(dst) : "r"((uint32_t)cond), "l"(p) : "memory");
+}
+#define BD_PIN32(x) asm volatile("" : "+r"(x))
+#define BD_PIN64(x) asm volatile("" : "+l"(x))
 BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 lanes take part
 #endif
 
@@ -112,6 +153,10 @@ struct LaneCtx {
   uint8_t* ctx_lit;
   uint8_t* ctx_dist;
   uint8_t* ctx_modes;
+  hw::sref_t hist;       // shared: 32-byte ring mirroring this lane's most recent output words
+  hw::sref_t stage;      // shared, 16-byte aligned: [0..31] two 16-byte blocks of copy source, [32..47] the block of a table entry
+  hw::sref_t ring;       // shared: this lane's first 16-byte input block buffer; the second one is ring_stride further
+  uint32_t ring_stride;
   hw::sref_t cmd_lut;    // shared: uint2[704], pack_cmd_lut
   hw::sref_t ctx_lut;    // shared: u8[2048]
   const uint8_t* dictionary;  // RFC 7932 dictionary (source of the expanded table)
@@ -120,13 +165,31 @@ struct LaneCtx {
   hw::sref_t transform_info;  // shared: u32[121], pack_transform_info
 };
 
+// Word j of the input for the bit window (per-metablock code: synchronous).  When j enters a new 16-byte block,
+// the block after it is requested into the ring half whose words are all in registers already, and everything
+// requested so far is waited for.  Blocks past the end of the stream repeat the last one.  The command loop
+// has its own asynchronous version of this (LN_SKIP).
+BD_DEV uint32_t ring_next(const uint8_t* gin, hw::sref_t ring, uint32_t ring_stride, uint32_t last_blk, uint32_t j) {
+  if ((j & 3u) == 0) {
+    const uint32_t b = (j >> 2) + 1;
+    cp_async16(ring + (b & 1u) * ring_stride, gin + 16 * (size_t)(b < last_blk ? b : last_blk));
+    cp_async_commit();
+    cp_async_wait_all();
+  }
+  return vlds32(ring + ((j >> 2) & 1u) * ring_stride + (j & 3u) * 4u);
+}
+
 // Decoder state of one lane's stream.  Lives in local memory for the per-metablock (cold) code; the
 // command loop works on register copies.
 struct Lane {
-  // bit window: 96 bits of look-ahead over aligned words of the input
-  const uint32_t* w;
+  // bit window: 96 bits of look-ahead (lo, hi, nx = words k, k+1, k+2 of the 16-byte aligned input) in
+  // registers, fed from a two-block ring in shared memory that cp.async fills one block ahead
+  const uint8_t* gin;    // 16-byte aligned base of the input
+  hw::sref_t ring;
+  uint32_t ring_stride;
   uint32_t lo, hi, nx, k, bp;
-  uint32_t k_max;        // last word holding stream bytes; loads never go past it
+  uint32_t k_max;        // last word holding stream bytes
+  uint32_t last_blk;     // last 16-byte block holding stream bytes; copies never go past it
   uint64_t end_bit;      // 8 * (lead + size), relative to the aligned base
   uint32_t lead;
   // output write combiner; positions are biased by (out & 3) so that word boundaries are absolute
@@ -149,8 +212,7 @@ struct Lane {
     bp += n;
     if (bp >= 32) {
       lo = hi; hi = nx; k++;
-      const uint32_t kk = k + 2 < k_max ? k + 2 : k_max;
-      nx = hw::ldg32(w + kk);
+      nx = ring_next(gin, ring, ring_stride, last_blk, k + 2);
       bp -= 32;
     }
   }
@@ -187,7 +249,11 @@ BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint3
 }
 
 // ---- output write combiner ----
-BD_DEV void store_word(uint8_t* out_al, uint32_t bias, uint32_t wpos, uint32_t word) {
+// Every word that leaves for global memory is mirrored into a 32-byte per-lane history ring in shared memory
+// (hist + (position & 31)): short-distance copies read their source from there instead of waiting for a
+// just-stored byte to come back from L2.
+BD_DEV void store_word(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
+  sts32(hist + (wpos & 28u), word);
   if (BD_UNLIKELY(wpos < bias)) {  // first word of an unaligned region: bytes below the region are not ours
     for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
   } else {
@@ -195,11 +261,11 @@ BD_DEV void store_word(uint8_t* out_al, uint32_t bias, uint32_t wpos, uint32_t w
   }
 }
 // v holds exactly n (1..4) valid low bytes, the rest is zero
-BD_DEV void append(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc, uint32_t v, uint32_t n) {
+BD_DEV void append(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& posb, uint32_t& acc, uint32_t v, uint32_t n) {
   const uint32_t a = posb & 3u, sh = a * 8u;
   const uint32_t word = acc | (v << sh);
   if (a + n >= 4) {
-    store_word(out_al, bias, posb & ~3u, word);
+    store_word(out_al, bias, hist, posb & ~3u, word);
     acc = funnelshift_rc(v, 0u, 32u - sh);
   } else {
     acc = word;
@@ -207,17 +273,18 @@ BD_DEV void append(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc
   posb += n;
 }
 // v_hi:v_lo holds exactly n (1..8) valid low bytes, the rest is zero
-BD_DEV void append8(uint8_t* out_al, uint32_t bias, uint32_t& posb, uint32_t& acc, uint32_t v_lo, uint32_t v_hi, uint32_t n) {
+BD_DEV void append8(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& posb, uint32_t& acc, uint32_t v_lo, uint32_t v_hi, uint32_t n) {
   const uint32_t a = posb & 3u, sh = a * 8u, wpos = posb & ~3u;
   const uint32_t x0 = acc | (v_lo << sh);
   const uint32_t x1 = funnelshift_l(v_lo, v_hi, sh);
   const uint32_t t = a + n;
   if (t >= 8) {
-    store_word(out_al, bias, wpos, x0);
+    store_word(out_al, bias, hist, wpos, x0);
+    sts32(hist + ((wpos + 4) & 28u), x1);
     st32(out_al + wpos + 4, x1);
     acc = funnelshift_rc(v_hi, 0u, 32u - sh);
   } else if (t >= 4) {
-    store_word(out_al, bias, wpos, x0);
+    store_word(out_al, bias, hist, wpos, x0);
     acc = x1;
   } else {
     acc = x0;
@@ -228,19 +295,14 @@ BD_DEV void flush_partial(uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_
   const uint32_t a = posb & 3u, wpos = posb & ~3u;
   for (uint32_t j = 0; j < a; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(acc >> (8 * j));
 }
-BD_DEV uint32_t reload_partial(const uint8_t* out_al, uint32_t posb) {
-  const uint32_t a = posb & 3u;
-  return a ? ld32(out_al + (posb & ~3u)) & mask_bits(8 * a) : 0u;
-}
 // Last two output bytes (p1 = newest), zero before the start of the stream: the literal context.
-BD_DEV void last_two(const uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_t acc, uint32_t& p1, uint32_t& p2) {
+BD_DEV void last_two(hw::sref_t hist, uint32_t bias, uint32_t posb, uint32_t acc, uint32_t& p1, uint32_t& p2) {
   const uint32_t a = posb & 3u;
   uint32_t x;  // the four bytes before posb, newest in the top byte
   if (a >= 2) {
     x = acc << (32 - 8 * a);
   } else {
-    const uint32_t wpos = posb & ~3u;
-    const uint32_t prev = wpos >= 4 ? ld32(out_al + wpos - 4) : 0u;
+    const uint32_t prev = vlds32(hist + (((posb & ~3u) - 4u) & 28u));  // the word before the partial one
     x = a ? (acc << 24) | (prev >> 8) : prev;
   }
   const uint32_t have = posb - bias;
@@ -498,9 +560,13 @@ BD_DEV void prepare_literal(const LaneCtx& c, Lane& L) {
   }
 }
 
+struct BlockTrees { uint32_t type_root[3], len_root[3]; };
+
 // DecodeBlockTypeAndLength + Decode{Literal,Command,Distance}BlockSwitch, src/decode.rs:1469-1658.
 // cat: 0 literal, 1 command, 2 distance.
-BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, uint32_t type_root, uint32_t len_root) {
+BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, const BlockTrees& trees) {
+  // the roots are read here, not at the call site: the caller's loop must not touch local memory
+  const uint32_t type_root = trees.type_root[cat], len_root = trees.len_root[cat];
   const uint32_t nbt = L.nbt[cat];
   if (nbt < 2) return kLaneBail;  // the counter of a single block type can only run out in a corrupt stream
   uint32_t bt = decode_generic(c, L, type_root, kBlockRootBits);
@@ -518,7 +584,6 @@ BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, uint32_t type_
   return L.overrun() ? kLaneBail : kLaneOk;
 }
 
-struct BlockTrees { uint32_t type_root[3], len_root[3]; };
 
 // Metablock header up to the first command: src/decode.rs:2980-3288.
 BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
@@ -713,8 +778,10 @@ enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a
 // (metablock complete) or kStBail for every lane that ran.
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
   // register copies of the hot state
-  const uint32_t* w = nullptr;
-  uint32_t lo = 0, hi = 0, nx = 0, k = 0, bp = 0, k_max = 0;
+  const uint8_t* gin = nullptr;
+  uint32_t lo = 0, hi = 0, nx = 0, k = 0, bp = 0, k_max = 0, last_blk = 0;
+  hw::sref_t ring = c.ring;
+  uint32_t ring_stride = c.ring_stride;
   uint8_t* out_al = nullptr;
   uint32_t bias = 0, capb = 0, posb = 0, acc = 0;
   int32_t mlen = 0;
@@ -724,20 +791,27 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t r_lit = 0, r_cmd = 0, r_dist = 0, root_lit = 0;
   uint32_t cmd_tv = 0, lit_tv = 0, trivial = 0;  // trees of the current command / literal block type
   hw::sref_t ctx_lut = 0;
-  const uint32_t E = c.E;
-  const hw::sref_t stab = c.stab;
-  const uint16_t* const gtab = c.gtab;
+  uint32_t E = c.E;
+  hw::sref_t stab = c.stab;
+  const uint16_t* gtab = c.gtab;
+  hw::sref_t slot = c.slot, cmd_lut = c.cmd_lut, word_info = c.word_info, transform_info = c.transform_info;
+  hw::sref_t ctx_lut_base = c.ctx_lut;
+  const uint8_t* xdict = c.xdict;
+  hw::sref_t hist = c.hist, stage = c.stage;
+  BD_PIN32(ring); BD_PIN32(ring_stride); BD_PIN32(E); BD_PIN32(stab); BD_PIN64(gtab); BD_PIN32(slot); BD_PIN32(cmd_lut);
+  BD_PIN32(word_info); BD_PIN32(transform_info); BD_PIN32(ctx_lut_base); BD_PIN64(xdict); BD_PIN32(hist); BD_PIN32(stage);
 
 #define LN_TREES()                                                          \
   do {                                                                      \
     cmd_tv = tree_root(L, 1, L.cmd_tree);                                   \
     trivial = L.trivial;                                                    \
     lit_tv = tree_root(L, 0, L.lit_tree);                                   \
-    ctx_lut = c.ctx_lut + L.ctx_mode_off;                                   \
+    ctx_lut = ctx_lut_base + L.ctx_mode_off;                                \
+    BD_PIN32(cmd_tv); BD_PIN32(trivial); BD_PIN32(lit_tv); BD_PIN32(ctx_lut); \
   } while (0)
 
   if (run) {
-    w = L.w; lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp; k_max = L.k_max;
+    gin = L.gin; lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp; k_max = L.k_max; last_blk = L.last_blk;
     out_al = L.out_al; bias = L.bias; capb = L.capb; posb = L.posb; acc = L.acc;
     mlen = L.mlen;
     d0 = L.d0; d1 = L.d1; d2 = L.d2; d3 = L.d3;
@@ -746,28 +820,46 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     r_lit = L.rbits[0]; r_cmd = L.rbits[1]; r_dist = L.rbits[2]; root_lit = L.root[0];
     LN_TREES();
   }
+  BD_PIN64(gin); BD_PIN32(k_max); BD_PIN32(last_blk); BD_PIN64(out_al); BD_PIN32(bias); BD_PIN32(capb);
+  BD_PIN32(max_backward); BD_PIN32(npostfix); BD_PIN32(ndirect); BD_PIN32(r_lit); BD_PIN32(r_cmd); BD_PIN32(r_dist); BD_PIN32(root_lit);
+  const bool ran = run;
   uint32_t ph = kPhCmd;
   uint32_t ins = 0, copy_len = 0, cmd_bits = 0;
   uint32_t p1 = 0, p2 = 0;
   bool ctx_fresh = false;     // p1/p2 hold the last two output bytes (non-trivial literal contexts)
-  // copy chunk in flight: up to 8 source bytes in three aligned words, shifted by pend_s8 bits
-  uint32_t pw0 = 0, pw1 = 0, pw2 = 0, pend_n = 0, pend_s8 = 0;
-  const uint8_t* csrc = nullptr;  // next aligned source word of a copy longer than one chunk
+  // copy chunk in flight: up to 16 source bytes starting pend_off bytes into the two aligned 16-byte blocks
+  // on their way (cp.async) to stage[0..31]
+  uint32_t pend_n = 0, pend_off = 0;
+  const uint8_t* csrc = nullptr;  // next source byte of the copy being made
   uint32_t crem = 0;              // its remaining bytes
-  // second-level table entry requested in an earlier round for the symbol this lane is waiting to decode
-  uint32_t de = 0;
+  // second-level table entry requested (cp.async of its aligned 16-byte block to stage[32..47]) in an earlier
+  // round for the symbol this lane is waiting to decode; dsel = byte offset of the entry in that block
+  uint32_t dsel = 0;
+  bool dfresh = false;  // requested in THIS round: not there yet, the lane must not retry before the next round
+  // round counter and the round in which this lane last requested an input block (see LN_SKIP)
+  uint32_t rnd = 0, blk_round = 0xFFFFFFFFu;
   bool dhave = false;
 
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
-#define LN_SKIP(n)                                                     \
-  do {                                                                 \
-    bp += (n);                                                         \
-    if (bp >= 32) {                                                    \
-      lo = hi; hi = nx; k++;                                           \
-      const uint32_t kk_ = k + 2 < k_max ? k + 2 : k_max;              \
-      nx = hw::ldg32(w + kk_);                                         \
-      bp -= 32;                                                        \
-    }                                                                  \
+// Bits consumed; on a word boundary the window takes word k + 2 from the ring.  When that word starts a new
+// 16-byte block, the block after it is requested with cp.async -- not committed here: the round's convergent
+// commit covers it, and the convergent wait at the start of the next round completes it long before its words
+// are needed.  Only a lane that eats more than a whole block within one round has to commit and wait itself.
+#define LN_SKIP(n)                                                                               \
+  do {                                                                                           \
+    bp += (n);                                                                                   \
+    if (bp >= 32) {                                                                              \
+      lo = hi; hi = nx; k++;                                                                     \
+      const uint32_t j_ = k + 2;                                                                 \
+      if ((j_ & 3u) == 0) {                                                                      \
+        if (BD_UNLIKELY(blk_round == rnd)) { cp_async_commit(); cp_async_wait_all(); }           \
+        const uint32_t b_ = (j_ >> 2) + 1;                                                       \
+        cp_async16(ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
+        blk_round = rnd;                                                                         \
+      }                                                                                          \
+      nx = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);                       \
+      bp -= 32;                                                                                  \
+    }                                                                                            \
   } while (0)
 #define LN_SAVE()                                                                                   \
   do {                                                                                              \
@@ -779,8 +871,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_BLOCK_SWITCH(CAT)                                                          \
   do {                                                                                \
     LN_SAVE();                                                                        \
-    const int r_ = block_switch(c, L, CAT, bt.type_root[CAT], bt.len_root[CAT]);      \
-    lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;                              \
+    const int r_ = block_switch(c, L, CAT, bt);                                       \
+    lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;                                       \
     bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];                                   \
     LN_TREES();                                                                       \
     ctx_fresh = false;                                                                \
@@ -792,45 +884,65 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
-    uint32_t e_;                                                                                 \
-    if (BD_UNLIKELY(dhave)) {                                                                    \
-      e_ = de; dhave = false;                                                                    \
-    } else {                                                                                     \
-      const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                         \
-      e_ = v_ < E ? vlds16(stab + (v_ << 1)) : (uint32_t)gtab[v_ - E];                           \
-      if (BD_UNLIKELY((e_ & 15u) > (TR))) {                                                      \
-        de = gtab[((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits((e_ & 15u) - (TR)))];           \
-        dhave = true; WAIT = true;                                                               \
-      }                                                                                          \
-    }                                                                                            \
+    const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                           \
+    uint32_t e_ = vlds16(stab + ((v_ < E ? v_ : 0u) << 1));                                      \
+    ld16_if(v_ >= E, gtab + (v_ - E), e_);  /* root outside the shared slot (rare) */             \
+    if (BD_UNLIKELY(dhave)) e_ = vlds16(stage + 32u + dsel);  /* the entry requested last round */ \
+    const bool need2_ = !dhave && (e_ & 15u) > (TR);                                             \
+    const uint32_t sub_ = need2_ ? (e_ & 15u) - (TR) : 0u;                                       \
+    const uint32_t i2_ = ((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits(sub_));                  \
+    cp_async16_if(need2_, stage + 32u, gtab + (i2_ & ~7u));                                      \
+    if (need2_) { dsel = (i2_ & 7u) << 1; dfresh = true; }                                       \
+    dhave = need2_; WAIT = need2_;                                                               \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
-// loads of the next copy chunk: min(crem, 8) bytes starting pend_s8 bits into the aligned word at csrc;
-// only words that hold source bytes are touched
-#define LN_ISSUE_CHUNK()                                                   \
+// request the next copy chunk: min(crem, 16) bytes from csrc on; only 16-byte blocks that hold source bytes
+// are touched
+#define LN_ISSUE_CHUNK(ISS)                                                \
   do {                                                                     \
-    pend_n = crem < 8 ? crem : 8u;                                         \
-    crem -= pend_n;                                                        \
-    const uint32_t end_ = pend_s8 + 8 * pend_n;                            \
-    pw0 = ld32(csrc);                                                      \
-    pw1 = end_ > 32 ? ld32(csrc + 4) : 0u;                                 \
-    pw2 = end_ > 64 ? ld32(csrc + 8) : 0u;                                 \
-    csrc += 8;                                                             \
+    const bool iss_ = (ISS);                                               \
+    const uint32_t nn_ = crem < 16 ? crem : 16u;                           \
+    const uint32_t off_ = (uint32_t)(uintptr_t)csrc & 15u;                 \
+    cp_async16_if(iss_, stage, csrc - off_);                               \
+    cp_async16_if(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16);  \
+    if (iss_) { pend_n = nn_; pend_off = off_; crem -= nn_; csrc += 16; }  \
   } while (0)
 // append the chunk in flight to the output
 #define LN_RETIRE_CHUNK()                                                  \
   do {                                                                     \
-    uint32_t v_lo_ = hw::funnelshift_r(pw0, pw1, pend_s8);                 \
-    uint32_t v_hi_ = hw::funnelshift_r(pw1, pw2, pend_s8);                 \
-    if (pend_n < 4) v_lo_ &= mask_bits(8 * pend_n);                        \
-    if (pend_n <= 4) v_hi_ = 0;                                            \
-    else if (pend_n < 8) v_hi_ &= mask_bits(8 * (pend_n - 4));             \
-    append8(out_al, bias, posb, acc, v_lo_, v_hi_, pend_n);                \
+    const hw::sref_t sw_ = stage + (pend_off & 12u);                       \
+    const uint32_t s8_ = (pend_off & 3u) * 8u;                             \
+    const uint32_t pw0_ = vlds32(sw_), pw1_ = vlds32(sw_ + 4), pw2_ = vlds32(sw_ + 8); \
+    uint32_t v0_ = hw::funnelshift_r(pw0_, pw1_, s8_);                     \
+    uint32_t v1_ = hw::funnelshift_r(pw1_, pw2_, s8_);                     \
+    const uint32_t n0_ = pend_n < 8 ? pend_n : 8u;                         \
+    if (n0_ < 4) v0_ &= mask_bits(8 * n0_);                                \
+    if (n0_ <= 4) v1_ = 0;                                                 \
+    else if (n0_ < 8) v1_ &= mask_bits(8 * (n0_ - 4));                     \
+    append8(out_al, bias, hist, posb, acc, v0_, v1_, n0_);                 \
+    if (pend_n > 8) {                                                      \
+      const uint32_t pw3_ = vlds32(sw_ + 12), pw4_ = vlds32(sw_ + 16);     \
+      uint32_t v2_ = hw::funnelshift_r(pw2_, pw3_, s8_);                   \
+      uint32_t v3_ = hw::funnelshift_r(pw3_, pw4_, s8_);                   \
+      const uint32_t n1_ = pend_n - 8;                                     \
+      if (n1_ < 4) v2_ &= mask_bits(8 * n1_);                              \
+      if (n1_ <= 4) v3_ = 0;                                               \
+      else if (n1_ < 8) v3_ &= mask_bits(8 * (n1_ - 4));                   \
+      append8(out_al, bias, hist, posb, acc, v2_, v3_, n1_);               \
+    }                                                                      \
     pend_n = 0;                                                            \
   } while (0)
 
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
+    rnd++;
+    dfresh = false;
+    // everything requested during the previous round's phases (second-level entries, input blocks) has landed;
+    // the copy chunk requested at its very end may still be on its way
+    cp_async_wait_all_but_latest();
+#ifdef BD_LANE_ROUND_STATS
+    BD_LANE_ROUND_STATS(ph, dhave);
+#endif
 
     // ---- phase A: insert&copy command and its extra bits (ReadCommandInternal, :2134-2189) ----
     if (run && ph == kPhCmd) {
@@ -840,7 +952,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         bool wait = false;
         LN_DECODE(cmd_tv, r_cmd, bits, len, sym, wait);
         if (!wait) {
-          const uint2 lut = vlds64(c.cmd_lut + (sym << 3));
+          const uint2 lut = vlds64(cmd_lut + (sym << 3));
           cmd_bits = lut.x;
           ins = lut.x & 0xFFFFu;
           copy_len = lut.y & 0xFFFFu;
@@ -864,28 +976,23 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     }
     warp_sync();
 
-    // ---- phase P: retire the copy chunk issued in an earlier round; keep a long copy going ----
-    if (run && pend_n != 0) {
-      LN_RETIRE_CHUNK();
-      if (crem != 0) {
-        LN_ISSUE_CHUNK();
-        if (crem == 0) ph = kPhCmd;  // last chunk in flight: the next command can be decoded meanwhile
-      }
-    }
+    // ---- phase P: retire the copy chunk requested at the end of the previous round ----
+    cp_async_wait_all();
+    if (run && pend_n != 0) LN_RETIRE_CHUNK();
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
 
     // ---- phase B: literals (:2391-2551), up to kMaxLitPhases per round ----
     for (uint32_t rep = 0; rep < kMaxLitPhases; rep++) {
-      if (!warp_any(run && ph == kPhLit && ev == kStCommands)) break;
-      if (run && ph == kPhLit && ev == kStCommands) {
+      if (!warp_any(run && ph == kPhLit && ev == kStCommands && !dfresh)) break;
+      if (run && ph == kPhLit && ev == kStCommands && !dfresh) {
         if (BD_UNLIKELY(bl_l == 0)) LN_BLOCK_SWITCH(0);
         if (ev == kStCommands) {
           uint32_t tv = lit_tv;
           if (!trivial) {  // tree by the context of the last two bytes (:2500-2507)
-            if (!ctx_fresh) { last_two(out_al, bias, posb, acc, p1, p2); ctx_fresh = true; }
+            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
             const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
-            tv = root_lit + (vlds8(c.slot + kSlotCtxMap + cx) << r_lit);
+            tv = root_lit + (vlds8(slot + kSlotCtxMap + cx) << r_lit);
           }
           uint32_t bits, len, sym;
           bool wait = false;
@@ -893,7 +1000,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           if (!wait) {
             LN_SKIP(len);
             bl_l--;
-            append(out_al, bias, posb, acc, sym, 1);
+            append(out_al, bias, hist, posb, acc, sym, 1);
             p2 = p1; p1 = sym;
             if (--ins == 0) {
               if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
@@ -914,7 +1021,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (!(cmd_bits & (1u << 26))) {  // explicit distance symbol
         if (BD_UNLIKELY(bl_d == 0)) LN_BLOCK_SWITCH(2);
         if (ev == kStCommands) {
-          const uint32_t tv = vlds32(c.slot + ((cmd_bits >> 24) & 3u) * 4u);
+          const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
           uint32_t bits, len, sym;
           LN_DECODE(tv, r_dist, bits, len, sym, wait);
           if (!wait) {
@@ -967,20 +1074,19 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
             ev = kStBail;
           } else {
-            const uint32_t wi = vlds32(c.word_info + copy_len * 4u);
+            const uint32_t wi = vlds32(word_info + copy_len * 4u);
             const uint32_t shift = wi & 15u;
             const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
             const uint32_t t = word_id >> shift;
             if (t >= BROTLI_NUM_TRANSFORMS) {
               ev = kStBail;
             } else {
-              const uint32_t ti = vlds32(c.transform_info + t * 4u);
+              const uint32_t ti = vlds32(transform_info + t * 4u);
               const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
               if (n > capb - posb) {
                 ev = kStBail;
               } else {
-                csrc = c.xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
-                pend_s8 = 0;
+                csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
                 crem = n;
                 mlen -= (int32_t)n;
               }
@@ -994,46 +1100,55 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             mlen -= (int32_t)copy_len;
             crem = copy_len;
             uint32_t ud = (uint32_t)dist;
-            if (BD_UNLIKELY(ud < 12)) {
-              // Short period: copy byte-wise until the period can be widened to >= 12 (a copy at distance d
+            if (BD_UNLIKELY(ud < 20)) {
+              // Short period: copy byte-wise until the period can be widened to >= 20 (a copy at distance d
               // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
-              const uint32_t wide = ud * ((11u + ud) / ud);
+              const uint32_t wide = ud * ((19u + ud) / ud);
               const uint32_t m = crem < wide ? crem : wide;
-              flush_partial(out_al, bias, posb, acc);
-              for (uint32_t i = 0; i < m; i++) out_al[posb + i] = out_al[posb + i - ud];
-              posb += m;
-              acc = reload_partial(out_al, posb);
+              for (uint32_t i = 0; i < m; i++) {
+                // source byte: still in the partial word, or in the history ring (never a load from global memory)
+                const uint32_t sp = posb - ud;
+                const uint32_t b = sp >= (posb & ~3u) ? (acc >> (8 * (sp & 3u))) & 0xFFu : vlds8(hist + (sp & 31u));
+                append(out_al, bias, hist, posb, acc, b, 1);
+              }
               crem -= m;
               ud = wide;
             }
-            // Everything below the current output word is in memory, and a distance >= 12 keeps the eight
+            // Everything below the current output word is in memory, and a distance >= 20 keeps the sixteen
             // source bytes of every chunk below that word at the time the chunk is loaded.
-            const uint32_t sp = posb - ud;
-            pend_s8 = (sp & 3u) * 8u;
-            csrc = out_al + (sp & ~3u);
+            csrc = out_al + (posb - ud);
           }
         }
         if (ev == kStCommands) {
-          if (crem != 0) LN_ISSUE_CHUNK();
-          if (mlen <= 0) {
-            // end of the metablock: drain the copy now
-            while (pend_n != 0) {
-              LN_RETIRE_CHUNK();
-              if (crem != 0) LN_ISSUE_CHUNK();
-            }
-            ev = kStHeader;
-          } else {
-            ph = crem != 0 ? kPhCopy : kPhCmd;
-          }
+          if (mlen <= 0) ev = kStHeader;  // end of the metablock; the copy is drained after the loop
+          else ph = kPhCopy;
         }
       }
     }
-    if (run && ev != kStCommands) {
+    // ---- the one place where copy source loads are issued (a single definition of the chunk registers
+    //      keeps the compiler from moving just-loaded values around) ----
+    warp_sync();
+    cp_async_commit();  // group 1 of the round: what the phases requested
+    LN_ISSUE_CHUNK(run && crem != 0 && ev != kStBail);
+    cp_async_commit();  // group 2 of the round: the copy chunk
+    // last chunk in flight (or nothing to copy: zero-length dictionary output): the next command can be decoded
+    if (run && ph == kPhCopy && crem == 0 && ev == kStCommands) ph = kPhCmd;
+    if (run && ev != kStCommands) {  // this lane's registers stay as they are until the whole warp is through
       run = false;
       st = ev;
-      LN_SAVE();
     }
   }
+  if (ran && st == kStHeader) {
+    // the metablock's last copy may still be in flight
+    while (pend_n != 0) {
+      cp_async_wait_all();
+      LN_RETIRE_CHUNK();
+      LN_ISSUE_CHUNK(crem != 0);
+      cp_async_commit();
+    }
+  }
+  cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
+  if (ran) LN_SAVE();
 #undef LN_PEEK
 #undef LN_SKIP
 #undef LN_SAVE
@@ -1045,18 +1160,32 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 }
 
 // Stream header: bit window and output cursor set-up, DecodeWindowBits (src/decode.rs:152-187).
-BD_DEV uint32_t stream_begin(Lane& L, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap) {
+BD_DEV uint32_t stream_begin(const LaneCtx& c, Lane& L, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap) {
   if (in_size == 0 || in_size >= ((uint64_t)1 << 31)) return kStBail;
   const uintptr_t ia = (uintptr_t)in;
-  L.lead = (uint32_t)(ia & 3u);
-  L.w = (const uint32_t*)(ia - L.lead);
+  L.lead = (uint32_t)(ia & 15u);
+  L.gin = in - L.lead;
+  L.ring = c.ring;
+  L.ring_stride = c.ring_stride;
   L.end_bit = 8 * ((uint64_t)L.lead + in_size);
   L.k_max = (uint32_t)((L.lead + in_size - 1) >> 2);
-  L.k = 0;
-  L.bp = 8 * L.lead;
-  L.lo = hw::ldg32(L.w);
-  L.hi = hw::ldg32(L.w + (1 < L.k_max ? 1 : L.k_max));
-  L.nx = hw::ldg32(L.w + (2 < L.k_max ? 2 : L.k_max));
+  L.last_blk = L.k_max >> 2;
+  L.k = L.lead >> 2;
+  L.bp = 8 * (L.lead & 3u);
+  // blocks 0 and 1 now; from here on ring_next keeps one block of look-ahead in flight
+  cp_async_wait_all();  // nothing of the previous stream may still be landing in the ring
+  cp_async16(L.ring, L.gin);
+  cp_async16(L.ring + L.ring_stride, L.gin + 16 * (size_t)(1 < L.last_blk ? 1 : L.last_blk));
+  cp_async_commit();
+  cp_async_wait_all();
+  L.lo = vlds32(L.ring + ((L.k >> 2) & 1u) * L.ring_stride + (L.k & 3u) * 4u);
+  L.hi = vlds32(L.ring + (((L.k + 1) >> 2) & 1u) * L.ring_stride + ((L.k + 1) & 3u) * 4u);
+  L.nx = vlds32(L.ring + (((L.k + 2) >> 2) & 1u) * L.ring_stride + ((L.k + 2) & 3u) * 4u);
+  if (L.k + 2 >= 4) {  // the window already reaches into block 1: block 2 must be on its way (block 0 is all in registers)
+    cp_async16(L.ring, L.gin + 16 * (size_t)(2 < L.last_blk ? 2 : L.last_blk));
+    cp_async_commit();
+    cp_async_wait_all();
+  }
   const uintptr_t oa = (uintptr_t)out;
   L.bias = (uint32_t)(oa & 3u);
   L.out_al = out - L.bias;
@@ -1101,7 +1230,7 @@ BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in,
   Lane L;
   BlockTrees bt;
   uint32_t st = kStIdle;
-  if (active) st = stream_begin(L, in, in_size, out, out_cap);
+  if (active) st = stream_begin(c, L, in, in_size, out, out_cap);
   for (;;) {
     if (st == kStHeader) {
       const int r = metablock_begin(c, L, bt);

@@ -26,6 +26,20 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
   c.ctx_lit = a + lane::ArenaLayout::kCtxLit;
   c.ctx_dist = a + lane::ArenaLayout::kCtxDist;
   c.ctx_modes = a + lane::ArenaLayout::kCtxModes;
+  // two 16-byte input blocks; the device copies whole aligned blocks, so give the stream padding on both sides
+  // while keeping its address modulo 16
+  alignas(16) static uint8_t ring[32];
+  alignas(16) static uint8_t hist[32];
+  alignas(16) static uint8_t stage[48];
+  c.hist = hw::to_sref(hist);
+  c.stage = hw::to_sref(stage);
+  c.ring = hw::to_sref(ring);
+  c.ring_stride = 16;
+  std::vector<uint8_t> padded(in_size + 64 + 16);
+  uint8_t* pin = padded.data() + 32;
+  pin += (((uintptr_t)in & 15u) - ((uintptr_t)pin & 15u)) & 15u;
+  memcpy(pin, in, in_size);
+  in = pin;
   c.cmd_lut = hw::to_sref(cmd_lut.data());
   c.ctx_lut = hw::to_sref(tbl::kBrotliContextLookup);
   c.dictionary = kBrotliDictionaryData;
