@@ -130,12 +130,12 @@ int query_lane_resident_ctas(int device, int warps) {
   const uint32_t dyn = (lane_slot_bytes(warps) + 112u) * (uint32_t)(warps * 32);
   int per_sm = -1;
   switch (warps) {
-    case 2: per_sm = lane_occupancy<2>(dyn); break;
     case 4: per_sm = lane_occupancy<4>(dyn); break;
-    case 6: per_sm = lane_occupancy<6>(dyn); break;
     case 8: per_sm = lane_occupancy<8>(dyn); break;
     case 12: per_sm = lane_occupancy<12>(dyn); break;
     case 16: per_sm = lane_occupancy<16>(dyn); break;
+    case 20: per_sm = lane_occupancy<20>(dyn); break;
+    case 24: per_sm = lane_occupancy<24>(dyn); break;
     default: return -1;
   }
   if (per_sm < 1) return -1;
@@ -149,12 +149,12 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
   if (e != cudaSuccess) return e;
   const uint32_t dyn = (la.slot_bytes + 112u) * (uint32_t)(warps * 32);
   switch (warps) {
-    case 2: brotli_decode_lane_kernel<2><<<ctas, 64, dyn, stream>>>(a, la); break;
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
-    case 6: brotli_decode_lane_kernel<6><<<ctas, 192, dyn, stream>>>(a, la); break;
     case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;
     case 12: brotli_decode_lane_kernel<12><<<ctas, 384, dyn, stream>>>(a, la); break;
     case 16: brotli_decode_lane_kernel<16><<<ctas, 512, dyn, stream>>>(a, la); break;
+    case 20: brotli_decode_lane_kernel<20><<<ctas, 640, dyn, stream>>>(a, la); break;
+    case 24: brotli_decode_lane_kernel<24><<<ctas, 768, dyn, stream>>>(a, la); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

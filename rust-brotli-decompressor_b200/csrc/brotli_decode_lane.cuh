@@ -55,10 +55,16 @@ constexpr uint32_t kSlotHeaderBytes = 16 + 64;
 constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
 constexpr uint32_t kBlockRootBits = 6;
-#ifndef BD_LANE_LIT_PHASES
-#define BD_LANE_LIT_PHASES 3
+// BD_LANE_DEFER: 1 = a symbol whose code is longer than the root requests its second-level entry and retries
+// next round (no L2 wait inside a round; best at low occupancy); 0 = the entry is loaded right away and the
+// warp's other residents cover the L2 latency (best at >= 4 warps per scheduler).
+#ifndef BD_LANE_DEFER
+#define BD_LANE_DEFER 0
 #endif
-constexpr uint32_t kMaxLitPhases = BD_LANE_LIT_PHASES;  // literal symbols a lane can decode per round
+#ifndef BD_LANE_LIT_PHASES
+#define BD_LANE_LIT_PHASES 1
+#endif
+constexpr uint32_t kMaxLitPhases = BD_LANE_LIT_PHASES;  // EXTRA literal symbols a lane can decode per round (phase B)
 
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
@@ -633,31 +639,42 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   if (decode_context_map(c, L, L.nbt[2] << 2, L.n_dist, c.ctx_dist) != kLaneOk) return kLaneBail;
   if (L.overrun()) return kLaneBail;
   L.dist_alphabet = L.ndirect + (48u << L.npostfix);  // 16 + NDIRECT + (24 << (NPOSTFIX + 1)), :3189-3194
-  // Root widths: as wide as the shared slot allows.  Group sizes in entries: n << rbits.
+  // Root widths.  Groups (0 literal, 1 command, 2 distance) whose narrowest roots do not all fit the shared
+  // slot are moved to the arena, largest first; the rest share the slot and are widened, cheapest step first.
   const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
-  uint32_t rb[3] = {8, 8, 7};
-  const uint32_t rmin[3] = {5, 5, 4};
+  const uint32_t rmin[3] = {5, 5, 4}, rmax[3] = {8, 8, 7};
+  uint32_t rb[3] = {rmin[0], rmin[1], rmin[2]};
+  bool shared[3] = {true, true, true};
   for (;;) {
-    const uint32_t sz[3] = {ntrees[0] << rb[0], ntrees[1] << rb[1], ntrees[2] << rb[2]};
-    if (sz[0] + sz[1] + sz[2] <= c.E) break;
-    uint32_t g = 3, best = 0;
-    for (uint32_t i = 0; i < 3; i++) if (rb[i] > rmin[i] && sz[i] >= best) { best = sz[i]; g = i; }
-    if (g == 3) break;
-    rb[g]--;
+    uint32_t total = 0, g = 3, best = 0;
+    for (uint32_t i = 0; i < 3; i++) if (shared[i]) {
+      const uint32_t sz = ntrees[i] << rb[i];
+      total += sz;
+      if (sz >= best) { best = sz; g = i; }
+    }
+    if (total <= c.E || g == 3) break;
+    shared[g] = false;
+    rb[g] = (ntrees[g] << rmax[g]) <= kGlobalTab / 2 ? rmax[g] : rmin[g];  // the arena has room for wide roots
   }
-  // Groups are placed command, literal, distance from the bottom of the slot; a group that does not
-  // fit any more goes to the arena as a whole (with narrow roots to bound the space).
+  for (;;) {
+    uint32_t total = 0, g = 3, best = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < 3; i++) if (shared[i]) total += ntrees[i] << rb[i];
+    for (uint32_t i = 0; i < 3; i++) if (shared[i] && rb[i] < rmax[i]) {
+      const uint32_t extra = ntrees[i] << rb[i];
+      if (total + extra <= c.E && extra < best) { best = extra; g = i; }
+    }
+    if (g == 3) break;
+    rb[g]++;
+  }
   uint32_t next_shared = 0;
   const uint32_t order[3] = {1, 0, 2};
   for (uint32_t oi = 0; oi < 3; oi++) {
     const uint32_t g = order[oi];
-    uint32_t sz = ntrees[g] << rb[g];
-    if (next_shared + sz <= c.E) {
+    const uint32_t sz = ntrees[g] << rb[g];
+    if (shared[g]) {
       L.root[g] = next_shared;
       next_shared += sz;
     } else {
-      rb[g] = rmin[g];
-      sz = ntrees[g] << rb[g];
       if (L.cold_next + sz > c.E + kGlobalTab) return kLaneBail;
       L.root[g] = L.cold_next;
       L.cold_next += sz;
@@ -881,6 +898,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 // One symbol of the tree rooted at TV (root width TR): sets BITS (the 32-bit peek), LEN and SYM, or -- when
 // the code is longer than the root -- requests the second-level entry and sets WAIT: the lane retries
 // this phase next round with the entry in `de` (DecodeSymbol, :377-391, over our table shape).
+#if BD_LANE_DEFER
 #define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
@@ -896,6 +914,19 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     dhave = need2_; WAIT = need2_;                                                               \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
+#else
+#define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
+  do {                                                                                           \
+    BITS = LN_PEEK();                                                                            \
+    const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                           \
+    uint32_t e_ = vlds16(stab + ((v_ < E ? v_ : 0u) << 1));                                      \
+    ld16_if(v_ >= E, gtab + (v_ - E), e_);  /* root outside the shared slot */                    \
+    const bool need2_ = (e_ & 15u) > (TR);                                                       \
+    const uint32_t sub_ = need2_ ? (e_ & 15u) - (TR) : 0u;                                       \
+    ld16_if(need2_, gtab + ((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits(sub_)), e_);           \
+    LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
+  } while (0)
+#endif
 // request the next copy chunk: min(crem, 16) bytes from csrc on; only 16-byte blocks that hold source bytes
 // are touched
 #define LN_ISSUE_CHUNK(ISS)                                                \
@@ -944,33 +975,56 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     BD_LANE_ROUND_STATS(ph, dhave);
 #endif
 
-    // ---- phase A: insert&copy command and its extra bits (ReadCommandInternal, :2134-2189) ----
-    if (run && ph == kPhCmd) {
-      if (BD_UNLIKELY(bl_c == 0)) LN_BLOCK_SWITCH(1);
+    // ---- phase A: one symbol for every lane at a command boundary (insert&copy command and its extra bits,
+    //      ReadCommandInternal :2134-2189) or inside a literal run (:2391-2551): the table lookup and the bit
+    //      skip are shared, only the short tails differ ----
+    if (run && (ph == kPhCmd || ph == kPhLit)) {
+      const bool is_lit = ph == kPhLit;
+      if (BD_UNLIKELY((is_lit ? bl_l : bl_c) == 0)) LN_BLOCK_SWITCH(is_lit ? 0u : 1u);
       if (ev == kStCommands) {
+        uint32_t tv = is_lit ? lit_tv : cmd_tv;
+        const uint32_t tr = is_lit ? r_lit : r_cmd;
+        if (is_lit && !trivial) {  // tree by the context of the last two bytes (:2500-2507)
+          if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
+          const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
+          tv = root_lit + (vlds8(slot + kSlotCtxMap + cx) << r_lit);
+        }
         uint32_t bits, len, sym;
         bool wait = false;
-        LN_DECODE(cmd_tv, r_cmd, bits, len, sym, wait);
+        LN_DECODE(tv, tr, bits, len, sym, wait);
         if (!wait) {
-          const uint2 lut = vlds64(cmd_lut + (sym << 3));
-          cmd_bits = lut.x;
-          ins = lut.x & 0xFFFFu;
-          copy_len = lut.y & 0xFFFFu;
-          const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
-          if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
-            const uint32_t x = bits >> len;
-            ins += x & mask_bits(ie);
-            copy_len += (x >> ie) & mask_bits(ce);
-            LN_SKIP(len + ie + ce);
+          uint32_t nskip = len;
+          if (is_lit) {
+            bl_l--;
+            append(out_al, bias, hist, posb, acc, sym, 1);
+            p2 = p1; p1 = sym;
+            if (--ins == 0) {
+              if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+              else ph = kPhDist;
+            }
           } else {
-            LN_SKIP(len);
-            if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
-            if (ce) { copy_len += LN_PEEK() & mask_bits(ce); LN_SKIP(ce); }
+            const uint2 lut = vlds64(cmd_lut + (sym << 3));
+            cmd_bits = lut.x;
+            ins = lut.x & 0xFFFFu;
+            copy_len = lut.y & 0xFFFFu;
+            const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
+            if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
+              const uint32_t x = bits >> len;
+              ins += x & mask_bits(ie);
+              copy_len += (x >> ie) & mask_bits(ce);
+              nskip = len + ie + ce;
+            } else {
+              LN_SKIP(len);
+              if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
+              copy_len += LN_PEEK() & mask_bits(ce);
+              nskip = ce;
+            }
+            bl_c--;
+            mlen -= (int32_t)ins;
+            ph = ins != 0 ? kPhLit : kPhDist;
+            ctx_fresh = false;
           }
-          bl_c--;
-          mlen -= (int32_t)ins;
-          ph = ins != 0 ? kPhLit : kPhDist;
-          ctx_fresh = false;
+          LN_SKIP(nskip);
         }
       }
     }
@@ -982,7 +1036,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
 
-    // ---- phase B: literals (:2391-2551), up to kMaxLitPhases per round ----
+    // ---- phase B (optional): further literals of the run (:2391-2551), up to kMaxLitPhases per round ----
     for (uint32_t rep = 0; rep < kMaxLitPhases; rep++) {
       if (!warp_any(run && ph == kPhLit && ev == kStCommands && !dfresh)) break;
       if (run && ph == kPhLit && ev == kStCommands && !dfresh) {
