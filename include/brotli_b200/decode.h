@@ -204,6 +204,12 @@ BROTLI_B200_API int BrotliB200ChecksumBatchDevice(size_t n, const uint8_t* d_byt
 BROTLI_B200_API uint64_t BrotliB200KernelLaunchCount(void);
 /* Device time of the most recent decode kernel launched through BrotliB200DecompressBatchPacked, ms. */
 BROTLI_B200_API double BrotliB200LastKernelMs(void);
+/* Device time of the decode kernels of the current device's BrotliB200DecompressBatch* launches since the last
+ * reset, measured with CUDA events recorded on the launching stream around each kernel (at most the 64 most
+ * recent launches are kept).  Synchronises the device.  lane_ms / exact_ms: summed duration of the
+ * lane-per-stream kernel and of the exact warp-per-stream kernel; launches: decode calls covered; bailed: streams
+ * the lane kernel handed to the exact kernel in the most recent call.  reset != 0 clears the record. */
+BROTLI_B200_API int BrotliB200KernelTimes(double* lane_ms, double* exact_ms, uint32_t* launches, uint32_t* bailed, int reset);
 /* Last library-level error message of the calling thread ("" if none). */
 BROTLI_B200_API const char* BrotliB200LastError(void);
 /* Resident decoding warps per launch on the current device (148 SMs x warps per SM on a B200). */

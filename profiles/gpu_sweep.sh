@@ -26,7 +26,7 @@ PY
 done
 if [ -n "$PROF_WARPS" ]; then
   BROTLI_B200_LANE_WARPS=$PROF_WARPS timeout 900 ncu --set full --clock-control none --import-source on -k regex:brotli_decode_lane -s 3 -c 1 -o $OUT/prof_lane \
-    python bench.py --streams 32768 --unique 1024 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_bench_lane.log 2>&1
+    python bench.py --streams 131072 --unique 2048 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_bench_lane.log 2>&1
   tail -2 $OUT/prof_bench_lane.log
 fi
 ls -la $OUT

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "BrotliDecoderGetErrorString", "BrotliDecoderErrorString", "BrotliDecoderVersion", "BrotliDecoderMallocU8",
     "BrotliDecoderFreeU8", "BrotliDecoderMallocUsize", "BrotliDecoderFreeUsize", "BrotliB200DecompressBatchDevice",
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
-    "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200LastError", "BrotliB200ResidentWarps",
+    "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
     "BrotliB200Shutdown",
 ]
 
@@ -96,6 +96,8 @@ def lib():
     L.BrotliB200ChecksumBatchDevice.argtypes = [sz, vp, vp, vp, vp, vp]
     L.BrotliB200KernelLaunchCount.restype = ctypes.c_uint64
     L.BrotliB200LastKernelMs.restype = ctypes.c_double
+    L.BrotliB200KernelTimes.restype = ctypes.c_int
+    L.BrotliB200KernelTimes.argtypes = [vp, vp, vp, vp, ctypes.c_int]
     L.BrotliB200LastError.restype = u8p
     L.BrotliB200ResidentWarps.restype = ctypes.c_int
     L.BrotliB200Shutdown.restype = None
@@ -111,6 +113,16 @@ def _check(rc, what):
 def error_string(code):
     """BrotliDecoderErrorString, c/brotli/decode.h:377"""
     return lib().BrotliDecoderErrorString(int(code)).decode()
+
+
+def kernel_times(reset=False):
+    """-> dict(lane_ms, exact_ms, launches, bailed): summed device time of the two decode kernels over the decode
+    calls since the last reset (CUDA events on the launching stream), and the bail count of the last call."""
+    lane, exact = ctypes.c_double(0), ctypes.c_double(0)
+    n, bailed = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    _check(lib().BrotliB200KernelTimes(ctypes.byref(lane), ctypes.byref(exact), ctypes.byref(n), ctypes.byref(bailed), 1 if reset else 0),
+           "BrotliB200KernelTimes")
+    return {"lane_ms": lane.value, "exact_ms": exact.value, "launches": n.value, "bailed": bailed.value}
 
 
 def kernel_launch_count():

@@ -106,6 +106,10 @@ struct DeviceCtx {
   uint32_t* ticket = nullptr;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  // per-launch kernel timing (BrotliB200KernelTimes): [i][0..2] = before lane kernel, between, after exact kernel
+  static constexpr int kTimedLaunches = 64;
+  cudaEvent_t ev_t[kTimedLaunches][3] = {};
+  uint32_t timed_count = 0;
   std::mutex launch_mu;          // orders launches: decode kernels share the scratch arena and the ticket
   cudaEvent_t ev_arena = nullptr;  // completion of the most recent decode launch
   bool arena_busy = false;
@@ -194,6 +198,9 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   a.n = (uint32_t)n; a.large_window = large_window; a.n_ptr = nullptr;
   std::lock_guard<std::mutex> lock(c->launch_mu);
   if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
+  const uint32_t slot = c->timed_count % DeviceCtx::kTimedLaunches;
+  for (int e = 0; e < 3; e++) if (!c->ev_t[slot][e]) CU_TRY(cudaEventCreate(&c->ev_t[slot][e]));
+  CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
   if (c->lane_ctas > 0) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
@@ -209,7 +216,10 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
     // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
     a.order = la.bail_list; a.n_ptr = la.bail_count; a.ticket = c->ticket + 8;
   }
+  CU_TRY(cudaEventRecord(c->ev_t[slot][1], stream));
   CU_TRY(brotli_b200::launch_decode_batch(a, c->ctas, stream));
+  CU_TRY(cudaEventRecord(c->ev_t[slot][2], stream));
+  c->timed_count++;
   CU_TRY(cudaEventRecord(c->ev_arena, stream));
   c->arena_busy = true;
   g_launches.fetch_add(1);
@@ -591,6 +601,30 @@ int BrotliB200ChecksumBatchDevice(size_t n, const uint8_t* d_bytes, const uint64
 
 uint64_t BrotliB200KernelLaunchCount(void) { return g_launches.load(); }
 double BrotliB200LastKernelMs(void) { return g_last_kernel_ms.load(); }
+
+int BrotliB200KernelTimes(double* lane_ms, double* exact_ms, uint32_t* launches, uint32_t* bailed, int reset) {
+  DeviceCtx* c = acquire_ctx();
+  if (!c) return BROTLI_DECODER_ERROR_UNREACHABLE;
+  std::lock_guard<std::mutex> lock(c->launch_mu);
+  CU_TRY(cudaDeviceSynchronize());
+  double lane = 0, exact = 0;
+  const uint32_t n = c->timed_count < (uint32_t)DeviceCtx::kTimedLaunches ? c->timed_count : (uint32_t)DeviceCtx::kTimedLaunches;
+  for (uint32_t i = 0; i < n; i++) {
+    float a = 0, b = 0;
+    CU_TRY(cudaEventElapsedTime(&a, c->ev_t[i][0], c->ev_t[i][1]));
+    CU_TRY(cudaEventElapsedTime(&b, c->ev_t[i][1], c->ev_t[i][2]));
+    lane += a; exact += b;
+  }
+  if (lane_ms) *lane_ms = lane;
+  if (exact_ms) *exact_ms = exact;
+  if (launches) *launches = n;
+  if (bailed) {
+    *bailed = 0;
+    if (c->bail_count) CU_TRY(cudaMemcpy(bailed, c->bail_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  if (reset) c->timed_count = 0;
+  return 0;
+}
 const char* BrotliB200LastError(void) { return tl_error.c_str(); }
 
 int BrotliB200ResidentWarps(void) {
@@ -611,6 +645,8 @@ void BrotliB200Shutdown(void) {
     c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
     cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
+    for (auto& t : c->ev_t) for (auto& e : t) if (e) { cudaEventDestroy(e); e = nullptr; }
+    c->timed_count = 0;
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); cudaEventDestroy(c->ev_arena); c->arena_busy = false;
     c->ready = false;
     cudaSetDevice(prev);

@@ -222,3 +222,59 @@ def test_decompressor_reader(gpu_lib, pkg):
     d = pkg.Decompressor(io.BytesIO(helpers.golden_fixture(name)[:1000]), 256)
     with pytest.raises(ValueError):
         d.read()
+
+
+def test_lane_kernel_takes_the_headline_streams(gpu_lib, pkg, corpus):
+    """The lane-per-stream kernel must decode every well-formed q5 text stream itself (nothing handed to the
+    exact kernel), and BrotliB200KernelTimes must see both kernels of the call."""
+    import torch
+    comp, orig, _ = corpus.make_config("headline", 320)
+    in_bytes, in_off = corpus.pack(comp)
+    out_off = np.arange(len(comp) + 1, dtype=np.uint64) * np.uint64(65536)
+    d_in = torch.from_numpy(in_bytes.copy()).cuda()
+    d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
+    d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device="cuda")
+    d_out_off = torch.from_numpy(out_off.view(np.int64)).cuda()
+    d_len = torch.zeros(len(comp), dtype=torch.int64, device="cuda")
+    d_codes = torch.zeros(len(comp), dtype=torch.int32, device="cuda")
+    pkg.kernel_times(reset=True)
+    pkg.decompress_batch_device(len(comp), d_in, d_in_off, d_out, d_out_off, d_len, d_codes)
+    t = pkg.kernel_times()
+    assert t["launches"] == 1 and t["lane_ms"] > 0 and t["bailed"] == 0, t
+    assert bool((d_codes == 1).all()) and d_out.cpu().numpy().tobytes() == b"".join(orig)
+
+
+def test_bails_reach_the_exact_kernel(gpu_lib, pkg, oracle, corpus):
+    """Streams the optimistic kernel gives up (uncompressed metablocks, too small a region, corruption) come back
+    with the exact kernel's codes and sizes; the bail count says they took that path."""
+    comp, orig, _ = corpus.make_config("C2", 40)
+    rnd = np.random.default_rng(5).integers(0, 256, size=3000, dtype=np.uint8).tobytes()
+    streams = list(comp) + [corpus.compress(rnd, 5), comp[0][: len(comp[0]) // 2], helpers.golden_fixture("x.compressed")]
+    caps = [len(o) for o in orig] + [3000, 65536, 1]
+    caps[3] -= 1  # a valid stream with too little room
+    pkg.kernel_times(reset=True)
+    check_batch(pkg, oracle, streams, caps)
+    assert pkg.kernel_times()["bailed"] >= 3
+
+
+@pytest.mark.parametrize("mode", ["exact_only", "lane_warps_8", "lane_deferred_lookups"])
+def test_other_kernel_configurations(gpu_lib, mode):
+    """The same parity run with the lane kernel switched off (every stream through the exact warp-per-stream
+    kernel), with another lane-kernel geometry, and with the deferred-lookup build when it is present."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    if mode == "exact_only":
+        env["BROTLI_B200_LANE"] = "0"
+    elif mode == "lane_warps_8":
+        env["BROTLI_B200_LANE_WARPS"] = "8"
+    else:
+        lib = os.path.join(helpers.ROOT, "rust-brotli-decompressor_b200", "variants", "libbrotli_b200_defer.so")
+        if not os.path.exists(lib):
+            pytest.skip("variant library not built")
+        env["BROTLI_B200_LIB"] = lib
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(helpers.ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "config_samples or corrupt_truncated or fixtures_one_shot or empty_and_ragged"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
