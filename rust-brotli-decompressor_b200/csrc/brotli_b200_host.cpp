@@ -255,7 +255,10 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
   std::vector<Chunk> chunks;
   for (size_t b = 0; b < n;) {
     size_t e = b; uint64_t acc = 0;
-    while (e < n && (e == b || acc < kPipelineChunkBytes)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
+    // a chunk should fill every resident lane of the lane kernel: a launch takes about as long for a few streams
+    // as for one stream per lane
+    const size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
+    while (e < n && (e == b || acc < kPipelineChunkBytes || e - b < min_streams)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
     chunks.push_back(Chunk{b, e, nullptr, nullptr});
     b = e;
   }

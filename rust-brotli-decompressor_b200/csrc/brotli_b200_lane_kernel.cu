@@ -133,6 +133,7 @@ int query_lane_resident_ctas(int device, int warps) {
     case 4: per_sm = lane_occupancy<4>(dyn); break;
     case 8: per_sm = lane_occupancy<8>(dyn); break;
     case 12: per_sm = lane_occupancy<12>(dyn); break;
+    case 14: per_sm = lane_occupancy<14>(dyn); break;
     case 16: per_sm = lane_occupancy<16>(dyn); break;
     case 20: per_sm = lane_occupancy<20>(dyn); break;
     case 24: per_sm = lane_occupancy<24>(dyn); break;
@@ -152,6 +153,7 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
     case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;
     case 12: brotli_decode_lane_kernel<12><<<ctas, 384, dyn, stream>>>(a, la); break;
+    case 14: brotli_decode_lane_kernel<14><<<ctas, 448, dyn, stream>>>(a, la); break;
     case 16: brotli_decode_lane_kernel<16><<<ctas, 512, dyn, stream>>>(a, la); break;
     case 20: brotli_decode_lane_kernel<20><<<ctas, 640, dyn, stream>>>(a, la); break;
     case 24: brotli_decode_lane_kernel<24><<<ctas, 768, dyn, stream>>>(a, la); break;

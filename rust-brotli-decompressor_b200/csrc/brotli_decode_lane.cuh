@@ -654,7 +654,11 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     }
     if (total <= c.E || g == 3) break;
     shared[g] = false;
+#ifdef BD_LANE_SPILL_NARROW
+    rb[g] = rmin[g];
+#else
     rb[g] = (ntrees[g] << rmax[g]) <= kGlobalTab / 2 ? rmax[g] : rmin[g];  // the arena has room for wide roots
+#endif
   }
   for (;;) {
     uint32_t total = 0, g = 3, best = 0xFFFFFFFFu;
