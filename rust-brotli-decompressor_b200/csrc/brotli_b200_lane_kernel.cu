@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   c.ring = hw::to_sref(s_dyn + (size_t)threadIdx.x * 16);
   c.ring_stride = WARPS * 32 * 16;
   c.hist = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 32 + (size_t)threadIdx.x * 32);  // 32-byte output history ring
-  c.stage = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 64 + (size_t)threadIdx.x * 48);  // cp.async landing zone
-  c.slot = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 112 + (size_t)threadIdx.x * la.slot_bytes);
+  c.stage = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 64 + (size_t)threadIdx.x * 64);  // cp.async landing zone
+  c.slot = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 128 + (size_t)threadIdx.x * la.slot_bytes);
   c.stab = c.slot + lane::kSlotHeaderBytes;
   c.E = (la.slot_bytes - lane::kSlotHeaderBytes) / 2;
   c.gtab = (uint16_t*)(arena + lane::ArenaLayout::kTab);
@@ -117,8 +117,9 @@ size_t lane_arena_bytes_per_lane() { return lane::ArenaLayout::kBytes; }
 // Slot size for `warps` warps per CTA: what is left of the SM's shared memory, an odd number of 32-bit
 // words so that equal offsets in different lanes' slots fall into different banks.
 uint32_t lane_slot_bytes(int warps) {
-  const uint32_t static_bytes = 704 * 8 + 2048 + 4 * (25 + BROTLI_NUM_TRANSFORMS) + 1024 + 128;  // the LUTs + the runtime's reserve
-  uint32_t per_lane = (232448u - static_bytes) / (uint32_t)(warps * 32) - 112u;  // 112: the lane's input ring (32), output history ring (32) and cp.async landing zone (48)
+  // static shared memory of the kernel: the command LUT (5632), the context LUT (2048), word / transform info (584)
+  const uint32_t static_bytes = 704 * 8 + 2048 + 4 * (25 + BROTLI_NUM_TRANSFORMS) + 64;
+  uint32_t per_lane = (232448u - static_bytes) / (uint32_t)(warps * 32) - 128u;  // 128: the lane's input ring (32), output history ring (32) and cp.async landing zone (64)
   uint32_t words = per_lane / 4;
   if ((words & 1u) == 0) words--;
   return words * 4;
@@ -127,7 +128,7 @@ uint32_t lane_slot_bytes(int warps) {
 int query_lane_resident_ctas(int device, int warps) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-  const uint32_t dyn = (lane_slot_bytes(warps) + 112u) * (uint32_t)(warps * 32);
+  const uint32_t dyn = (lane_slot_bytes(warps) + 128u) * (uint32_t)(warps * 32);
   int per_sm = -1;
   switch (warps) {
     case 4: per_sm = lane_occupancy<4>(dyn); break;
@@ -148,7 +149,7 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
-  const uint32_t dyn = (la.slot_bytes + 112u) * (uint32_t)(warps * 32);
+  const uint32_t dyn = (la.slot_bytes + 128u) * (uint32_t)(warps * 32);
   switch (warps) {
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
     case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;

@@ -5,15 +5,15 @@
 // streams has a better mapping: every lane owns a whole stream, so one issued instruction advances 32
 // bit windows / table lookups / output cursors at once.  What makes that work on the SM:
 //
-//   * phased rounds -- the warp runs rounds of fixed phases: [command symbol] [retire the copy issued last
-//     round] [literal symbol, up to kMaxLitPhases times] [distance symbol + issue the copy's loads].  Each
+//   * phased rounds -- the warp runs rounds of fixed phases: [A: command or literal symbol] [P: retire the copy
+//     requested last round] [C: distance symbol, copy set-up, request for the copy's source bytes].  Each
 //     phase's code is issued once per round for all lanes that are at that point of their stream, so a
 //     lane normally completes one whole insert-and-copy command per round; warp votes at the phase
 //     boundaries keep the 32 streams converged.
-//   * nothing on a round's critical path waits for L2/HBM: backreference (and dictionary) source words
-//     are loaded at the end of a round and consumed after the next round's command decode; a symbol whose
-//     code is longer than the root table requests its second-level entry and the lane simply retries
-//     that phase next round with the entry in a register.
+//   * software pipelining with cp.async: what a phase needs from L2/HBM is requested a phase earlier --
+//     backreference (and dictionary) source bytes at the end of a round for phase P of the next, the
+//     second-level table entry of the next command/literal symbol right after the distance symbol is read,
+//     that of the distance symbol right after the command is read -- and lands in per-lane shared staging.
 //   * per-lane prefix-code tables with a SMALL root level in shared memory (a private slot per lane;
 //     32 random addresses over 32 banks cost ~3 wavefronts) and the second level in a per-lane global
 //     arena.  Root widths are chosen per metablock so all roots fit the slot.
@@ -48,24 +48,14 @@ namespace BD_NS {
 namespace lane {
 
 // ---- per-lane storage geometry ----
-// shared slot: cur_dist[4] (root of the distance tree per distance context), the 64-entry literal context
-// map of the current literal block type, then E u16 table entries
-constexpr uint32_t kSlotCtxMap = 16;
-constexpr uint32_t kSlotHeaderBytes = 16 + 64;
+// shared slot: cur_dist[4] (root of the distance tree per distance context), then E u16 table entries; in
+// metablocks with context-modelled literals the top 32 entries hold the 64-entry context map of the current
+// literal block type instead
+constexpr uint32_t kSlotHeaderBytes = 16;
+constexpr uint32_t kCtxMapEntries = 32;      // table entries the 64-byte context map takes from the top of the slot when needed
 constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
 constexpr uint32_t kBlockRootBits = 6;
-// BD_LANE_DEFER: 1 = a symbol whose code is longer than the root requests its second-level entry and retries
-// next round (no L2 wait inside a round; best at low occupancy); 0 = the entry is loaded right away and the
-// warp's other residents cover the L2 latency (best at >= 4 warps per scheduler).
-#ifndef BD_LANE_DEFER
-#define BD_LANE_DEFER 0
-#endif
-#ifndef BD_LANE_LIT_PHASES
-#define BD_LANE_LIT_PHASES 1
-#endif
-constexpr uint32_t kMaxLitPhases = BD_LANE_LIT_PHASES;  // EXTRA literal symbols a lane can decode per round (phase B)
-
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
   static constexpr size_t kCtxLit = kTab + 2 * (size_t)kGlobalTab;    // u8[64 * kMaxBlockTypes]
@@ -160,7 +150,8 @@ struct LaneCtx {
   uint8_t* ctx_dist;
   uint8_t* ctx_modes;
   hw::sref_t hist;       // shared: 32-byte ring mirroring this lane's most recent output words
-  hw::sref_t stage;      // shared, 16-byte aligned: [0..31] two 16-byte blocks of copy source, [32..47] the block of a table entry
+  hw::sref_t stage;      // shared, 16-byte aligned: [0..31] two 16-byte blocks of copy source, [32..47] / [48..63] the
+                         // block holding the second-level table entry of the next phase-A / phase-C symbol
   hw::sref_t ring;       // shared: this lane's first 16-byte input block buffer; the second one is ring_stride further
   uint32_t ring_stride;
   hw::sref_t cmd_lut;    // shared: uint2[704], pack_cmd_lut
@@ -212,6 +203,7 @@ struct Lane {
   uint32_t trivial_lo, trivial_hi;      // bit i: literal block type i uses one tree for all 64 contexts
   uint32_t trivial, lit_tree, ctx_mode_off, ctx_slice, cmd_tree, dist_slice;
   uint32_t cold_next;    // next free virtual index of the arena part of the table space
+  uint32_t e_tab;        // entries of the shared slot available to tables in this metablock (E, or E - kCtxMapEntries)
 
   BD_DEV uint32_t peek() const { return hw::funnelshift_r(lo, hi, bp); }
   BD_DEV void skip(uint32_t n) {
@@ -562,7 +554,7 @@ BD_DEV void prepare_literal(const LaneCtx& c, Lane& L) {
   L.lit_tree = c.ctx_lit[L.ctx_slice];
   L.ctx_mode_off = (uint32_t)(c.ctx_modes[bt] & 3u) * 512u;
   if (!L.trivial) {  // the command loop reads the block type's context map from the shared slot
-    for (uint32_t j = 0; j < 64; j += 4) sts32(c.slot + kSlotCtxMap + j, ld32(c.ctx_lit + L.ctx_slice + j));
+    for (uint32_t j = 0; j < 64; j += 4) sts32(c.stab + 2 * L.e_tab + j, ld32(c.ctx_lit + L.ctx_slice + j));
   }
 }
 
@@ -639,6 +631,13 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   if (decode_context_map(c, L, L.nbt[2] << 2, L.n_dist, c.ctx_dist) != kLaneOk) return kLaneBail;
   if (L.overrun()) return kLaneBail;
   L.dist_alphabet = L.ndirect + (48u << L.npostfix);  // 16 + NDIRECT + (24 << (NPOSTFIX + 1)), :3189-3194
+  // context-modelled literals in this metablock: their block type's context map lives at the top of the slot
+  {
+    bool all_trivial = true;
+    for (uint32_t i = 0; i < L.nbt[0]; i++) all_trivial = all_trivial && (((i < 32 ? L.trivial_lo >> i : L.trivial_hi >> (i - 32)) & 1u) != 0);
+    if (!all_trivial && c.E < 2 * kCtxMapEntries) return kLaneBail;
+    L.e_tab = all_trivial ? c.E : c.E - kCtxMapEntries;
+  }
   // Root widths.  Groups (0 literal, 1 command, 2 distance) whose narrowest roots do not all fit the shared
   // slot are moved to the arena, largest first; the rest share the slot and are widened, cheapest step first.
   const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
@@ -652,7 +651,7 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
       total += sz;
       if (sz >= best) { best = sz; g = i; }
     }
-    if (total <= c.E || g == 3) break;
+    if (total <= L.e_tab || g == 3) break;
     shared[g] = false;
 #ifdef BD_LANE_SPILL_NARROW
     rb[g] = rmin[g];
@@ -665,7 +664,7 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     for (uint32_t i = 0; i < 3; i++) if (shared[i]) total += ntrees[i] << rb[i];
     for (uint32_t i = 0; i < 3; i++) if (shared[i] && rb[i] < rmax[i]) {
       const uint32_t extra = ntrees[i] << rb[i];
-      if (total + extra <= c.E && extra < best) { best = extra; g = i; }
+      if (total + extra <= L.e_tab && extra < best) { best = extra; g = i; }
     }
     if (g == 3) break;
     rb[g]++;
@@ -811,7 +810,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t max_backward = 0, npostfix = 0, ndirect = 0;
   uint32_t r_lit = 0, r_cmd = 0, r_dist = 0, root_lit = 0;
   uint32_t cmd_tv = 0, lit_tv = 0, trivial = 0;  // trees of the current command / literal block type
-  hw::sref_t ctx_lut = 0;
+  hw::sref_t ctx_lut = 0, ctx_map = 0;
   uint32_t E = c.E;
   hw::sref_t stab = c.stab;
   const uint16_t* gtab = c.gtab;
@@ -828,7 +827,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     trivial = L.trivial;                                                    \
     lit_tv = tree_root(L, 0, L.lit_tree);                                   \
     ctx_lut = ctx_lut_base + L.ctx_mode_off;                                \
-    BD_PIN32(cmd_tv); BD_PIN32(trivial); BD_PIN32(lit_tv); BD_PIN32(ctx_lut); \
+    ctx_map = stab + 2 * L.e_tab;                                           \
+    BD_PIN32(cmd_tv); BD_PIN32(trivial); BD_PIN32(lit_tv); BD_PIN32(ctx_lut); BD_PIN32(ctx_map); \
   } while (0)
 
   if (run) {
@@ -853,10 +853,6 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t pend_n = 0, pend_off = 0;
   const uint8_t* csrc = nullptr;  // next source byte of the copy being made
   uint32_t crem = 0;              // its remaining bytes
-  // second-level table entry requested (cp.async of its aligned 16-byte block to stage[32..47]) in an earlier
-  // round for the symbol this lane is waiting to decode; dsel = byte offset of the entry in that block
-  uint32_t dsel = 0;
-  bool dfresh = false;  // requested in THIS round: not there yet, the lane must not retry before the next round
   // round counter and the round in which this lane last requested an input block (see LN_SKIP)
   uint32_t rnd = 0, blk_round = 0xFFFFFFFFu;
   bool dhave = false;
@@ -902,24 +898,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 // One symbol of the tree rooted at TV (root width TR): sets BITS (the 32-bit peek), LEN and SYM, or -- when
 // the code is longer than the root -- requests the second-level entry and sets WAIT: the lane retries
 // this phase next round with the entry in `de` (DecodeSymbol, :377-391, over our table shape).
-#if BD_LANE_DEFER
-#define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
-  do {                                                                                           \
-    BITS = LN_PEEK();                                                                            \
-    const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                           \
-    uint32_t e_ = vlds16(stab + ((v_ < E ? v_ : 0u) << 1));                                      \
-    ld16_if(v_ >= E, gtab + (v_ - E), e_);  /* root outside the shared slot (rare) */             \
-    if (BD_UNLIKELY(dhave)) e_ = vlds16(stage + 32u + dsel);  /* the entry requested last round */ \
-    const bool need2_ = !dhave && (e_ & 15u) > (TR);                                             \
-    const uint32_t sub_ = need2_ ? (e_ & 15u) - (TR) : 0u;                                       \
-    const uint32_t i2_ = ((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits(sub_));                  \
-    cp_async16_if(need2_, stage + 32u, gtab + (i2_ & ~7u));                                      \
-    if (need2_) { dsel = (i2_ & 7u) << 1; dfresh = true; }                                       \
-    dhave = need2_; WAIT = need2_;                                                               \
-    LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
-  } while (0)
-#else
-#define LN_DECODE(TV, TR, BITS, LEN, SYM, WAIT)                                                  \
+#define LN_DECODE(TV, TR, BITS, LEN, SYM)                                                        \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
     const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                           \
@@ -930,7 +909,6 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     ld16_if(need2_, gtab + ((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits(sub_)), e_);           \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
-#endif
 // request the next copy chunk: min(crem, 16) bytes from csrc on; only 16-byte blocks that hold source bytes
 // are touched
 #define LN_ISSUE_CHUNK(ISS)                                                \
@@ -968,227 +946,272 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     pend_n = 0;                                                            \
   } while (0)
 
+  // Look-ahead for a symbol that will be decoded a phase later: the root look-up is done now and, when the code
+  // is longer than the root, its second-level entry (the aligned 16-byte block holding it) is requested with
+  // cp.async into stage[SLOT..SLOT+15].  PV/PE/PSEL: valid flag, entry (bit 31: take it from the stage), byte
+  // offset in the block.  Only for trees whose roots are in the shared slot (otherwise the later decode does
+  // the look-ups itself).
+#define LN_LOOKAHEAD(TV, TR, SLOT, PV, PE, PSEL)                                                 \
+  do {                                                                                           \
+    const uint32_t bits_ = LN_PEEK();                                                            \
+    const uint32_t v_ = (TV) + (bits_ & mask_bits(TR));                                          \
+    if (v_ < E) {                                                                                \
+      const uint32_t e_ = vlds16(stab + (v_ << 1));                                              \
+      PV = true; PE = e_;                                                                        \
+      if ((e_ & 15u) > (TR)) {                                                                   \
+        const uint32_t i2_ = ((e_ >> 4) << 1) + ((bits_ >> (TR)) & mask_bits((e_ & 15u) - (TR))); \
+        cp_async16(stage + (SLOT), (const uint8_t*)(gtab + (i2_ & ~7u)));                        \
+        PE = 0x80000000u; PSEL = (i2_ & 7u) << 1;                                                \
+      }                                                                                          \
+    }                                                                                            \
+  } while (0)
+// entry of a looked-ahead symbol (its group has been waited for)
+#define LN_TAKE(SLOT, PV, PE, PSEL, BITS, LEN, SYM)                                              \
+  do {                                                                                           \
+    BITS = LN_PEEK();                                                                            \
+    const uint32_t e_ = (PE & 0x80000000u) ? vlds16(stage + (SLOT) + PSEL) : PE;                 \
+    PV = false;                                                                                  \
+    LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
+  } while (0)
+
+  // look-ahead state: pa_* for the symbol phase A will decode next, pc_* for the distance symbol of phase C
+  bool pa_valid = false, pc_valid = false;
+  uint32_t pa_e = 0, pa_sel = 0, pc_e = 0, pc_sel = 0;
+
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
     rnd++;
-    dfresh = false;
-    // everything requested during the previous round's phases (second-level entries, input blocks) has landed;
-    // the copy chunk requested at its very end may still be on its way
+    // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
     cp_async_wait_all_but_latest();
 #ifdef BD_LANE_ROUND_STATS
-    BD_LANE_ROUND_STATS(ph, dhave);
+    BD_LANE_ROUND_STATS(ph, pa_valid);
 #endif
 
     // ---- phase A: one symbol for every lane at a command boundary (insert&copy command and its extra bits,
-    //      ReadCommandInternal :2134-2189) or inside a literal run (:2391-2551): the table lookup and the bit
+    //      ReadCommandInternal :2134-2189) or inside a literal run (:2391-2551): the table look-up and the bit
     //      skip are shared, only the short tails differ ----
     if (run && (ph == kPhCmd || ph == kPhLit)) {
       const bool is_lit = ph == kPhLit;
-      if (BD_UNLIKELY((is_lit ? bl_l : bl_c) == 0)) LN_BLOCK_SWITCH(is_lit ? 0u : 1u);
+      if (BD_UNLIKELY((is_lit ? bl_l : bl_c) == 0)) { LN_BLOCK_SWITCH(is_lit ? 0u : 1u); pa_valid = false; }
       if (ev == kStCommands) {
-        uint32_t tv = is_lit ? lit_tv : cmd_tv;
-        const uint32_t tr = is_lit ? r_lit : r_cmd;
-        if (is_lit && !trivial) {  // tree by the context of the last two bytes (:2500-2507)
-          if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
-          const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
-          tv = root_lit + (vlds8(slot + kSlotCtxMap + cx) << r_lit);
-        }
         uint32_t bits, len, sym;
-        bool wait = false;
-        LN_DECODE(tv, tr, bits, len, sym, wait);
-        if (!wait) {
-          uint32_t nskip = len;
-          if (is_lit) {
-            bl_l--;
-            append(out_al, bias, hist, posb, acc, sym, 1);
-            p2 = p1; p1 = sym;
-            if (--ins == 0) {
-              if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
-              else ph = kPhDist;
-            }
-          } else {
-            const uint2 lut = vlds64(cmd_lut + (sym << 3));
-            cmd_bits = lut.x;
-            ins = lut.x & 0xFFFFu;
-            copy_len = lut.y & 0xFFFFu;
-            const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
-            if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
-              const uint32_t x = bits >> len;
-              ins += x & mask_bits(ie);
-              copy_len += (x >> ie) & mask_bits(ce);
-              nskip = len + ie + ce;
-            } else {
-              LN_SKIP(len);
-              if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
-              copy_len += LN_PEEK() & mask_bits(ce);
-              nskip = ce;
-            }
-            bl_c--;
-            mlen -= (int32_t)ins;
-            ph = ins != 0 ? kPhLit : kPhDist;
-            ctx_fresh = false;
+        if (BD_LIKELY(pa_valid)) {
+          LN_TAKE(32u, pa_valid, pa_e, pa_sel, bits, len, sym);
+        } else {
+          uint32_t tv = is_lit ? lit_tv : cmd_tv;
+          const uint32_t tr = is_lit ? r_lit : r_cmd;
+          if (is_lit && !trivial) {  // tree by the context of the last two bytes (:2500-2507)
+            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
+            const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
+            tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
           }
-          LN_SKIP(nskip);
+          LN_DECODE(tv, tr, bits, len, sym);
+#ifdef BD_LANE_FALLBACK_STATS
+          BD_LANE_FALLBACK_STATS(0, is_lit);
+#endif
+        }
+        uint32_t nskip = len;
+        if (is_lit) {
+          bl_l--;
+          append(out_al, bias, hist, posb, acc, sym, 1);
+          p2 = p1; p1 = sym;
+          --ins;
+          // A second literal of the run in the same round when it costs no trip to the arena: one tree for all
+          // contexts, its root in the shared slot and the code no longer than the root.
+          if (ins != 0 && trivial && bl_l != 0 && len + r_lit <= 32) {
+            const uint32_t v2 = lit_tv + ((bits >> len) & mask_bits(r_lit));
+            const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
+            if (v2 < E && (e2 & 15u) <= r_lit) {
+              bl_l--;
+              append(out_al, bias, hist, posb, acc, e2 >> 4, 1);
+              p2 = p1; p1 = e2 >> 4;
+              --ins;
+              nskip += e2 & 15u;
+            }
+          }
+          if (ins == 0) {
+            if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+            else ph = kPhDist;
+          }
+        } else {
+          const uint2 lut = vlds64(cmd_lut + (sym << 3));
+          cmd_bits = lut.x;
+          ins = lut.x & 0xFFFFu;
+          copy_len = lut.y & 0xFFFFu;
+          const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
+          if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
+            const uint32_t x = bits >> len;
+            ins += x & mask_bits(ie);
+            copy_len += (x >> ie) & mask_bits(ce);
+            nskip = len + ie + ce;
+          } else {
+            LN_SKIP(len);
+            if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
+            copy_len += LN_PEEK() & mask_bits(ce);
+            nskip = ce;
+          }
+          bl_c--;
+          mlen -= (int32_t)ins;
+          ph = ins != 0 ? kPhLit : kPhDist;
+          ctx_fresh = false;
+        }
+        LN_SKIP(nskip);
+        // look ahead for the distance symbol this lane decodes in phase C of this round
+        if (ph == kPhDist && ev == kStCommands && !(cmd_bits & (1u << 26)) && bl_d != 0) {
+          const uint32_t tvd = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
+          LN_LOOKAHEAD(tvd, r_dist, 48u, pc_valid, pc_e, pc_sel);
         }
       }
     }
     warp_sync();
+    cp_async_commit();  // group: what phase A requested (distance look-ahead, input blocks)
 
     // ---- phase P: retire the copy chunk requested at the end of the previous round ----
-    cp_async_wait_all();
+    cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
     if (run && pend_n != 0) LN_RETIRE_CHUNK();
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
+    warp_sync();
+    cp_async_wait_all();  // the distance look-ahead
 
-    // ---- phase B (optional): further literals of the run (:2391-2551), up to kMaxLitPhases per round ----
-    for (uint32_t rep = 0; rep < kMaxLitPhases; rep++) {
-      if (!warp_any(run && ph == kPhLit && ev == kStCommands && !dfresh)) break;
-      if (run && ph == kPhLit && ev == kStCommands && !dfresh) {
-        if (BD_UNLIKELY(bl_l == 0)) LN_BLOCK_SWITCH(0);
-        if (ev == kStCommands) {
-          uint32_t tv = lit_tv;
-          if (!trivial) {  // tree by the context of the last two bytes (:2500-2507)
-            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
-            const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
-            tv = root_lit + (vlds8(slot + kSlotCtxMap + cx) << r_lit);
+    // ---- phase C1: distance symbol (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049) ----
+    int32_t dist = d0;
+    uint32_t push = 0;
+    const bool go = run && ph == kPhDist && ev == kStCommands;  // this lane makes its copy in this round
+    if (go && !(cmd_bits & (1u << 26))) {  // explicit distance symbol
+      if (BD_UNLIKELY(bl_d == 0)) { LN_BLOCK_SWITCH(2); pc_valid = false; }
+      if (ev == kStCommands) {
+        uint32_t bits, len, sym;
+        if (BD_LIKELY(pc_valid)) {
+          LN_TAKE(48u, pc_valid, pc_e, pc_sel, bits, len, sym);
+        } else {
+          const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
+          LN_DECODE(tv, r_dist, bits, len, sym);
+#ifdef BD_LANE_FALLBACK_STATS
+          BD_LANE_FALLBACK_STATS(1, 0);
+#endif
+        }
+        bl_d--;
+        push = 1;
+        if (sym >= 16) {
+          uint32_t base, nbits;
+          if (sym >= ndirect) {
+            const uint32_t distval = sym - ndirect;
+            const uint32_t hcode = distval >> npostfix;
+            nbits = (hcode >> 1) + 1;
+            base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
+          } else {
+            nbits = 0; base = sym - 15u;
           }
-          uint32_t bits, len, sym;
-          bool wait = false;
-          LN_DECODE(tv, r_lit, bits, len, sym, wait);
-          if (!wait) {
+          uint32_t extra;
+          if (BD_LIKELY(len + nbits <= 32)) {
+            extra = (bits >> len) & mask_bits(nbits);
+            LN_SKIP(len + nbits);
+          } else {
             LN_SKIP(len);
-            bl_l--;
-            append(out_al, bias, hist, posb, acc, sym, 1);
-            p2 = p1; p1 = sym;
-            if (--ins == 0) {
-              if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
-              else ph = kPhDist;
-            }
+            extra = LN_PEEK() & mask_bits(nbits);
+            LN_SKIP(nbits);
+          }
+          dist = (int32_t)(base + (extra << npostfix));
+        } else {
+          LN_SKIP(len);
+          if (sym == 0) {
+            push = 0;
+          } else if (sym < 4) {
+            dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
+          } else {
+            const uint32_t cc = sym - 4;
+            const int32_t b = cc < 6 ? d0 : d1;
+            const uint32_t m = cc < 6 ? cc : cc - 6;
+            const int32_t delta = (int32_t)(m >> 1) + 1;
+            dist = (m & 1) ? b + delta : b - delta;
+            if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
           }
         }
       }
     }
-    warp_sync();
-
-    // ---- phase C: distance (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049),
-    //      then the copy or static dictionary word (:2583-2689) whose source loads are issued here ----
-    if (run && ph == kPhDist && ev == kStCommands) {
-      int32_t dist = d0;
-      uint32_t push = 0;
-      bool wait = false;
-      if (!(cmd_bits & (1u << 26))) {  // explicit distance symbol
-        if (BD_UNLIKELY(bl_d == 0)) LN_BLOCK_SWITCH(2);
-        if (ev == kStCommands) {
-          const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
-          uint32_t bits, len, sym;
-          LN_DECODE(tv, r_dist, bits, len, sym, wait);
-          if (!wait) {
-            bl_d--;
-            push = 1;
-            if (sym >= 16) {
-              uint32_t base, nbits;
-              if (sym >= ndirect) {
-                const uint32_t distval = sym - ndirect;
-                const uint32_t hcode = distval >> npostfix;
-                nbits = (hcode >> 1) + 1;
-                base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
-              } else {
-                nbits = 0; base = sym - 15u;
-              }
-              uint32_t extra;
-              if (BD_LIKELY(len + nbits <= 32)) {
-                extra = (bits >> len) & mask_bits(nbits);
-                LN_SKIP(len + nbits);
-              } else {
-                LN_SKIP(len);
-                extra = LN_PEEK() & mask_bits(nbits);
-                LN_SKIP(nbits);
-              }
-              dist = (int32_t)(base + (extra << npostfix));
-            } else {
-              LN_SKIP(len);
-              if (sym == 0) {
-                push = 0;
-              } else if (sym < 4) {
-                dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
-              } else {
-                const uint32_t cc = sym - 4;
-                const int32_t b = cc < 6 ? d0 : d1;
-                const uint32_t m = cc < 6 ? cc : cc - 6;
-                const int32_t delta = (int32_t)(m >> 1) + 1;
-                dist = (m & 1) ? b + delta : b - delta;
-                if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
-              }
-            }
-          }
+    // ---- look ahead for the symbol phase A decodes next: the bit position of every lane is final for this round.
+    //      Lanes that just read their distance will be at a command boundary; lanes inside a literal run
+    //      (one tree for all contexts) continue with the literal tree ----
+    if (run && !pa_valid && ev == kStCommands) {
+      const bool next_cmd = go || ph == kPhCmd;
+      const bool next_lit = ph == kPhLit;
+      if (next_cmd ? bl_c != 0 : (next_lit && bl_l != 0)) {
+        uint32_t tv = next_cmd ? cmd_tv : lit_tv;
+        if (!next_cmd && !trivial) {  // tree by the context of the last two bytes (:2500-2507); phase P is over
+          if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
+          const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
+          tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
         }
+        LN_LOOKAHEAD(tv, next_cmd ? r_cmd : r_lit, 32u, pa_valid, pa_e, pa_sel);
       }
-      if (!wait && ev == kStCommands) {
-        const uint32_t pos = posb - bias;
-        const uint32_t max_distance = pos < max_backward ? pos : max_backward;
-        crem = 0;
-        if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
-          // static dictionary: the transformed word is an entry of the expanded table
-          if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
+    }
+    warp_sync();
+    cp_async_commit();  // group: next-A look-ahead (and phase C1's input blocks)
+
+    // ---- phase C2: the copy or static dictionary word (:2583-2689); its source bytes are requested below ----
+    if (go && ev == kStCommands) {
+      const uint32_t pos = posb - bias;
+      const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+      crem = 0;
+      if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
+        // static dictionary: the transformed word is an entry of the expanded table
+        if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
+          ev = kStBail;
+        } else {
+          const uint32_t wi = vlds32(word_info + copy_len * 4u);
+          const uint32_t shift = wi & 15u;
+          const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
+          const uint32_t t = word_id >> shift;
+          if (t >= BROTLI_NUM_TRANSFORMS) {
             ev = kStBail;
           } else {
-            const uint32_t wi = vlds32(word_info + copy_len * 4u);
-            const uint32_t shift = wi & 15u;
-            const uint32_t word_id = (uint32_t)dist - max_distance - 1u;
-            const uint32_t t = word_id >> shift;
-            if (t >= BROTLI_NUM_TRANSFORMS) {
+            const uint32_t ti = vlds32(transform_info + t * 4u);
+            const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
+            if (n > capb - posb) {
               ev = kStBail;
             } else {
-              const uint32_t ti = vlds32(transform_info + t * 4u);
-              const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
-              if (n > capb - posb) {
-                ev = kStBail;
-              } else {
-                csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
-                crem = n;
-                mlen -= (int32_t)n;
-              }
+              csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
+              crem = n;
+              mlen -= (int32_t)n;
             }
-          }
-        } else {
-          if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
-          if (BD_UNLIKELY(copy_len > capb - posb)) {
-            ev = kStBail;
-          } else {
-            mlen -= (int32_t)copy_len;
-            crem = copy_len;
-            uint32_t ud = (uint32_t)dist;
-            if (BD_UNLIKELY(ud < 20)) {
-              // Short period: copy byte-wise until the period can be widened to >= 20 (a copy at distance d
-              // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
-              const uint32_t wide = ud * ((19u + ud) / ud);
-              const uint32_t m = crem < wide ? crem : wide;
-              for (uint32_t i = 0; i < m; i++) {
-                // source byte: still in the partial word, or in the history ring (never a load from global memory)
-                const uint32_t sp = posb - ud;
-                const uint32_t b = sp >= (posb & ~3u) ? (acc >> (8 * (sp & 3u))) & 0xFFu : vlds8(hist + (sp & 31u));
-                append(out_al, bias, hist, posb, acc, b, 1);
-              }
-              crem -= m;
-              ud = wide;
-            }
-            // Everything below the current output word is in memory, and a distance >= 20 keeps the sixteen
-            // source bytes of every chunk below that word at the time the chunk is loaded.
-            csrc = out_al + (posb - ud);
           }
         }
-        if (ev == kStCommands) {
-          if (mlen <= 0) ev = kStHeader;  // end of the metablock; the copy is drained after the loop
-          else ph = kPhCopy;
+      } else {
+        if (push) { d3 = d2; d2 = d1; d1 = d0; d0 = dist; }
+        if (BD_UNLIKELY(copy_len > capb - posb)) {
+          ev = kStBail;
+        } else {
+          mlen -= (int32_t)copy_len;
+          crem = copy_len;
+          uint32_t ud = (uint32_t)dist;
+          if (BD_UNLIKELY(ud < 20)) {
+            // Short period: copy byte-wise until the period can be widened to >= 20 (a copy at distance d
+            // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
+            const uint32_t wide = ud * ((19u + ud) / ud);
+            const uint32_t m = crem < wide ? crem : wide;
+            for (uint32_t i = 0; i < m; i++) {
+              // source byte: still in the partial word, or in the history ring (never a load from global memory)
+              const uint32_t sp = posb - ud;
+              const uint32_t b = sp >= (posb & ~3u) ? (acc >> (8 * (sp & 3u))) & 0xFFu : vlds8(hist + (sp & 31u));
+              append(out_al, bias, hist, posb, acc, b, 1);
+            }
+            crem -= m;
+            ud = wide;
+          }
+          // Everything below the current output word is in memory, and a distance >= 20 keeps the sixteen
+          // source bytes of every chunk below that word at the time the chunk is loaded.
+          csrc = out_al + (posb - ud);
         }
       }
+      if (ev == kStCommands) {
+        if (mlen <= 0) ev = kStHeader;  // end of the metablock; the copy is drained after the loop
+        else ph = kPhCopy;
+      }
     }
-    // ---- the one place where copy source loads are issued (a single definition of the chunk registers
-    //      keeps the compiler from moving just-loaded values around) ----
     warp_sync();
-    cp_async_commit();  // group 1 of the round: what the phases requested
     LN_ISSUE_CHUNK(run && crem != 0 && ev != kStBail);
-    cp_async_commit();  // group 2 of the round: the copy chunk
+    cp_async_commit();  // group: the copy chunk
     // last chunk in flight (or nothing to copy: zero-length dictionary output): the next command can be decoded
     if (run && ph == kPhCopy && crem == 0 && ev == kStCommands) ph = kPhCmd;
     if (run && ev != kStCommands) {  // this lane's registers stay as they are until the whole warp is through
@@ -1213,6 +1236,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #undef LN_TREES
 #undef LN_BLOCK_SWITCH
 #undef LN_DECODE
+#undef LN_LOOKAHEAD
+#undef LN_TAKE
 #undef LN_ISSUE_CHUNK
 #undef LN_RETIRE_CHUNK
 }

@@ -30,7 +30,7 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
   // while keeping its address modulo 16
   alignas(16) static uint8_t ring[32];
   alignas(16) static uint8_t hist[32];
-  alignas(16) static uint8_t stage[48];
+  alignas(16) static uint8_t stage[64];
   c.hist = hw::to_sref(hist);
   c.stage = hw::to_sref(stage);
   c.ring = hw::to_sref(ring);
