@@ -641,7 +641,7 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   // Root widths.  Groups (0 literal, 1 command, 2 distance) whose narrowest roots do not all fit the shared
   // slot are moved to the arena, largest first; the rest share the slot and are widened, cheapest step first.
   const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
-  const uint32_t rmin[3] = {5, 5, 4}, rmax[3] = {8, 8, 7};
+  const uint32_t rmin[3] = {4, 4, 3}, rmax[3] = {8, 8, 7};
   uint32_t rb[3] = {rmin[0], rmin[1], rmin[2]};
   bool shared[3] = {true, true, true};
   for (;;) {
