@@ -101,6 +101,8 @@ struct DeviceCtx {
   uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
   uint32_t* bail_count = nullptr;
   DevBuf bail_list;
+  DevBuf order;                // longest-first order of a batch (lane kernel), see launch_order_by_size
+  bool sort_streams = true;    // BROTLI_B200_SORT=0: decode in batch order
   uint8_t* arena = nullptr;
   uint8_t* dictionary = nullptr;
   uint32_t* ticket = nullptr;
@@ -180,6 +182,8 @@ DeviceCtx* acquire_ctx() {
     }
     g_launches.fetch_add(1);
     c->bail_count = c->ticket + 16;  // same 256-byte allocation as the tickets
+    const char* sort_env = getenv("BROTLI_B200_SORT");
+    c->sort_streams = !(sort_env && sort_env[0] == '0');
   }
   c->ready = true;
   return c;
@@ -211,6 +215,13 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
     const size_t total_warps = (size_t)c->lane_ctas * c->lane_warps;
     const size_t per_warp = (n + total_warps - 1) / total_warps;
     la.chunk = per_warp >= 32 ? 32u : (uint32_t)per_warp;
+    if (c->sort_streams && n >= 64) {
+      const size_t temp = brotli_b200::order_temp_bytes((uint32_t)n);
+      CU_TRY(c->order.reserve(4 * n * sizeof(uint32_t) + temp + 256));
+      CU_TRY(brotli_b200::launch_order_by_size((uint32_t)n, d_in_off, (uint32_t*)c->order.p, temp, stream));
+      g_launches.fetch_add(2);
+      a.order = (const uint32_t*)c->order.p + 3 * n;
+    }
     CU_TRY(brotli_b200::launch_decode_lane(a, la, c->lane_ctas, c->lane_warps, stream));
     g_launches.fetch_add(1);
     // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
@@ -257,7 +268,9 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     size_t e = b; uint64_t acc = 0;
     // a chunk should fill every resident lane of the lane kernel: a launch takes about as long for a few streams
     // as for one stream per lane
-    const size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
+    // (the first chunk is a quarter of that: its H2D copy is not hidden behind anything)
+    size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
+    if (b == 0) min_streams /= 4;
     while (e < n && (e == b || acc < kPipelineChunkBytes || e - b < min_streams)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
     chunks.push_back(Chunk{b, e, nullptr, nullptr});
     b = e;
@@ -645,7 +658,7 @@ void BrotliB200Shutdown(void) {
     if (c->lane_arena) cudaFree(c->lane_arena);
     if (c->xdict) cudaFree(c->xdict);
     c->xdict = nullptr;
-    c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release();
+    c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release(); c->order.release();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
     cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
     for (auto& t : c->ev_t) for (auto& e : t) if (e) { cudaEventDestroy(e); e = nullptr; }

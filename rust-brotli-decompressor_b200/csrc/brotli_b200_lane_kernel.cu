@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "brotli_b200_runtime.h"
 #include "brotli_decode_lane.cuh"
 
@@ -100,6 +102,36 @@ size_t xdict_bytes() { return (size_t)lane::xdict_layout().total + 64; }
 cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream) {
   brotli_build_xdict_kernel<<<dim3(64, BROTLI_MAX_DICTIONARY_WORD_LENGTH - BROTLI_MIN_DICTIONARY_WORD_LENGTH + 1), 256, 0, stream>>>(dictionary, xdict);
   return cudaGetLastError();
+}
+
+// ---- longest-first order ----------------------------------------------------------------------------
+// The rounds a warp needs are the maximum over its 32 streams, so streams that take similar work should share
+// a warp, and the longest should start first.  Compressed size predicts the work well (correlation 0.9 on
+// text, and it separates the stream families of a mixed batch): streams are ordered by descending
+// compressed size in 256-byte buckets (stable, so equal buckets keep batch order).
+__global__ void brotli_order_keys_kernel(uint32_t n, const uint64_t* in_off, uint32_t* keys, uint32_t* vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint64_t sz = (in_off[i + 1] - in_off[i]) >> 8;
+    keys[i] = sz > 0xFFFFFFu ? 0xFFFFFFu : (uint32_t)sz;
+    vals[i] = i;
+  }
+}
+
+size_t order_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)n, 0, 24);
+  return bytes;
+}
+
+// scratch: 4 * n uint32 (keys in/out, values in/out) followed by order_temp_bytes(n); the order lands in scratch + 3 * n
+cudaError_t launch_order_by_size(uint32_t n, const uint64_t* in_off, uint32_t* scratch, size_t temp_bytes, cudaStream_t stream) {
+  uint32_t* keys_a = scratch, *keys_b = scratch + n, *vals_a = scratch + 2 * (size_t)n, *vals_b = scratch + 3 * (size_t)n;
+  brotli_order_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, in_off, keys_a, vals_a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cub::DeviceRadixSort::SortPairsDescending((void*)(scratch + 4 * (size_t)n), temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 24, stream);
 }
 
 namespace {

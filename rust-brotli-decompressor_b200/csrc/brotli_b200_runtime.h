@@ -63,6 +63,8 @@ int query_resident_ctas(int device);
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream);
 size_t lane_arena_bytes_per_lane();
 uint32_t lane_slot_bytes(int warps);
+size_t order_temp_bytes(uint32_t n);
+cudaError_t launch_order_by_size(uint32_t n, const uint64_t* in_off, uint32_t* scratch, size_t temp_bytes, cudaStream_t stream);
 size_t xdict_bytes();
 cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream);
 int query_lane_resident_ctas(int device, int warps);

@@ -56,6 +56,10 @@ constexpr uint32_t kCtxMapEntries = 32;      // table entries the 64-byte contex
 constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
 constexpr uint32_t kBlockRootBits = 6;
+#ifndef BD_LANE_EXTRA_LITERALS
+#define BD_LANE_EXTRA_LITERALS 1
+#endif
+constexpr uint32_t kMaxExtraLiterals = BD_LANE_EXTRA_LITERALS;  // literals a lane may add to its phase-A literal per round
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
   static constexpr size_t kCtxLit = kTab + 2 * (size_t)kGlobalTab;    // u8[64 * kMaxBlockTypes]
@@ -1016,15 +1020,16 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           append(out_al, bias, hist, posb, acc, sym, 1);
           p2 = p1; p1 = sym;
           --ins;
-          // A second literal of the run in the same round when it costs no trip to the arena: one tree for all
-          // contexts, its root in the shared slot and the code no longer than the root.
-          if (ins != 0 && trivial && bl_l != 0 && len + r_lit <= 32) {
-            const uint32_t v2 = lit_tv + ((bits >> len) & mask_bits(r_lit));
-            const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
-            if (v2 < E && (e2 & 15u) <= r_lit) {
+          // Further literals of the run in the same round while they cost no trip to the arena: one tree for all
+          // contexts, its root in the shared slot, the code no longer than the root and inside the 32-bit peek.
+          if (trivial) {
+            for (uint32_t rep = 0; rep < kMaxExtraLiterals; rep++) {
+              if (ins == 0 || bl_l == 0 || nskip + r_lit > 32) break;
+              const uint32_t v2 = lit_tv + ((bits >> nskip) & mask_bits(r_lit));
+              const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
+              if (v2 >= E || (e2 & 15u) > r_lit) break;
               bl_l--;
               append(out_al, bias, hist, posb, acc, e2 >> 4, 1);
-              p2 = p1; p1 = e2 >> 4;
               --ins;
               nskip += e2 & 15u;
             }
