@@ -359,7 +359,7 @@ def main():
                            int(all_n), desc, n_unique, n),
                        "compressed_bytes": int(all_c), "decompressed_bytes": int(all_d), "l2_policy": "inputs+outputs per step (%.1f GB/GPU) >> 126 MB L2" % algo,
                        "parallelism": "independent streams split evenly over %d GPU(s), no data-path collective" % world},
-            "bit_exact": bool(all_exact == world),
+            "bit_exact": bool(all_exact >= 1.0),  # minimum over ranks of each rank's verdict
             "verification": "per-stream 64-bit checksums of all streams vs originals + full byte compare of 4096 streams per GPU",
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
