@@ -663,12 +663,22 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     rb[g] = (ntrees[g] << rmax[g]) <= kGlobalTab / 2 ? rmax[g] : rmin[g];  // the arena has room for wide roots
 #endif
   }
+  // Widen where it pays most: a step R -> R+1 of group g costs ntrees << R entries and saves the second-level
+  // look-ups of the symbols whose codes are R+1 bits long.  Typical shares of symbols with codes longer than R
+  // (per cent; text and binary corpora) stand in for the streams' own statistics, weighted by
+  // how many symbols of each kind a command brings (literals count double in literal-heavy data; here 1:1:1).
+  static const uint8_t kLongShare[3][6] = {{97, 66, 36, 18, 9, 3},   // literal:  R = 3..8
+                                           {51, 37, 25, 16, 10, 6},  // command
+                                           {78, 32, 12, 5, 3, 1}};   // distance
   for (;;) {
-    uint32_t total = 0, g = 3, best = 0xFFFFFFFFu;
+    uint32_t total = 0, g = 3;
+    uint32_t best_num = 0, best_den = 1;  // benefit / cost of the best step, compared as fractions
     for (uint32_t i = 0; i < 3; i++) if (shared[i]) total += ntrees[i] << rb[i];
     for (uint32_t i = 0; i < 3; i++) if (shared[i] && rb[i] < rmax[i]) {
       const uint32_t extra = ntrees[i] << rb[i];
-      if (total + extra <= L.e_tab && extra < best) { best = extra; g = i; }
+      if (total + extra > L.e_tab) continue;
+      const uint32_t num = (uint32_t)kLongShare[i][rb[i] - 3] - (rb[i] + 1 <= 8 ? (uint32_t)kLongShare[i][rb[i] - 2] : 0u);
+      if (g == 3 || num * best_den > best_num * extra) { best_num = num; best_den = extra; g = i; }
     }
     if (g == 3) break;
     rb[g]++;
@@ -1173,7 +1183,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           } else {
             const uint32_t ti = vlds32(transform_info + t * 4u);
             const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
-            if (n > capb - posb) {
+            if (n > capb - posb || n == 0) {  // (an empty word makes no progress: left to the exact decoder)
               ev = kStBail;
             } else {
               csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
