@@ -95,6 +95,11 @@ static inline void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) { if (co
 // asynchronous 16-byte copy global -> "shared": immediate on the host
 static inline void cp_async16(hw::sref_t dst, const uint8_t* src) { memcpy((void*)dst, src, 16); }
 static inline void cp_async16_if(bool cond, hw::sref_t dst, const void* src) { if (cond) memcpy((void*)dst, src, 16); }
+static inline uint64_t l2_policy_stream() { return 0; }
+static inline uint64_t l2_policy_keep() { return 0; }
+static inline void cp_async16_hint(hw::sref_t dst, const uint8_t* src, uint64_t) { memcpy((void*)dst, src, 16); }
+static inline void cp_async16_if_hint(bool cond, hw::sref_t dst, const void* src, uint64_t) { if (cond) memcpy((void*)dst, src, 16); }
+static inline void st32_stream(uint8_t* p, uint32_t v, uint64_t) { memcpy(p, &v, 4); }
 static inline void cp_async_commit() {}
 static inline void cp_async_wait_all_but_latest() {}
 static inline void cp_async_wait_all() {}
@@ -109,10 +114,28 @@ BD_DEV uint2 vlds64(hw::sref_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,
 BD_DEV uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
 BD_DEV uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
+#ifndef BD_LANE_L2_HINTS
+#define BD_LANE_L2_HINTS 1
+#endif
+#if BD_LANE_L2_HINTS
+BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }  // streaming: evict first
+#else
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
+#endif
 // LDGSTS: the input stream reaches shared memory without passing through a register, so nothing in the
 // decode loop ever waits on (or moves) an in-flight global load of compressed bytes
 BD_DEV void cp_async16(hw::sref_t dst, const uint8_t* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+// L2 eviction policies: streaming data (compressed input, output words, backreference sources) is marked
+// evict-first, the per-lane table arena evict-last, so that the tables stay L2-resident under the stream
+BD_DEV uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+BD_DEV uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+BD_DEV void cp_async16_hint(hw::sref_t dst, const uint8_t* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+BD_DEV void cp_async16_if_hint(bool cond, hw::sref_t dst, const void* src, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%1], [%2], 16, %3;\n\t}" ::"r"((uint32_t)cond), "r"(dst), "l"(src), "l"(pol) : "memory");
+}
+BD_DEV void st32_stream(uint8_t* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory"); }
 BD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // predicated 16-byte copy (stays predicated: no branch, see ld16_if).  .cg: served by L2, where this thread's
 // earlier stores are, never by a possibly stale L1 line.
@@ -296,6 +319,14 @@ BD_DEV void append8(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& p
 BD_DEV void flush_partial(uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_t acc) {
   const uint32_t a = posb & 3u, wpos = posb & ~3u;
   for (uint32_t j = 0; j < a; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(acc >> (8 * j));
+}
+// Four recent output bytes sp .. sp+3 (sp + 3 < posb, sp within the last 28 bytes): from the partial word and the
+// history ring.
+BD_DEV uint32_t recent4(hw::sref_t hist, uint32_t posb, uint32_t acc, uint32_t sp) {
+  const uint32_t wcur = posb & ~3u, w0p = sp & ~3u, w1p = w0p + 4;
+  const uint32_t w0 = w0p == wcur ? acc : vlds32(hist + (w0p & 28u));
+  const uint32_t w1 = w1p == wcur ? acc : (w1p < wcur ? vlds32(hist + (w1p & 28u)) : 0u);
+  return hw::funnelshift_r(w0, w1, 8 * (sp & 3u));
 }
 // Last two output bytes (p1 = newest), zero before the start of the stream: the literal context.
 BD_DEV void last_two(hw::sref_t hist, uint32_t bias, uint32_t posb, uint32_t acc, uint32_t& p1, uint32_t& p2) {
@@ -871,6 +902,17 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t rnd = 0, blk_round = 0xFFFFFFFFu;
   bool dhave = false;
 
+#if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
+  uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
+  BD_PIN64(pol_stream); BD_PIN64(pol_keep);
+#define LN_CP16_STREAM(DST, SRC) cp_async16_hint(DST, SRC, pol_stream)
+#define LN_CP16_KEEP(DST, SRC) cp_async16_hint(DST, SRC, pol_keep)
+#define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
+#else
+#define LN_CP16_STREAM(DST, SRC) cp_async16(DST, SRC)
+#define LN_CP16_KEEP(DST, SRC) cp_async16(DST, SRC)
+#define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
+#endif
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
 // Bits consumed; on a word boundary the window takes word k + 2 from the ring.  When that word starts a new
 // 16-byte block, the block after it is requested with cp.async -- not committed here: the round's convergent
@@ -885,7 +927,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if ((j_ & 3u) == 0) {                                                                      \
         if (BD_UNLIKELY(blk_round == rnd)) { cp_async_commit(); cp_async_wait_all(); }           \
         const uint32_t b_ = (j_ >> 2) + 1;                                                       \
-        cp_async16(ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
+        LN_CP16_STREAM(ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
         blk_round = rnd;                                                                         \
       }                                                                                          \
       nx = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);                       \
@@ -930,8 +972,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool iss_ = (ISS);                                               \
     const uint32_t nn_ = crem < 16 ? crem : 16u;                           \
     const uint32_t off_ = (uint32_t)(uintptr_t)csrc & 15u;                 \
-    cp_async16_if(iss_, stage, csrc - off_);                               \
-    cp_async16_if(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16);  \
+    LN_CP16_IF_STREAM(iss_, stage, csrc - off_);                           \
+    LN_CP16_IF_STREAM(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
     if (iss_) { pend_n = nn_; pend_off = off_; crem -= nn_; csrc += 16; }  \
   } while (0)
 // append the chunk in flight to the output
@@ -974,7 +1016,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       PV = true; PE = e_;                                                                        \
       if ((e_ & 15u) > (TR)) {                                                                   \
         const uint32_t i2_ = ((e_ >> 4) << 1) + ((bits_ >> (TR)) & mask_bits((e_ & 15u) - (TR))); \
-        cp_async16(stage + (SLOT), (const uint8_t*)(gtab + (i2_ & ~7u)));                        \
+        LN_CP16_KEEP(stage + (SLOT), (const uint8_t*)(gtab + (i2_ & ~7u)));                      \
         PE = 0x80000000u; PSEL = (i2_ & 7u) << 1;                                                \
       }                                                                                          \
     }                                                                                            \
@@ -1205,11 +1247,17 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
             const uint32_t wide = ud * ((19u + ud) / ud);
             const uint32_t m = crem < wide ? crem : wide;
-            for (uint32_t i = 0; i < m; i++) {
-              // source byte: still in the partial word, or in the history ring (never a load from global memory)
-              const uint32_t sp = posb - ud;
-              const uint32_t b = sp >= (posb & ~3u) ? (acc >> (8 * (sp & 3u))) & 0xFFu : vlds8(hist + (sp & 31u));
-              append(out_al, bias, hist, posb, acc, b, 1);
+            // up to four bytes per step, sources from the partial word and the history ring (never a load from
+            // global memory); while the period is shorter than four bytes it is widened as the bytes come out
+            uint32_t dd = ud;
+            for (uint32_t left = m; left != 0;) {
+              uint32_t n4 = dd < 4 ? dd : 4u;
+              if (n4 > left) n4 = left;
+              uint32_t v = recent4(hist, posb, acc, posb - dd);
+              if (n4 < 4) v &= mask_bits(8 * n4);
+              append(out_al, bias, hist, posb, acc, v, n4);
+              left -= n4;
+              if (dd < 4) dd += ud;
             }
             crem -= m;
             ud = wide;
@@ -1246,6 +1294,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
   if (ran) LN_SAVE();
 #undef LN_PEEK
+#undef LN_CP16_STREAM
+#undef LN_CP16_KEEP
+#undef LN_CP16_IF_STREAM
 #undef LN_SKIP
 #undef LN_SAVE
 #undef LN_TREES
