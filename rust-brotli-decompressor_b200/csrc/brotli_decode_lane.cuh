@@ -905,11 +905,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
   BD_PIN64(pol_stream); BD_PIN64(pol_keep);
-#define LN_CP16_STREAM(DST, SRC) cp_async16_hint(DST, SRC, pol_stream)
 #define LN_CP16_KEEP(DST, SRC) cp_async16_hint(DST, SRC, pol_keep)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
 #else
-#define LN_CP16_STREAM(DST, SRC) cp_async16(DST, SRC)
 #define LN_CP16_KEEP(DST, SRC) cp_async16(DST, SRC)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #endif
@@ -921,18 +919,17 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_SKIP(n)                                                                               \
   do {                                                                                           \
     bp += (n);                                                                                   \
-    if (bp >= 32) {                                                                              \
-      lo = hi; hi = nx; k++;                                                                     \
-      const uint32_t j_ = k + 2;                                                                 \
-      if ((j_ & 3u) == 0) {                                                                      \
-        if (BD_UNLIKELY(blk_round == rnd)) { cp_async_commit(); cp_async_wait_all(); }           \
-        const uint32_t b_ = (j_ >> 2) + 1;                                                       \
-        LN_CP16_STREAM(ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
-        blk_round = rnd;                                                                         \
-      }                                                                                          \
-      nx = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);                       \
-      bp -= 32;                                                                                  \
-    }                                                                                            \
+    const bool adv_ = bp >= 32;  /* branch-free word shift: nearly every round some lane needs it */ \
+    k += adv_ ? 1u : 0u;                                                                         \
+    const uint32_t j_ = k + 2;                                                                   \
+    const bool blk_ = adv_ && (j_ & 3u) == 0;                                                    \
+    if (BD_UNLIKELY(blk_ && blk_round == rnd)) { cp_async_commit(); cp_async_wait_all(); }       \
+    const uint32_t b_ = (j_ >> 2) + 1;                                                           \
+    LN_CP16_IF_STREAM(blk_, ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
+    blk_round = blk_ ? rnd : blk_round;                                                          \
+    const uint32_t nw_ = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);         \
+    lo = adv_ ? hi : lo; hi = adv_ ? nx : hi; nx = adv_ ? nw_ : nx;                              \
+    bp &= 31u;                                                                                   \
   } while (0)
 #define LN_SAVE()                                                                                   \
   do {                                                                                              \
@@ -1025,7 +1022,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_TAKE(SLOT, PV, PE, PSEL, BITS, LEN, SYM)                                              \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
-    const uint32_t e_ = (PE & 0x80000000u) ? vlds16(stage + (SLOT) + PSEL) : PE;                 \
+    const uint32_t es_ = vlds16(stage + (SLOT) + PSEL);  /* unconditional: no branch */          \
+    const uint32_t e_ = (PE & 0x80000000u) ? es_ : PE;                                           \
     PV = false;                                                                                  \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
@@ -1294,7 +1292,6 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
   if (ran) LN_SAVE();
 #undef LN_PEEK
-#undef LN_CP16_STREAM
 #undef LN_CP16_KEEP
 #undef LN_CP16_IF_STREAM
 #undef LN_SKIP
