@@ -86,6 +86,8 @@ static inline uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {  //
 }
 static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+static inline void st32_if(bool cond, uint8_t* p, uint32_t v) { if (cond) memcpy(p, &v, 4); }
+static inline void sts32_if(bool cond, hw::sref_t a, uint32_t v) { if (cond) *(uint32_t*)a = v; }
 static inline void warp_sync() {}
 static inline bool warp_any(bool p) { return p; }
 #define BD_PIN32(x) ((void)0)
@@ -122,6 +124,17 @@ BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], 
 #else
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
 #endif
+// predicated stores that stay predicated (no branch around a one-instruction body)
+BD_DEV void sts32_if(bool cond, hw::sref_t a, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "r"(a), "r"(v) : "memory");
+}
+BD_DEV void st32_if(bool cond, uint8_t* p, uint32_t v) {
+#if BD_LANE_L2_HINTS
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
+#endif
+}
 // LDGSTS: the input stream reaches shared memory without passing through a register, so nothing in the
 // decode loop ever waits on (or moves) an in-flight global load of compressed bytes
 BD_DEV void cp_async16(hw::sref_t dst, const uint8_t* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
@@ -277,24 +290,21 @@ BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint3
 // Every word that leaves for global memory is mirrored into a 32-byte per-lane history ring in shared memory
 // (hist + (position & 31)): short-distance copies read their source from there instead of waiting for a
 // just-stored byte to come back from L2.
-BD_DEV void store_word(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
-  sts32(hist + (wpos & 28u), word);
-  if (BD_UNLIKELY(wpos < bias)) {  // first word of an unaligned region: bytes below the region are not ours
+BD_DEV void store_word_if(bool cond, uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
+  sts32_if(cond, hist + (wpos & 28u), word);
+  if (BD_UNLIKELY(cond && wpos < bias)) {  // first word of an unaligned region: bytes below the region are not ours
     for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
   } else {
-    st32(out_al + wpos, word);
+    st32_if(cond, out_al + wpos, word);
   }
 }
 // v holds exactly n (1..4) valid low bytes, the rest is zero
 BD_DEV void append(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& posb, uint32_t& acc, uint32_t v, uint32_t n) {
   const uint32_t a = posb & 3u, sh = a * 8u;
   const uint32_t word = acc | (v << sh);
-  if (a + n >= 4) {
-    store_word(out_al, bias, hist, posb & ~3u, word);
-    acc = funnelshift_rc(v, 0u, 32u - sh);
-  } else {
-    acc = word;
-  }
+  const bool full = a + n >= 4;
+  store_word_if(full, out_al, bias, hist, posb & ~3u, word);
+  acc = full ? funnelshift_rc(v, 0u, 32u - sh) : word;
   posb += n;
 }
 // v_hi:v_lo holds exactly n (1..8) valid low bytes, the rest is zero
@@ -303,17 +313,11 @@ BD_DEV void append8(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& p
   const uint32_t x0 = acc | (v_lo << sh);
   const uint32_t x1 = funnelshift_l(v_lo, v_hi, sh);
   const uint32_t t = a + n;
-  if (t >= 8) {
-    store_word(out_al, bias, hist, wpos, x0);
-    sts32(hist + ((wpos + 4) & 28u), x1);
-    st32(out_al + wpos + 4, x1);
-    acc = funnelshift_rc(v_hi, 0u, 32u - sh);
-  } else if (t >= 4) {
-    store_word(out_al, bias, hist, wpos, x0);
-    acc = x1;
-  } else {
-    acc = x0;
-  }
+  const bool s0 = t >= 4, s1 = t >= 8;
+  store_word_if(s0, out_al, bias, hist, wpos, x0);
+  sts32_if(s1, hist + ((wpos + 4) & 28u), x1);
+  st32_if(s1, out_al + wpos + 4, x1);
+  acc = s1 ? funnelshift_rc(v_hi, 0u, 32u - sh) : (s0 ? x1 : x0);
   posb += n;
 }
 BD_DEV void flush_partial(uint8_t* out_al, uint32_t bias, uint32_t posb, uint32_t acc) {
@@ -905,10 +909,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
   BD_PIN64(pol_stream); BD_PIN64(pol_keep);
-#define LN_CP16_KEEP(DST, SRC) cp_async16_hint(DST, SRC, pol_keep)
+#define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_keep)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
 #else
-#define LN_CP16_KEEP(DST, SRC) cp_async16(DST, SRC)
+#define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #endif
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
@@ -1008,15 +1012,13 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   do {                                                                                           \
     const uint32_t bits_ = LN_PEEK();                                                            \
     const uint32_t v_ = (TV) + (bits_ & mask_bits(TR));                                          \
-    if (v_ < E) {                                                                                \
-      const uint32_t e_ = vlds16(stab + (v_ << 1));                                              \
-      PV = true; PE = e_;                                                                        \
-      if ((e_ & 15u) > (TR)) {                                                                   \
-        const uint32_t i2_ = ((e_ >> 4) << 1) + ((bits_ >> (TR)) & mask_bits((e_ & 15u) - (TR))); \
-        LN_CP16_KEEP(stage + (SLOT), (const uint8_t*)(gtab + (i2_ & ~7u)));                      \
-        PE = 0x80000000u; PSEL = (i2_ & 7u) << 1;                                                \
-      }                                                                                          \
-    }                                                                                            \
+    const bool in_ = v_ < E;                                                                     \
+    const uint32_t e_ = vlds16(stab + ((in_ ? v_ : 0u) << 1));                                   \
+    const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
+    const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
+    const uint32_t i2_ = ((e_ >> 4) << 1) + ((bits_ >> (TR)) & mask_bits(sub_));                 \
+    LN_CP16_IF_KEEP(two_, stage + (SLOT), gtab + (i2_ & ~7u));                                   \
+    PV = in_; PE = two_ ? 0x80000000u : e_; PSEL = two_ ? (i2_ & 7u) << 1 : PSEL;                \
   } while (0)
 // entry of a looked-ahead symbol (its group has been waited for)
 #define LN_TAKE(SLOT, PV, PE, PSEL, BITS, LEN, SYM)                                              \
@@ -1147,42 +1149,33 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #endif
         }
         bl_d--;
-        push = 1;
-        if (sym >= 16) {
-          uint32_t base, nbits;
-          if (sym >= ndirect) {
-            const uint32_t distval = sym - ndirect;
-            const uint32_t hcode = distval >> npostfix;
-            nbits = (hcode >> 1) + 1;
-            base = ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
-          } else {
-            nbits = 0; base = sym - 15u;
-          }
-          uint32_t extra;
-          if (BD_LIKELY(len + nbits <= 32)) {
-            extra = (bits >> len) & mask_bits(nbits);
-            LN_SKIP(len + nbits);
-          } else {
-            LN_SKIP(len);
-            extra = LN_PEEK() & mask_bits(nbits);
-            LN_SKIP(nbits);
-          }
-          dist = (int32_t)(base + (extra << npostfix));
-        } else {
+        // one straight-line computation for both kinds of distance symbol, one bit skip
+        const bool longcode = sym >= 16;
+        const bool direct = sym < ndirect;
+        const uint32_t distval = sym - ndirect;
+        const uint32_t hcode = distval >> npostfix;
+        const uint32_t nbits = (longcode && !direct) ? (hcode >> 1) + 1 : 0u;
+        const uint32_t base = direct ? sym - 15u
+                                     : ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
+        uint32_t extra, nskip = len + nbits;
+        if (BD_UNLIKELY(nskip > 32)) {
           LN_SKIP(len);
-          if (sym == 0) {
-            push = 0;
-          } else if (sym < 4) {
-            dist = sym == 1 ? d1 : (sym == 2 ? d2 : d3);
-          } else {
-            const uint32_t cc = sym - 4;
-            const int32_t b = cc < 6 ? d0 : d1;
-            const uint32_t m = cc < 6 ? cc : cc - 6;
-            const int32_t delta = (int32_t)(m >> 1) + 1;
-            dist = (m & 1) ? b + delta : b - delta;
-            if (!(m & 1) && dist <= 0) dist = 0x7fffffff;
-          }
+          extra = LN_PEEK() & mask_bits(nbits);
+          nskip = nbits;
+        } else {
+          extra = (bits >> len) & mask_bits(nbits);
         }
+        LN_SKIP(nskip);
+        // last distances (sym 0..3) and last / second-to-last distance -3..+3 (sym 4..15), :2017-2049
+        const uint32_t cc = sym - 4;
+        const uint32_t m = cc < 6 ? cc : cc - 6;
+        const int32_t delta = (int32_t)(m >> 1) + 1;
+        const int32_t rb0 = sym == 1 ? d1 : (sym == 2 ? d2 : (sym == 3 ? d3 : d0));
+        const int32_t rb4 = cc < 6 ? d0 : d1;
+        int32_t sd = sym < 4 ? rb0 : ((m & 1) ? rb4 + delta : rb4 - delta);
+        if (sym >= 4 && !(m & 1) && sd <= 0) sd = 0x7fffffff;
+        dist = longcode ? (int32_t)(base + (extra << npostfix)) : sd;
+        push = sym != 0 ? 1u : 0u;
       }
     }
     // ---- look ahead for the symbol phase A decodes next: the bit position of every lane is final for this round.
@@ -1292,7 +1285,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
   if (ran) LN_SAVE();
 #undef LN_PEEK
-#undef LN_CP16_KEEP
+#undef LN_CP16_IF_KEEP
 #undef LN_CP16_IF_STREAM
 #undef LN_SKIP
 #undef LN_SAVE
