@@ -119,7 +119,7 @@ BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 #ifndef BD_LANE_L2_HINTS
 #define BD_LANE_L2_HINTS 1
 #endif
-#if BD_LANE_L2_HINTS
+#if BD_LANE_L2_HINTS == 1
 BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }  // streaming: evict first
 #else
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
@@ -129,7 +129,7 @@ BD_DEV void sts32_if(bool cond, hw::sref_t a, uint32_t v) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "r"(a), "r"(v) : "memory");
 }
 BD_DEV void st32_if(bool cond, uint8_t* p, uint32_t v) {
-#if BD_LANE_L2_HINTS
+#if BD_LANE_L2_HINTS == 1
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
 #else
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
@@ -911,9 +911,15 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   BD_PIN64(pol_stream); BD_PIN64(pol_keep);
 #define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_keep)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
+#if BD_LANE_L2_HINTS == 2
+#define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
+#else
+#define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
+#endif
 #else
 #define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
+#define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #endif
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
 // Bits consumed; on a word boundary the window takes word k + 2 from the ring.  When that word starts a new
@@ -973,8 +979,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool iss_ = (ISS);                                               \
     const uint32_t nn_ = crem < 16 ? crem : 16u;                           \
     const uint32_t off_ = (uint32_t)(uintptr_t)csrc & 15u;                 \
-    LN_CP16_IF_STREAM(iss_, stage, csrc - off_);                           \
-    LN_CP16_IF_STREAM(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
+    LN_CP16_IF_SRC(iss_, stage, csrc - off_);                              \
+    LN_CP16_IF_SRC(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
     if (iss_) { pend_n = nn_; pend_off = off_; crem -= nn_; csrc += 16; }  \
   } while (0)
 // append the chunk in flight to the output
@@ -1287,6 +1293,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #undef LN_PEEK
 #undef LN_CP16_IF_KEEP
 #undef LN_CP16_IF_STREAM
+#undef LN_CP16_IF_SRC
 #undef LN_SKIP
 #undef LN_SAVE
 #undef LN_TREES
