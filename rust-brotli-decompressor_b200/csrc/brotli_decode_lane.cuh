@@ -53,7 +53,7 @@ namespace lane {
 // literal block type instead
 constexpr uint32_t kSlotHeaderBytes = 16;
 constexpr uint32_t kCtxMapEntries = 32;      // table entries the 64-byte context map takes from the top of the slot when needed
-constexpr uint32_t kGlobalTab = 8192;       // u16 entries of virtual table space behind the shared slot
+constexpr uint32_t kGlobalTab = 16384;      // u16 entries of virtual table space behind the shared slot (12-bit pointers x 4)
 constexpr uint32_t kMaxBlockTypes = 64;     // per category handled here (more: bail)
 constexpr uint32_t kBlockRootBits = 6;
 #ifndef BD_LANE_EXTRA_LITERALS
@@ -273,13 +273,13 @@ BD_DEV void tab_store(const LaneCtx& c, uint32_t v, uint32_t e) {
 
 // One symbol of the tree whose root (2^rbits entries) starts at virtual index root_v.
 // Entry = symbol << 4 | code length; length > rbits marks a pointer: its second-level table starts at
-// virtual index E + 2 * value and is indexed by the next (length - rbits) bits.
+// virtual index E + 4 * value and is indexed by the next (length - rbits) bits.
 BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t rbits) {
   const uint32_t bits = L.peek();
   uint32_t e = tab_load(c, root_v + (bits & mask_bits(rbits)));
   uint32_t len = e & 15u;
   if (len > rbits) {
-    e = c.gtab[((e >> 4) << 1) + ((bits >> rbits) & mask_bits(len - rbits))];
+    e = c.gtab[((e >> 4) << 2) + ((bits >> rbits) & mask_bits(len - rbits))];
     len = e & 15u;
   }
   L.skip(len);
@@ -386,10 +386,11 @@ BD_DEV int fill_table(const LaneCtx& c, Lane& L, const uint16_t* sorted, const u
             ll++; left <<= 1;
           }
           sub_w = ll - rbits;
-          sub_v = L.cold_next - c.E;  // index into the arena part; every allocation there is even-sized
-          if (sub_v + (1u << sub_w) > kGlobalTab) return kLaneBail;
-          L.cold_next += 1u << sub_w;
-          tab_store(c, root_v + (rev & mask_bits(rbits)), ((sub_v >> 1) << 4) | (rbits + sub_w));
+          sub_v = L.cold_next - c.E;  // index into the arena part
+          const uint32_t sub_size = sub_w < 2 ? 4u : 1u << sub_w;  // every arena allocation is a multiple of four entries
+          if (sub_v + sub_size > kGlobalTab) return kLaneBail;
+          L.cold_next += sub_size;
+          tab_store(c, root_v + (rev & mask_bits(rbits)), ((sub_v >> 2) << 4) | (rbits + sub_w));
         }
         for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) c.gtab[sub_v + t] = (uint16_t)e;
       }
@@ -969,7 +970,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     ld16_if(v_ >= E, gtab + (v_ - E), e_);  /* root outside the shared slot */                    \
     const bool need2_ = (e_ & 15u) > (TR);                                                       \
     const uint32_t sub_ = need2_ ? (e_ & 15u) - (TR) : 0u;                                       \
-    ld16_if(need2_, gtab + ((e_ >> 4) << 1) + ((BITS >> (TR)) & mask_bits(sub_)), e_);           \
+    ld16_if(need2_, gtab + ((e_ >> 4) << 2) + ((BITS >> (TR)) & mask_bits(sub_)), e_);           \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
 // request the next copy chunk: min(crem, 16) bytes from csrc on; only 16-byte blocks that hold source bytes
@@ -1022,7 +1023,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const uint32_t e_ = vlds16(stab + ((in_ ? v_ : 0u) << 1));                                   \
     const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
     const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
-    const uint32_t i2_ = ((e_ >> 4) << 1) + ((bits_ >> (TR)) & mask_bits(sub_));                 \
+    const uint32_t i2_ = ((e_ >> 4) << 2) + ((bits_ >> (TR)) & mask_bits(sub_));                 \
     LN_CP16_IF_KEEP(two_, stage + (SLOT), gtab + (i2_ & ~7u));                                   \
     PV = in_; PE = two_ ? 0x80000000u : e_; PSEL = two_ ? (i2_ & 7u) << 1 : PSEL;                \
   } while (0)

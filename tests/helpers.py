@@ -85,7 +85,7 @@ class HostSim:
 
     LANE_BAIL = 1000
 
-    def lane_decode(self, data, capacity, table_entries=430, misalign=0):
+    def lane_decode(self, data, capacity, table_entries=178, misalign=0):
         """Lane-per-stream (optimistic) path -> (code, bytes, input bytes used); code 1 = decoded, LANE_BAIL = the
         path gave the stream up (the exact kernel decodes it on the device; bytes are then meaningless).
         table_entries = u16 entries of the lane's shared-memory slot; misalign = output address modulo 4."""

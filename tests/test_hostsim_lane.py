@@ -21,7 +21,7 @@ MUST_DECODE = ["alice29.txt.compressed", "asyoulik.txt.compressed", "lcet10.txt.
 def test_fixture(hostsim, name):
     e = MAN[name]
     data = helpers.golden_fixture(name)
-    for entries in (866, 430, 202, 100000):
+    for entries in (430, 178, 146, 100000):
         for mis in (0, 1, 2, 3):
             code, out, used = hostsim.lane_decode(data, e["original_size"], entries, mis)
             if code == 1:
@@ -29,7 +29,7 @@ def test_fixture(hostsim, name):
                 assert used <= len(data)
             else:
                 assert code == hostsim.LANE_BAIL
-                assert not (name in MUST_DECODE and entries >= 430), name
+                assert not (name in MUST_DECODE and entries >= 146), name
 
 
 def test_generated_configs_and_capacity(hostsim, oracle, corpus):
@@ -39,7 +39,7 @@ def test_generated_configs_and_capacity(hostsim, oracle, corpus):
         comp, orig, _ = corpus.make_config(cfg, n, size=size)
         ok = 0
         for c, o in zip(comp, orig):
-            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([866, 430])), int(rng.integers(0, 4)))
+            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([178, 146])), int(rng.integers(0, 4)))
             if code == 1:
                 assert out == o and used == len(c)
                 ok += 1
