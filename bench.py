@@ -214,6 +214,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Everything libraries print to stdout (NCCL's version banner, ...) goes to stderr: stdout carries the one JSON line.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -372,7 +376,8 @@ def main():
             "e2e": e2e,
         }
         line["cpu_baseline"] = cpu_baseline(args, corpus, comp[:min(n_unique, 2048)], orig[:min(n_unique, 2048)]) if world == 1 and not args.no_cpu else None
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
