@@ -290,10 +290,14 @@ BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint3
 // Every word that leaves for global memory is mirrored into a 32-byte per-lane history ring in shared memory
 // (hist + (position & 31)): short-distance copies read their source from there instead of waiting for a
 // just-stored byte to come back from L2.
+// first word of an unaligned region: bytes below the region are not ours (out of line: once per stream at most)
+BD_COLD void store_head_bytes(uint8_t* out_al, uint32_t bias, uint32_t wpos, uint32_t word) {
+  for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
+}
 BD_DEV void store_word_if(bool cond, uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
   sts32_if(cond, hist + (wpos & 28u), word);
-  if (BD_UNLIKELY(cond && wpos < bias)) {  // first word of an unaligned region: bytes below the region are not ours
-    for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
+  if (BD_UNLIKELY(cond && wpos < bias)) {
+    store_head_bytes(out_al, bias, wpos, word);
   } else {
     st32_if(cond, out_al + wpos, word);
   }
