@@ -60,6 +60,10 @@ constexpr uint32_t kBlockRootBits = 6;
 #define BD_LANE_EXTRA_LITERALS 1
 #endif
 constexpr uint32_t kMaxExtraLiterals = BD_LANE_EXTRA_LITERALS;  // literals a lane may add to its phase-A literal per round
+#ifndef BD_LANE_CMD_LITERALS
+#define BD_LANE_CMD_LITERALS 2
+#endif
+constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may decode in the round of their command
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
   static constexpr size_t kCtxLit = kTab + 2 * (size_t)kGlobalTab;    // u8[64 * kMaxBlockTypes]
@@ -910,6 +914,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   // round counter and the round in which this lane last requested an input block (see LN_SKIP)
   uint32_t rnd = 0, blk_round = 0xFFFFFFFFu;
   bool dhave = false;
+  uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
 
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
@@ -1115,13 +1120,36 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           } else {
             LN_SKIP(len);
             if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
-            copy_len += LN_PEEK() & mask_bits(ce);
+            bits = LN_PEEK();  // (the literals below continue from this peek)
+            copy_len += bits & mask_bits(ce);
             nskip = ce;
           }
           bl_c--;
           mlen -= (int32_t)ins;
-          ph = ins != 0 ? kPhLit : kPhDist;
           ctx_fresh = false;
+          ph = kPhDist;
+          if (ins != 0) {
+            // The command's first literals are decoded in the command's own round, while they come out of the same
+            // 32-bit peek: one tree for all contexts, root in the shared slot, codes no longer than the root (a short
+            // insert -- 98 % are <= 4 -- then costs no round of its own).  They are appended in phase P, behind the
+            // previous command's copy chunk, which is still in flight.  The bounds phase P checks for a literal run
+            // are checked here first.
+            if (kCmdLiterals != 0 && trivial && mlen >= 0 && ins + pend_n <= capb - posb) {
+              for (uint32_t rep = 0; rep < kCmdLiterals; rep++) {
+                if (ins == 0 || bl_l == 0 || nskip + r_lit > 32) break;
+                const uint32_t v2 = lit_tv + ((bits >> nskip) & mask_bits(r_lit));
+                const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
+                if (v2 >= E || (e2 & 15u) > r_lit) break;
+                bl_l--;
+                lit_pack |= (e2 >> 4) << (8 * lit_n);
+                lit_n++;
+                --ins;
+                nskip += e2 & 15u;
+              }
+            }
+            if (ins != 0) ph = kPhLit;
+            else if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+          }
         }
         LN_SKIP(nskip);
         // look ahead for the distance symbol this lane decodes in phase C of this round
@@ -1137,6 +1165,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     // ---- phase P: retire the copy chunk requested at the end of the previous round ----
     cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
     if (run && pend_n != 0) LN_RETIRE_CHUNK();
+    if (kCmdLiterals != 0 && run) {  // literals decoded in their command's round (phase A); nothing happens for lit_n == 0
+      append(out_al, bias, hist, posb, acc, lit_pack, lit_n);
+      lit_pack = 0; lit_n = 0;
+    }
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
     warp_sync();
