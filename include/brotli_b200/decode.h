@@ -193,6 +193,20 @@ BROTLI_B200_API int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in
                                               uint8_t* const* out, size_t* out_size, BrotliDecoderResult* results,
                                               BrotliDecoderErrorCode* codes);
 
+/* Custom LZ77 dictionary: `dictionary` logically precedes the output of every stream of the call, as in the
+ * reference's BrotliState::new_with_custom_dictionary (src/state.rs:400-411; reached through
+ * BrotliDecompressCustomDict, src/lib.rs:105-131, Decompressor::new_with_custom_dict, src/reader.rs:105, and the
+ * CLI's -dict, src/bin/brotli-decompressor.rs:239-257 -- the reference's C FFI has no entry for it).  Only the last
+ * (1 << WBITS) - 16 bytes of the dictionary are reachable (src/decode.rs:1831-1838).  Result fields as for
+ * BrotliDecoderDecompressWithReturnInfo. */
+BROTLI_B200_API BrotliDecoderReturnInfo BrotliB200DecompressWithDictionary(size_t encoded_size, const uint8_t* encoded_buffer,
+                                                                           size_t decoded_size, uint8_t* decoded_buffer,
+                                                                           const uint8_t* dictionary, size_t dictionary_size);
+/* BrotliB200DecompressBatchPacked with one custom dictionary (host memory) shared by all streams of the batch. */
+BROTLI_B200_API int BrotliB200DecompressBatchPackedWithDictionary(size_t n, const uint8_t* in_bytes, const uint64_t* in_off,
+                                                                  uint8_t* out_bytes, const uint64_t* out_off, uint64_t* out_len,
+                                                                  int32_t* codes, const uint8_t* dictionary, size_t dictionary_size);
+
 /* Per-stream 64-bit checksums of device-resident output regions: sums[i] =
  * (sum over j < len[i] of mix((b_j + 1) * (0x9E3779B97F4A7C15 + 2j)) * 0xBF58476D1CE4E5B9) ^ (len[i] * 0x94D049BB133111EB),
  * mix(x) = x ^ (x >> 29), all mod 2^64.  Used to verify bit-exactness of full-size batches without

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "BrotliDecoderGetErrorString", "BrotliDecoderErrorString", "BrotliDecoderVersion", "BrotliDecoderMallocU8",
     "BrotliDecoderFreeU8", "BrotliDecoderMallocUsize", "BrotliDecoderFreeUsize", "BrotliB200DecompressBatchDevice",
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
+    "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary",
     "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
     "BrotliB200Shutdown",
 ]
@@ -92,6 +93,10 @@ def lib():
     L.BrotliB200DecompressBatchPacked.argtypes = [sz, vp, vp, vp, vp, vp, vp]
     L.BrotliB200DecompressBatch.restype = ctypes.c_int
     L.BrotliB200DecompressBatch.argtypes = [sz, vp, vp, vp, vp, vp, vp]
+    L.BrotliB200DecompressWithDictionary.restype = BrotliDecoderReturnInfo
+    L.BrotliB200DecompressWithDictionary.argtypes = [sz, vp, sz, vp, vp, sz]
+    L.BrotliB200DecompressBatchPackedWithDictionary.restype = ctypes.c_int
+    L.BrotliB200DecompressBatchPackedWithDictionary.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
     L.BrotliB200ChecksumBatchDevice.restype = ctypes.c_int
     L.BrotliB200ChecksumBatchDevice.argtypes = [sz, vp, vp, vp, vp, vp]
     L.BrotliB200KernelLaunchCount.restype = ctypes.c_uint64
@@ -140,6 +145,16 @@ def brotli_decode(data, capacity):
     data = bytes(data)
     buf = ctypes.create_string_buffer(max(int(capacity), 1))
     info = lib().BrotliDecoderDecompressWithReturnInfo(len(data), data, int(capacity), buf)
+    return info, buf.raw[:info.decoded_size]
+
+
+def brotli_decode_custom_dict(data, capacity, custom_dictionary):
+    """One stream decoded with a custom LZ77 dictionary, the one-shot form of ``BrotliDecompressCustomDict``
+    (src/lib.rs:105-131; ``BrotliState::new_with_custom_dictionary``, src/state.rs:400-411).  Returns
+    ``(info, output_bytes)`` like :func:`brotli_decode`."""
+    data, cd = bytes(data), bytes(custom_dictionary)
+    buf = ctypes.create_string_buffer(max(int(capacity), 1))
+    info = lib().BrotliB200DecompressWithDictionary(len(data), data, int(capacity), buf, cd, len(cd))
     return info, buf.raw[:info.decoded_size]
 
 
@@ -266,6 +281,15 @@ def decompress_batch_packed(in_bytes, in_off, out_bytes, out_off, out_len, codes
     n = len(out_len)
     _check(lib().BrotliB200DecompressBatchPacked(n, _ptr(in_bytes), _ptr(in_off), _ptr(out_bytes), _ptr(out_off), _ptr(out_len),
                                                  _ptr(codes)), "BrotliB200DecompressBatchPacked")
+
+
+def decompress_batch_packed_custom_dict(in_bytes, in_off, out_bytes, out_off, out_len, codes, custom_dictionary):
+    """:func:`decompress_batch_packed` with one custom LZ77 dictionary shared by every stream of the batch."""
+    n = len(out_len)
+    cd = bytes(custom_dictionary)
+    _check(lib().BrotliB200DecompressBatchPackedWithDictionary(n, _ptr(in_bytes), _ptr(in_off), _ptr(out_bytes), _ptr(out_off),
+                                                               _ptr(out_len), _ptr(codes), cd, len(cd)),
+           "BrotliB200DecompressBatchPackedWithDictionary")
 
 
 def decompress_batch_device(n, d_in, d_in_off, d_out, d_out_off, d_out_len, d_codes, stream=None):

@@ -55,6 +55,50 @@ def compress(data, quality=5, lgwin=22):
     return buf.raw[:size.value]
 
 
+def compress_with_dictionary(data, dictionary, quality=5, lgwin=22):
+    """libbrotlienc streaming encoder with a raw LZ77 dictionary attached (BrotliEncoderPrepareDictionary +
+    BrotliEncoderAttachPreparedDictionary, libbrotli >= 1.1).  While dictionary + data fit the window, the
+    stream is what the reference decodes with BrotliState::new_with_custom_dictionary: distances past the start
+    of the output reach back into the dictionary, and static-dictionary references come after it."""
+    enc = _encoder()
+    data, dictionary = bytes(data), bytes(dictionary)
+    if len(data) + len(dictionary) + 16 > (1 << lgwin):
+        raise ValueError("dictionary + data must fit the window for custom-dictionary semantics")
+    enc.BrotliEncoderCreateInstance.restype = ctypes.c_void_p
+    enc.BrotliEncoderCreateInstance.argtypes = [ctypes.c_void_p] * 3
+    enc.BrotliEncoderSetParameter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
+    enc.BrotliEncoderPrepareDictionary.restype = ctypes.c_void_p
+    enc.BrotliEncoderPrepareDictionary.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+    enc.BrotliEncoderAttachPreparedDictionary.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    enc.BrotliEncoderDestroyPreparedDictionary.argtypes = [ctypes.c_void_p]
+    enc.BrotliEncoderDestroyInstance.argtypes = [ctypes.c_void_p]
+    enc.BrotliEncoderCompressStream.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p),
+                                                ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+    st = enc.BrotliEncoderCreateInstance(None, None, None)
+    prepared = enc.BrotliEncoderPrepareDictionary(0, len(dictionary), dictionary, int(quality), None, None, None)  # 0: BROTLI_SHARED_DICTIONARY_RAW
+    try:
+        if not st or not prepared:
+            raise RuntimeError("libbrotlienc: cannot create the encoder / prepare the dictionary")
+        enc.BrotliEncoderSetParameter(st, 1, int(quality))  # BROTLI_PARAM_QUALITY
+        enc.BrotliEncoderSetParameter(st, 2, int(lgwin))    # BROTLI_PARAM_LGWIN
+        if not enc.BrotliEncoderAttachPreparedDictionary(st, prepared):
+            raise RuntimeError("BrotliEncoderAttachPreparedDictionary failed")
+        cap = enc.BrotliEncoderMaxCompressedSize(len(data)) or (len(data) + 1024)
+        out = ctypes.create_string_buffer(cap + 64)
+        src = ctypes.create_string_buffer(data, len(data) or 1)
+        avail_in, next_in = ctypes.c_size_t(len(data)), ctypes.c_void_p(ctypes.addressof(src))
+        avail_out, next_out = ctypes.c_size_t(cap + 64), ctypes.c_void_p(ctypes.addressof(out))
+        if not enc.BrotliEncoderCompressStream(st, 2, ctypes.byref(avail_in), ctypes.byref(next_in), ctypes.byref(avail_out),
+                                               ctypes.byref(next_out), None) or avail_in.value != 0:  # 2: BROTLI_OPERATION_FINISH
+            raise RuntimeError("BrotliEncoderCompressStream failed")
+        return out.raw[:cap + 64 - avail_out.value]
+    finally:
+        if prepared:
+            enc.BrotliEncoderDestroyPreparedDictionary(prepared)
+        if st:
+            enc.BrotliEncoderDestroyInstance(st)
+
+
 def system_decompress(data, capacity):
     """Google C decoder (libbrotlidec 1.1.0) one-shot; returns (ok, bytes)."""
     data = bytes(data)

@@ -116,6 +116,7 @@ struct DeviceCtx {
   cudaEvent_t ev_arena = nullptr;  // completion of the most recent decode launch
   bool arena_busy = false;
   DevBuf in, out, in_off, out_off, out_len, codes, in_used;
+  DevBuf cdict;            // custom LZ77 dictionary of the batch in flight
   void* pinned = nullptr;  // small pinned staging area for one-shot calls
   size_t pinned_cap = 0;
 };
@@ -192,7 +193,7 @@ DeviceCtx* acquire_ctx() {
 // ---- device-resident batch -------------------------------------------------------------------
 int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                   const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_codes, uint64_t* d_in_used, uint32_t large_window,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const uint8_t* d_dict = nullptr, uint64_t dict_size = 0) {
   if (n == 0) return 0;
   if (n > 0xFFFFFFF0ull) { set_error("brotli_b200: batch too large"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
   BatchArgs a;
@@ -200,12 +201,15 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   a.in_used = d_in_used;
   a.order = nullptr; a.ticket = c->ticket; a.arena = c->arena; a.dictionary = c->dictionary;
   a.n = (uint32_t)n; a.large_window = large_window; a.n_ptr = nullptr;
+  a.custom_dict = dict_size ? d_dict : nullptr; a.custom_dict_size = d_dict ? dict_size : 0;
   std::lock_guard<std::mutex> lock(c->launch_mu);
   if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
   const uint32_t slot = c->timed_count % DeviceCtx::kTimedLaunches;
   for (int e = 0; e < 3; e++) if (!c->ev_t[slot][e]) CU_TRY(cudaEventCreate(&c->ev_t[slot][e]));
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
-  if (c->lane_ctas > 0) {
+  // (streams with a custom dictionary go straight to the exact kernel: the lane kernel keeps every distance inside
+  // the output region)
+  if (c->lane_ctas > 0 && a.custom_dict_size == 0) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
     brotli_b200::LaneArgs la;
@@ -243,9 +247,14 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
 // k+1 and the D2H of chunk k-1 overlap the decode of chunk k.  Decode kernels stay on one stream
 // because they share the per-warp scratch arena.
 int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const uint64_t* in_off, uint8_t* out_bytes,
-                       const uint64_t* out_off, uint64_t* out_len, int32_t* codes, uint64_t* in_used, uint32_t large_window) {
+                       const uint64_t* out_off, uint64_t* out_len, int32_t* codes, uint64_t* in_used, uint32_t large_window,
+                       const uint8_t* dict = nullptr, size_t dict_size = 0) {
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lock(c->mu);
+  if (dict_size) {
+    CU_TRY(c->cdict.reserve(dict_size));
+    CU_TRY(cudaMemcpyAsync(c->cdict.p, dict, dict_size, cudaMemcpyHostToDevice, c->s_h2d));  // ordered before the first chunk's h2d event
+  }
   const uint64_t in_base = in_off[0], out_base = out_off[0];
   const uint64_t in_total = in_off[n] - in_base, out_total = out_off[n] - out_base;
   for (size_t i = 0; i < n; i++)
@@ -292,7 +301,7 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     if (e != cudaSuccess) { set_error(std::string("brotli_b200: H2D stage failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; break; }
     rc = decode_device(c, k.e - k.b, d_in, (const uint64_t*)c->in_off.p + k.b, d_out, (const uint64_t*)c->out_off.p + k.b,
                        (uint64_t*)c->out_len.p + k.b, (int32_t*)c->codes.p + k.b, in_used ? (uint64_t*)c->in_used.p + k.b : nullptr,
-                       large_window, c->s_compute);
+                       large_window, c->s_compute, dict_size ? (const uint8_t*)c->cdict.p : nullptr, dict_size);
     if (rc != 0) break;
     if (ci + 1 == chunks.size()) cudaEventRecord(c->ev_k1, c->s_compute);
     e = cudaEventRecord(k.done, c->s_compute);
@@ -343,7 +352,7 @@ BrotliDecoderReturnInfo invalid_arguments_info() {  // src/ffi/mod.rs:83-106
 
 // brotli_decode (src/lib.rs:446-468) on the GPU: a batch of one.
 BrotliDecoderReturnInfo one_shot(const uint8_t* in, size_t in_size, uint8_t* out, size_t out_cap, uint32_t large_window,
-                                 uint64_t* in_used) {
+                                 uint64_t* in_used, const uint8_t* dict = nullptr, size_t dict_size = 0) {
   DeviceCtx* c = acquire_ctx();
   if (!c) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
   if (in_size >= ((uint64_t)1 << 32)) return invalid_arguments_info();  // src/decode.rs:2799-2812
@@ -351,7 +360,7 @@ BrotliDecoderReturnInfo one_shot(const uint8_t* in, size_t in_size, uint8_t* out
   int32_t code = 0;
   static const uint8_t kNothing[1] = {0};
   uint8_t dummy_out[1];
-  int rc = decode_host_packed(c, 1, in ? in : kNothing, in_off, out ? out : dummy_out, out_off, &out_len, &code, &used, large_window);
+  int rc = decode_host_packed(c, 1, in ? in : kNothing, in_off, out ? out : dummy_out, out_off, &out_len, &code, &used, large_window, dict, dict_size);
   if (rc != 0) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
   if (in_used) *in_used = used;
   int result = code == 1 ? 1 : (code == 2 ? 2 : (code == 3 ? 3 : 0));  // BrotliResult
@@ -602,6 +611,35 @@ int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in, const size_t* 
       if (codes) codes[i] = (BrotliDecoderErrorCode)cds[i];
     }
     return 0;
+  } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
+}
+
+// ---- custom LZ77 dictionary (BrotliState::new_with_custom_dictionary, src/state.rs:400-411; src/lib.rs:105-131) ----
+BrotliDecoderReturnInfo BrotliB200DecompressWithDictionary(size_t encoded_size, const uint8_t* encoded_buffer, size_t decoded_size,
+                                                           uint8_t* decoded_buffer, const uint8_t* dictionary, size_t dictionary_size) {
+  try {
+    if (!valid_slice(encoded_buffer, encoded_size, 1) || !valid_slice(decoded_buffer, decoded_size, 1) ||
+        !valid_slice(dictionary, dictionary_size, 1))
+      return invalid_arguments_info();
+    return one_shot(encoded_buffer, encoded_size, decoded_buffer, decoded_size, 1u, nullptr, dictionary, dictionary_size);
+  } catch (const std::exception& e) {
+    return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, e.what());
+  } catch (...) {
+    return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, "brotli_b200: unknown exception");
+  }
+}
+
+int BrotliB200DecompressBatchPackedWithDictionary(size_t n, const uint8_t* in_bytes, const uint64_t* in_off, uint8_t* out_bytes,
+                                                  const uint64_t* out_off, uint64_t* out_len, int32_t* codes, const uint8_t* dictionary,
+                                                  size_t dictionary_size) {
+  try {
+    if (n == 0) return 0;
+    if (!in_off || !out_off || !out_len || !codes || !in_bytes || !out_bytes || (dictionary_size && !dictionary)) {
+      set_error("brotli_b200: null batch array"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS;
+    }
+    DeviceCtx* c = acquire_ctx();
+    if (!c) return BROTLI_DECODER_ERROR_UNREACHABLE;
+    return decode_host_packed(c, n, in_bytes, in_off, out_bytes, out_off, out_len, codes, nullptr, 1u, dictionary, dictionary_size);
   } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
 }
 

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
     const uint64_t in0 = a.in_off[i], in1 = a.in_off[i + 1];
     const uint64_t out0 = a.out_off[i], out1 = a.out_off[i + 1];
     uint64_t decoded = 0, used = 0;
-    const int code = decode_stream(d, a.in + in0, in1 - in0, a.out + out0, out1 - out0, a.large_window, &decoded, &used);
+    const int code = decode_stream(d, a.in + in0, in1 - in0, a.out + out0, out1 - out0, a.large_window, &decoded, &used, a.custom_dict,
+                                   a.custom_dict_size);
     if (lane == 0) {
       a.out_len[i] = decoded;
       a.codes[i] = code;

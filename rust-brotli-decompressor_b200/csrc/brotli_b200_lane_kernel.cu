@@ -15,10 +15,10 @@ namespace brotli_b200 {
 // all lanes.  Dynamic shared memory: one private slot per lane (slot header + root tables).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(BatchArgs a, LaneArgs la) {
-  __shared__ uint2 s_cmd_lut[704];
-  __shared__ __align__(16) uint8_t s_ctx_lut[2048];
-  __shared__ uint32_t s_word_info[25];
-  __shared__ uint32_t s_transform_info[BROTLI_NUM_TRANSFORMS];
+  uint2* const s_cmd_lut = lane::g_cmd_lut;
+  uint8_t* const s_ctx_lut = lane::g_ctx_lut;
+  uint32_t* const s_word_info = lane::g_word_info;
+  uint32_t* const s_transform_info = lane::g_transform_info;
   extern __shared__ __align__(16) uint8_t s_dyn[];
   for (uint32_t i = threadIdx.x; i < 704; i += blockDim.x) s_cmd_lut[i] = pack_cmd_lut(i);
   for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_ctx_lut[i] = tbl::kBrotliContextLookup[i];
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
     }
     uint64_t decoded = 0, used = 0;
     // the whole warp decodes together: one stream per lane, one prefix-code symbol per lane and iteration
-    const uint32_t r = lane::decode_streams(c, active, a.in + in0, in1 - in0, a.out + out0, out1 - out0, &decoded, &used);
+    const uint32_t r = lane::decode_streams<WARPS * 32 * 16>(c, active, a.in + in0, in1 - in0, a.out + out0, out1 - out0, &decoded, &used);
     if (active) {
       if (r == lane::kStDone) {
         a.out_len[i] = decoded;

@@ -46,6 +46,8 @@ struct BatchArgs {
   uint32_t n;
   uint32_t large_window;    // accept the large-window header (one-shot: 1, src/state.rs:394)
   const uint32_t* n_ptr;    // optional: the stream count lives in device memory (fallback pass over a bail list)
+  const uint8_t* custom_dict;  // optional custom LZ77 dictionary shared by the batch (device memory), src/state.rs:400-411
+  uint64_t custom_dict_size;
 };
 
 // Extra arguments of the lane kernel.

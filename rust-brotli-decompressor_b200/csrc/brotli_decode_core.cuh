@@ -292,6 +292,13 @@ struct Decoder {
   uint32_t wbits;
   uint32_t max_backward;  // (1 << wbits) - 16
   uint32_t large_window;  // stream carries the large-window marker (src/decode.rs:152-187)
+  // custom LZ77 dictionary (BrotliState::new_with_custom_dictionary, src/state.rs:400-411): bytes that logically
+  // precede the output.  cdict points at the part the window can reach (its last cdict_size bytes,
+  // src/decode.rs:1831-1838); cdict_limit = max_backward - the UNCLIPPED length (src/decode.rs:2954-2955).
+  const uint8_t* cdict;
+  uint32_t cdict_size;
+  int64_t cdict_limit;
+  uint32_t cdict_given;
   // ring-buffer flush emulation (src/decode.rs:1693-1738,1808-1871)
   uint32_t rb_allocated;
   uint64_t rbsize;
@@ -835,6 +842,7 @@ BD_COLD int process_commands(Decoder& d) {
       if (i != 0) {  // context-dependent literals, src/decode.rs:2463-2551
         hw::syncwarp();
         uint32_t p1 = d.pos >= 1 ? d.out[d.pos - 1] : 0, p2 = d.pos >= 2 ? d.out[d.pos - 2] : 0;
+        if (d.cdict_given && d.pos < 2) { p1 = 0; p2 = 0; }  // custom_dict_avoid_context_seed, src/decode.rs:2466-2476
         const uint8_t* map = d.map_lit;
         const uint16_t* const* lit_ptrs = d.lit_ptrs;
         do {
@@ -888,7 +896,8 @@ BD_COLD int process_commands(Decoder& d) {
       dist = read_distance<FAST>(d, push);
       if (SAFE && br.overrun()) return kNeedsMoreInput;
     }
-    const uint32_t max_distance = d.pos < d.max_backward ? d.pos : d.max_backward;  // src/decode.rs:2583-2589
+    // src/decode.rs:2583-2589 (and :1799-1801, :3314-3316: the full-size ring has wrapped by the time pos passes max_backward)
+    const uint32_t max_distance = (int64_t)d.pos < d.cdict_limit ? d.pos + d.cdict_size : d.max_backward;
     const uint32_t copy_len = d.copy_len;
     if (dist > (int32_t)max_distance) {  // static dictionary, src/decode.rs:2593-2640
       if (dist > 0x7FFFFFFC) return kErrDistance;
@@ -924,7 +933,7 @@ BD_COLD int process_commands(Decoder& d) {
       if (dist <= 0) return kErrUnreachable;  // cannot happen for symbols < max_symbol; keeps the copy in bounds
       if (push) { d.d3 = d.d2; d.d2 = d.d1; d.d1 = d.d0; d.d0 = dist; }
       d.mlen -= (int32_t)copy_len;
-      if (FAST) {
+      if (FAST && (uint32_t)dist <= d.pos) {
         warp_copy(d.out, d.pos, (uint32_t)dist, copy_len);
         d.pos += copy_len;
       } else {
@@ -937,6 +946,12 @@ BD_COLD int process_commands(Decoder& d) {
           uint64_t seg = left;
           if (seg > d.cap - d.pos) seg = d.cap - d.pos;
           if (seg > d.next_flush - d.pos) seg = d.next_flush - d.pos;
+          if ((uint32_t)dist > d.pos) {  // the source starts in the custom dictionary, which precedes the output
+            const uint32_t back = (uint32_t)dist - d.pos;  // <= cdict_size by the max_distance test above
+            if (seg > back) seg = back;
+            hw::syncwarp();
+            for (uint32_t i = lane; i < (uint32_t)seg; i += hw::kWarp) d.out[d.pos + i] = hw::ldg8(d.cdict + (d.cdict_size - back) + i);
+          } else
           warp_copy(d.out, d.pos, (uint32_t)dist, (uint32_t)seg);
           d.pos += (uint32_t)seg; left -= (uint32_t)seg;
           if (d.pos == d.next_flush) { int r = flush_event(d); if (r != kSuccess) return r; }
@@ -1483,7 +1498,7 @@ BD_DEV void allocate_ring_emulation(Decoder& d, uint32_t is_last, uint32_t is_un
   }
   uint64_t size = (uint64_t)1 << d.wbits;
   if (is_last)
-    while (size >= ((uint64_t)d.mlen + 16) * 2 && size > 32) size >>= 1;
+    while (size >= ((uint64_t)d.cdict_size + (uint64_t)d.mlen + 16) * 2 && size > 32) size >>= 1;  // src/decode.rs:1843-1847
   d.rbsize = size;
   d.full_ring = size == ((uint64_t)1 << d.wbits);
   d.next_flush = size;
@@ -1530,7 +1545,7 @@ BD_COLD int copy_uncompressed(Decoder& d) {
 // success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity, fatal -> only
 // what the ring buffer had flushed (multiples of its size).
 BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint32_t allow_large_window,
-                         uint64_t* decoded_size, uint64_t* in_used) {
+                         uint64_t* decoded_size, uint64_t* in_used, const uint8_t* custom_dict = nullptr, uint64_t custom_dict_size = 0) {
   BitReader& br = d.br;
   br.init(in, in_size);
   d.out = out;
@@ -1563,6 +1578,11 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
       }
     }
     d.max_backward = (1u << d.wbits) - 16;
+    // custom dictionary: the window reaches its last max_backward bytes (src/decode.rs:1831-1838)
+    d.cdict_given = custom_dict_size != 0;
+    d.cdict_size = custom_dict_size > d.max_backward ? d.max_backward : (uint32_t)custom_dict_size;
+    d.cdict = custom_dict + (custom_dict_size - d.cdict_size);
+    d.cdict_limit = (int64_t)d.max_backward - (int64_t)custom_dict_size;
     for (;;) {  // metablocks
       // DecodeMetaBlockLength, src/decode.rs:243-372
       const uint32_t is_last = br.read<false>(1);
@@ -1621,7 +1641,9 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
           if (result == kSuccess && br.overrun()) result = kNeedsMoreInput;
           if (result != kSuccess) break;
           for (;;) {  // ProcessCommands / SafeProcessCommands, src/decode.rs:3289-3298
-            result = d.all_shared ? process_commands_shared(d) : process_commands_fast(d);
+            // (streams with a custom dictionary take the checked loop for every command: the register-resident
+            // loops assume that every distance stays inside the output region)
+            result = d.cdict_given ? kNeedSafe : (d.all_shared ? process_commands_shared(d) : process_commands_fast(d));
             if (result == kNeedSafe) result = process_commands<true>(d);
             if (result != kRetryFast) break;
           }

@@ -184,6 +184,15 @@ BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 l
 
 BD_DEV uint32_t mask_bits(uint32_t n) { return (1u << n) - 1u; }  // n <= 31
 
+#if !defined(BROTLI_B200_HOSTSIM)
+// LUTs read by all lanes of the CTA (filled by the kernel before its first __syncthreads()).  At namespace scope so
+// that the command loop addresses them as link-time constants instead of carrying four pointers in registers.
+__shared__ uint2 g_cmd_lut[704];                       // pack_cmd_lut
+__shared__ __align__(16) uint8_t g_ctx_lut[2048];      // kBrotliContextLookup
+__shared__ uint32_t g_word_info[25];                   // pack_word_info
+__shared__ uint32_t g_transform_info[BROTLI_NUM_TRANSFORMS];  // pack_transform_info
+#endif
+
 // Constant per-lane context (where this lane's storage lives).
 struct LaneCtx {
   hw::sref_t slot;       // shared: kSlotHeaderBytes header, then E u16 table entries
@@ -854,12 +863,15 @@ enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a
 // Restates ProcessCommandsInternal (src/decode.rs:2330-2744) for one metablock.  The WHOLE WARP calls
 // this together; lanes with run == false only take part in the votes.  On return st is kStHeader
 // (metablock complete) or kStBail for every lane that ran.
+// kStride: distance between the two 16-byte blocks of a lane's block-interleaved input ring (16 x the CTA's
+// threads), a compile-time constant of the kernel instance.
+template <uint32_t kStride>
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
   // register copies of the hot state
   const uint8_t* gin = nullptr;
   uint32_t lo = 0, hi = 0, nx = 0, k = 0, bp = 0, k_max = 0, last_blk = 0;
   hw::sref_t ring = c.ring;
-  uint32_t ring_stride = c.ring_stride;
+  constexpr uint32_t ring_stride = kStride;
   uint8_t* out_al = nullptr;
   uint32_t bias = 0, capb = 0, posb = 0, acc = 0;
   int32_t mlen = 0;
@@ -872,12 +884,16 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t E = c.E;
   hw::sref_t stab = c.stab;
   const uint16_t* gtab = c.gtab;
-  hw::sref_t slot = c.slot, cmd_lut = c.cmd_lut, word_info = c.word_info, transform_info = c.transform_info;
-  hw::sref_t ctx_lut_base = c.ctx_lut;
+  hw::sref_t slot = c.slot;
   const uint8_t* xdict = c.xdict;
   hw::sref_t hist = c.hist, stage = c.stage;
-  BD_PIN32(ring); BD_PIN32(ring_stride); BD_PIN32(E); BD_PIN32(stab); BD_PIN64(gtab); BD_PIN32(slot); BD_PIN32(cmd_lut);
-  BD_PIN32(word_info); BD_PIN32(transform_info); BD_PIN32(ctx_lut_base); BD_PIN64(xdict); BD_PIN32(hist); BD_PIN32(stage);
+#if defined(BROTLI_B200_HOSTSIM)
+  const hw::sref_t cmd_lut = c.cmd_lut, word_info = c.word_info, transform_info = c.transform_info, ctx_lut_base = c.ctx_lut;
+#else
+  const hw::sref_t cmd_lut = hw::to_sref(g_cmd_lut), word_info = hw::to_sref(g_word_info), transform_info = hw::to_sref(g_transform_info);
+  const hw::sref_t ctx_lut_base = hw::to_sref(g_ctx_lut);
+#endif
+  BD_PIN32(ring); BD_PIN32(E); BD_PIN32(stab); BD_PIN64(gtab); BD_PIN32(slot); BD_PIN64(xdict); BD_PIN32(hist); BD_PIN32(stage);
 
 #define LN_TREES()                                                          \
   do {                                                                      \
@@ -911,10 +927,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t pend_n = 0, pend_off = 0;
   const uint8_t* csrc = nullptr;  // next source byte of the copy being made
   uint32_t crem = 0;              // its remaining bytes
-  // round counter and the round in which this lane last requested an input block (see LN_SKIP)
-  uint32_t rnd = 0, blk_round = 0xFFFFFFFFu;
   bool dhave = false;
-  uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
 
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
@@ -943,10 +956,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     k += adv_ ? 1u : 0u;                                                                         \
     const uint32_t j_ = k + 2;                                                                   \
     const bool blk_ = adv_ && (j_ & 3u) == 0;                                                    \
-    if (BD_UNLIKELY(blk_ && blk_round == rnd)) { cp_async_commit(); cp_async_wait_all(); }       \
+    if (BD_UNLIKELY(blk_ && blk_seen)) { cp_async_commit(); cp_async_wait_all(); }               \
     const uint32_t b_ = (j_ >> 2) + 1;                                                           \
     LN_CP16_IF_STREAM(blk_, ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
-    blk_round = blk_ ? rnd : blk_round;                                                          \
+    blk_seen = blk_seen || blk_;                                                                 \
     const uint32_t nw_ = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);         \
     lo = adv_ ? hi : lo; hi = adv_ ? nx : hi; nx = adv_ ? nw_ : nx;                              \
     bp &= 31u;                                                                                   \
@@ -1052,7 +1065,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
-    rnd++;
+    bool blk_seen = false;       // this lane has requested an input block in this round (see LN_SKIP)
+    uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
     // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
     cp_async_wait_all_but_latest();
 #ifdef BD_LANE_ROUND_STATS
@@ -1167,7 +1181,6 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     if (run && pend_n != 0) LN_RETIRE_CHUNK();
     if (kCmdLiterals != 0 && run) {  // literals decoded in their command's round (phase A); nothing happens for lit_n == 0
       append(out_al, bias, hist, posb, acc, lit_pack, lit_n);
-      lit_pack = 0; lit_n = 0;
     }
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
@@ -1408,6 +1421,7 @@ BD_DEV uint32_t stream_finish(Lane& L, uint64_t* decoded, uint64_t* used) {
 
 // One stream per lane, the whole warp together (lanes without a stream pass active == false).
 // Returns kStDone (decoded; sizes written) or kStBail (hand the stream to the exact kernel).
+template <uint32_t kStride>
 BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap,
                                uint64_t* decoded, uint64_t* used) {
   Lane L;
@@ -1421,7 +1435,7 @@ BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in,
     }
     warp_sync();
     if (!warp_any(st == kStCommands)) break;
-    run_commands(c, L, bt, st == kStCommands, st);
+    run_commands<kStride>(c, L, bt, st == kStCommands, st);
     // METABLOCK_DONE, src/decode.rs:3345-3381: BLOCK_LENGTH_2 (:3356-3359) / truncated input
     if (st == kStHeader && (L.mlen < 0 || L.overrun())) st = kStBail;
     if (st == kStHeader && L.is_last) st = kStFinish;

@@ -78,6 +78,9 @@ class HostSim:
         L.hostsim_decode.restype = ctypes.c_int
         L.hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_decode_dict.restype = ctypes.c_int
+        L.hostsim_decode_dict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
         L.hostsim_lane_decode.restype = ctypes.c_int
         L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -88,11 +91,12 @@ class HostSim:
     def lane_decode(self, data, capacity, table_entries=178, misalign=0):
         """Lane-per-stream (optimistic) path -> (code, bytes, input bytes used); code 1 = decoded, LANE_BAIL = the
         path gave the stream up (the exact kernel decodes it on the device; bytes are then meaningless).
-        table_entries = u16 entries of the lane's shared-memory slot; misalign = output address modulo 4."""
+        table_entries = u16 entries of the lane's shared-memory slot; misalign = output address modulo 32 (the
+        path writes whole 32-byte sectors; the head and tail of an unaligned region are written byte-wise)."""
         data = bytes(data)
-        buf = ctypes.create_string_buffer(max(int(capacity), 1) + 72)
+        buf = ctypes.create_string_buffer(max(int(capacity), 1) + 136)
         addr = ctypes.addressof(buf)
-        addr += (-addr) % 8 + misalign
+        addr += (-addr) % 32 + 32 + misalign
         off = addr - ctypes.addressof(buf)
         n = ctypes.c_uint64(0)
         used = ctypes.c_uint64(0)
@@ -101,12 +105,13 @@ class HostSim:
         assert raw[:off] == bytes(off) and raw[off + int(capacity):] == bytes(len(raw) - off - int(capacity)), "wrote outside the region"
         return code, raw[off:off + n.value], used.value
 
-    def decode(self, data, capacity, large_window=True):
+    def decode(self, data, capacity, large_window=True, custom_dict=None):
         """-> (code, bytes): code is the BrotliDecoderErrorCode, bytes the reference's decoded_size prefix."""
         data = bytes(data)
         buf = ctypes.create_string_buffer(max(int(capacity), 1))
         n = ctypes.c_uint64(0)
-        code = self.lib.hostsim_decode(data, len(data), buf, int(capacity), 1 if large_window else 0, ctypes.byref(n))
+        cd = bytes(custom_dict) if custom_dict else b""
+        code = self.lib.hostsim_decode_dict(data, len(data), buf, int(capacity), 1 if large_window else 0, cd, len(cd), ctypes.byref(n))
         return code, buf.raw[:n.value]
 
 

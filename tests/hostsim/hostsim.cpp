@@ -18,7 +18,13 @@ extern "C" void hostsim_last_table_stats(uint32_t* stab_used, uint32_t* all_shar
   *stab_used = g_last_stab_used; *all_shared = g_last_all_shared; *unpromoted = g_last_unpromoted;
 }
 
+extern "C" int hostsim_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, const uint8_t* dict,
+                                   size_t dict_size, uint64_t* decoded);
 extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, uint64_t* decoded) {
+  return hostsim_decode_dict(in, in_size, out, cap, large_window, nullptr, 0, decoded);
+}
+extern "C" int hostsim_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, const uint8_t* dict,
+                                   size_t dict_size, uint64_t* decoded) {
   using namespace brotli_b200;
   static std::vector<uint2> cmd_lut;
   if (cmd_lut.empty()) { cmd_lut.resize(704); for (uint32_t i = 0; i < 704; i++) cmd_lut[i] = pack_cmd_lut(i); }
@@ -40,7 +46,7 @@ extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, s
   d.luts.ctx_lut = tbl::kBrotliContextLookup;
   d.luts.dictionary = kBrotliDictionaryData;
   uint64_t used = 0;
-  int rc = decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used);
+  int rc = decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used, dict, dict_size);
   g_last_stab_used = d.stab_used; g_last_all_shared = d.all_shared; g_last_unpromoted = d.n_unpromoted;
   return rc;
 }

@@ -64,7 +64,7 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
   c.word_info = hw::to_sref(word_info);
   c.transform_info = hw::to_sref(transform_info);
   uint64_t d = 0, u = 0;
-  const uint32_t r = lane::decode_streams(c, true, in, in_size, out, cap, &d, &u);
+  const uint32_t r = lane::decode_streams<16>(c, true, in, in_size, out, cap, &d, &u);
   *decoded = d;
   if (used) *used = u;
   return r == lane::kStDone ? 1 : 1000;

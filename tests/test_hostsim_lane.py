@@ -22,7 +22,7 @@ def test_fixture(hostsim, name):
     e = MAN[name]
     data = helpers.golden_fixture(name)
     for entries in (430, 178, 146, 100000):
-        for mis in (0, 1, 2, 3):
+        for mis in (0, 1, 2, 3, 13, 16, 28, 31):
             code, out, used = hostsim.lane_decode(data, e["original_size"], entries, mis)
             if code == 1:
                 assert hashlib.sha256(out).hexdigest() == e["original_sha256"], (name, entries, mis)
@@ -39,7 +39,7 @@ def test_generated_configs_and_capacity(hostsim, oracle, corpus):
         comp, orig, _ = corpus.make_config(cfg, n, size=size)
         ok = 0
         for c, o in zip(comp, orig):
-            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([178, 146])), int(rng.integers(0, 4)))
+            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([178, 146])), int(rng.integers(0, 32)))
             if code == 1:
                 assert out == o and used == len(c)
                 ok += 1
@@ -59,7 +59,7 @@ def test_mutations_never_accept_what_the_oracle_rejects(hostsim, oracle, corpus)
             if not m:
                 continue
             cap = len(o) + int(rng.integers(0, 64))
-            code, out, _ = hostsim.lane_decode(m, cap)
+            code, out, _ = hostsim.lane_decode(m, cap, 178, int(rng.integers(0, 32)))
             if code == 1:
                 _, ocode, oout = oracle.decode(m, cap)
                 assert ocode == 1 and out == oout
