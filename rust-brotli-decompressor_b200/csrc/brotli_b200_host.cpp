@@ -122,6 +122,7 @@ struct DeviceCtx {
 };
 
 DeviceCtx g_ctx[kMaxDevices];
+constexpr int kDefaultL2FetchBytes = 0;  // see acquire_ctx
 
 #define CU_TRY(expr)                                                                              \
   do {                                                                                            \
@@ -162,6 +163,16 @@ DeviceCtx* acquire_ctx() {
   if (!ok) {
     set_error(std::string("brotli_b200: device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
     return nullptr;
+  }
+  // L2 -> DRAM fetch granularity.  The decoders gather 4..16 bytes per backreference from windows that are, summed
+  // over the resident streams, far larger than L2; a smaller fetch unit cuts the over-fetch of every such miss.
+  // BROTLI_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity for the device, 0 leaves it alone.
+  {
+    const char* fetch_env = getenv("BROTLI_B200_L2_FETCH");
+    const int fetch = fetch_env ? atoi(fetch_env) : kDefaultL2FetchBytes;
+    if (fetch == 32 || fetch == 64 || fetch == 128) {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();  // a hint: not fatal
+    }
   }
   const char* lane_env = getenv("BROTLI_B200_LANE");
   if (!(lane_env && lane_env[0] == '0')) {
@@ -277,9 +288,17 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     size_t e = b; uint64_t acc = 0;
     // a chunk should fill every resident lane of the lane kernel: a launch takes about as long for a few streams
     // as for one stream per lane
-    // (the first chunk is a quarter of that: its H2D copy is not hidden behind anything)
+    // (the first chunk is a quarter of that: its H2D copy is not hidden behind anything.  A longer geometric ramp --
+    // BROTLI_B200_PIPE_RAMP=k: 1/2^k, ..., 1/2, 1 -- was measured and loses: every extra launch costs a full wave,
+    // 374 / 380 / 396 ms per headline call for k = 2 / 3 / 4 against 373 ms for the single quarter chunk)
     size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
-    if (b == 0) min_streams /= 4;
+    {
+      static const int ramp = getenv("BROTLI_B200_PIPE_RAMP") ? atoi(getenv("BROTLI_B200_PIPE_RAMP")) : 0;
+      const int ci = (int)chunks.size();
+      if (ramp > 0) { if (ci < ramp) min_streams >>= (ramp - ci); }
+      else if (b == 0) min_streams /= 4;
+      if (min_streams == 0) min_streams = 1;
+    }
     while (e < n && (e == b || acc < kPipelineChunkBytes || e - b < min_streams)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
     chunks.push_back(Chunk{b, e, nullptr, nullptr});
     b = e;

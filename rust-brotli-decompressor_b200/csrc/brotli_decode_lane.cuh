@@ -857,6 +857,9 @@ BD_DEV uint32_t build_xdict_entry(uint8_t* dst, const uint8_t* word, uint32_t le
 }
 
 // ======================= the command loop: phased rounds =======================
+#ifndef BD_LANE_COUNT
+#define BD_LANE_COUNT(i) ((void)0)  /* path statistics hook of the host build (tests/hostsim) */
+#endif
 enum : uint32_t { kStIdle = 0, kStHeader = 1, kStCommands = 2, kStFinish = 3, kStDone = 4, kStBail = 5 };
 enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a lane's stream needs next
 
@@ -1020,6 +1023,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     else if (n0_ < 8) v1_ &= mask_bits(8 * (n0_ - 4));                     \
     append8(out_al, bias, hist, posb, acc, v0_, v1_, n0_);                 \
     if (pend_n > 8) {                                                      \
+      BD_LANE_COUNT(3);                                                    \
       const uint32_t pw3_ = vlds32(sw_ + 12), pw4_ = vlds32(sw_ + 16);     \
       uint32_t v2_ = hw::funnelshift_r(pw2_, pw3_, s8_);                   \
       uint32_t v3_ = hw::funnelshift_r(pw3_, pw4_, s8_);                   \
@@ -1091,6 +1095,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
             tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
           }
+          BD_LANE_COUNT(6);
           LN_DECODE(tv, tr, bits, len, sym);
 #ifdef BD_LANE_FALLBACK_STATS
           BD_LANE_FALLBACK_STATS(0, is_lit);
@@ -1132,6 +1137,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             copy_len += (x >> ie) & mask_bits(ce);
             nskip = len + ie + ce;
           } else {
+            BD_LANE_COUNT(4);
             LN_SKIP(len);
             if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
             bits = LN_PEEK();  // (the literals below continue from this peek)
@@ -1199,6 +1205,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           LN_TAKE(48u, pc_valid, pc_e, pc_sel, bits, len, sym);
         } else {
           const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
+          BD_LANE_COUNT(7);
           LN_DECODE(tv, r_dist, bits, len, sym);
 #ifdef BD_LANE_FALLBACK_STATS
           BD_LANE_FALLBACK_STATS(1, 0);
@@ -1215,6 +1222,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
                                      : ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
         uint32_t extra, nskip = len + nbits;
         if (BD_UNLIKELY(nskip > 32)) {
+          BD_LANE_COUNT(5);
           LN_SKIP(len);
           extra = LN_PEEK() & mask_bits(nbits);
           nskip = nbits;
@@ -1255,11 +1263,13 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 
     // ---- phase C2: the copy or static dictionary word (:2583-2689); its source bytes are requested below ----
     if (go && ev == kStCommands) {
+      BD_LANE_COUNT(8);
       const uint32_t pos = posb - bias;
       const uint32_t max_distance = pos < max_backward ? pos : max_backward;
       crem = 0;
       if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
         // static dictionary: the transformed word is an entry of the expanded table
+        BD_LANE_COUNT(2);
         if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
           ev = kStBail;
         } else {
@@ -1290,6 +1300,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           crem = copy_len;
           uint32_t ud = (uint32_t)dist;
           if (BD_UNLIKELY(ud < 20)) {
+            BD_LANE_COUNT(0);
             // Short period: copy byte-wise until the period can be widened to >= 20 (a copy at distance d
             // equals a copy at distance k*d once k*d bytes are out); chunks do the rest.
             const uint32_t wide = ud * ((19u + ud) / ud);
@@ -1298,6 +1309,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             // global memory); while the period is shorter than four bytes it is widened as the bytes come out
             uint32_t dd = ud;
             for (uint32_t left = m; left != 0;) {
+              BD_LANE_COUNT(1);
               uint32_t n4 = dd < 4 ? dd : 4u;
               if (n4 > left) n4 = left;
               uint32_t v = recent4(hist, posb, acc, posb - dd);
