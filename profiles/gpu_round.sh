@@ -24,4 +24,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --cs
 # full capture of the dominant decode kernel (4th launch = first timed step)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:brotli_decode_lane -s 3 -c 1 -o $OUT/prof_lane \
   python bench.py --streams 131072 --unique 2048 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_bench.log 2>&1
+ncu -i $OUT/prof_lane.ncu-rep --page source --csv > $OUT/source.csv 2>/dev/null
+python profiles/ncu_l2_by_inst.py $OUT/source.csv 16 > $OUT/ncu_l2_by_inst.txt 2>&1
+python profiles/ncu_hot.py $OUT/prof_lane.ncu-rep > $OUT/ncu_lane_kernel.txt 2>&1
+ncu -i $OUT/prof_lane.ncu-rep --page raw --csv > $OUT/ncu_lane_kernel_raw.csv 2>/dev/null
+rm -f $OUT/source.csv
+if [ -n "$WITH_CONFIGS" ]; then timeout 900 python profiles/gpu_configs.py > $OUT/configs.jsonl 2> $OUT/configs.err; cat $OUT/configs.jsonl | cut -c1-250; fi
 ls -la $OUT

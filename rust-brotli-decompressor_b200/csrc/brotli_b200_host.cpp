@@ -282,13 +282,15 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
   CU_TRY(cudaMemcpyAsync(c->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
   CU_TRY(cudaMemcpyAsync(c->out_off.p, out_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
 
-  struct Chunk { size_t b, e; cudaEvent_t h2d, done; };
+  struct Chunk { size_t b, e; cudaEvent_t h2d, done; cudaEvent_t d2h = nullptr; };
+  static const bool trace = getenv("BROTLI_B200_PIPE_TRACE") != nullptr;  // per-chunk timeline on stderr
   std::vector<Chunk> chunks;
   for (size_t b = 0; b < n;) {
     size_t e = b; uint64_t acc = 0;
     // a chunk should fill every resident lane of the lane kernel: a launch takes about as long for a few streams
     // as for one stream per lane
-    // (the first chunk is a quarter of that: its H2D copy is not hidden behind anything.  A longer geometric ramp --
+    // (the first chunk is 0.4 of that: its H2D copy is not hidden behind anything, but its D2H copy should last as long
+    // as the decode of the second chunk -- BROTLI_B200_PIPE_TRACE timeline, profiles/r01/zz_pipe_trace.txt.  A longer geometric ramp --
     // BROTLI_B200_PIPE_RAMP=k: 1/2^k, ..., 1/2, 1 -- was measured and loses: every extra launch costs a full wave,
     // 374 / 380 / 396 ms per headline call for k = 2 / 3 / 4 against 373 ms for the single quarter chunk)
     size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
@@ -296,17 +298,19 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
       static const int ramp = getenv("BROTLI_B200_PIPE_RAMP") ? atoi(getenv("BROTLI_B200_PIPE_RAMP")) : 0;
       const int ci = (int)chunks.size();
       if (ramp > 0) { if (ci < ramp) min_streams >>= (ramp - ci); }
-      else if (b == 0) min_streams /= 4;
+      else if (b == 0) min_streams = min_streams * 2 / 5;
       if (min_streams == 0) min_streams = 1;
     }
     while (e < n && (e == b || acc < kPipelineChunkBytes || e - b < min_streams)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
-    chunks.push_back(Chunk{b, e, nullptr, nullptr});
+    chunks.push_back(Chunk{b, e, nullptr, nullptr, nullptr});
     b = e;
   }
   int rc = 0;
   for (auto& k : chunks) {
-    if (cudaEventCreateWithFlags(&k.h2d, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) { rc = BROTLI_DECODER_ERROR_UNREACHABLE; set_error("brotli_b200: cudaEventCreate failed"); break; }
+    const unsigned flags = trace ? cudaEventDefault : cudaEventDisableTiming;
+    if (trace) cudaEventCreate(&k.d2h);
+    if (cudaEventCreateWithFlags(&k.h2d, flags) != cudaSuccess ||
+        cudaEventCreateWithFlags(&k.done, flags) != cudaSuccess) { rc = BROTLI_DECODER_ERROR_UNREACHABLE; set_error("brotli_b200: cudaEventCreate failed"); break; }
   }
   bool timed = false;
   for (size_t ci = 0; ci < chunks.size() && rc == 0; ci++) {
@@ -326,6 +330,7 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     e = cudaEventRecord(k.done, c->s_compute);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_d2h, k.done, 0);
     if (e == cudaSuccess && o1 > o0) e = cudaMemcpyAsync(out_bytes + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, c->s_d2h);
+    if (trace && k.d2h) cudaEventRecord(k.d2h, c->s_d2h);
     if (e != cudaSuccess) { set_error(std::string("brotli_b200: D2H stage failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; break; }
   }
   if (rc == 0) {
@@ -341,7 +346,17 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     rc = BROTLI_DECODER_ERROR_UNREACHABLE;
   }
   if (rc == 0 && timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) == cudaSuccess) g_last_kernel_ms.store(ms); }
-  for (auto& k : chunks) { if (k.h2d) cudaEventDestroy(k.h2d); if (k.done) cudaEventDestroy(k.done); }
+  if (trace && rc == 0 && !chunks.empty()) {
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+      float th = 0, td = 0, to = 0;
+      cudaEventElapsedTime(&th, chunks[0].h2d, chunks[ci].h2d);  // relative to the end of the first H2D copy
+      cudaEventElapsedTime(&td, chunks[0].h2d, chunks[ci].done);
+      if (chunks[ci].d2h) cudaEventElapsedTime(&to, chunks[0].h2d, chunks[ci].d2h);
+      fprintf(stderr, "brotli_b200 pipe: chunk %zu streams %zu  h2d_done %.1f ms  decode_done %.1f ms  d2h_done %.1f ms\n", ci,
+              chunks[ci].e - chunks[ci].b, th, td, to);
+    }
+  }
+  for (auto& k : chunks) { if (k.h2d) cudaEventDestroy(k.h2d); if (k.done) cudaEventDestroy(k.done); if (k.d2h) cudaEventDestroy(k.d2h); }
   return rc;
 }
 
