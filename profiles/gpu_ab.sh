@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun call: A/B of library variants on the headline probe and on the other configs (same box, back to back).
+TAG=${1:-ab}
+VARS=${2:-"default"}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+for rep in 1 2; do
+for v in $VARS; do
+  LIB=""
+  if [ "$v" != "default" ]; then LIB=$PWD/rust-brotli-decompressor_b200/variants/libbrotli_b200_$v.so; fi
+  BROTLI_B200_LIB=$LIB timeout 600 python bench.py --streams 131072 --unique 2048 --steps 3 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${v}_$rep.json 2> $OUT/bench_${v}_$rep.err
+  python -c "import json; j=json.load(open('$OUT/bench_${v}_$rep.json')); print('$v rep $rep headline probe', j['value'], 'GB/s ms', j['ms_per_step'], 'bit_exact', j.get('bit_exact'))"
+  if [ $rep = 1 ]; then
+    BROTLI_B200_LIB=$LIB timeout 900 python profiles/gpu_configs.py > $OUT/configs_$v.jsonl 2> $OUT/configs_$v.err
+    python -c "
+import json
+for l in open('$OUT/configs_$v.jsonl'):
+    j=json.loads(l); print('$v', j['config'], j['GBps'], 'GB/s', j['ms'], 'ms bailed', j['bailed_to_exact'], j['bit_exact'])"
+  fi
+done
+done

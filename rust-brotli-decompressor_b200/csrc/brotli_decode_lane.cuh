@@ -60,8 +60,10 @@ constexpr uint32_t kBlockRootBits = 6;
 #define BD_LANE_EXTRA_LITERALS 1
 #endif
 constexpr uint32_t kMaxExtraLiterals = BD_LANE_EXTRA_LITERALS;  // literals a lane may add to its phase-A literal per round
+// (measured and rejected: 2 takes 14 % of the rounds off a text stream, but the extra code is issued in every round of
+// every warp -- headline +-0, C3 -2 %, C5 -7 %: the kernel is bound by instructions per round, not by rounds)
 #ifndef BD_LANE_CMD_LITERALS
-#define BD_LANE_CMD_LITERALS 2
+#define BD_LANE_CMD_LITERALS 0
 #endif
 constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may decode in the round of their command
 struct ArenaLayout {
