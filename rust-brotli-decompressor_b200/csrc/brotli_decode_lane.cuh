@@ -185,6 +185,12 @@ BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 l
 #endif
 
 BD_DEV uint32_t mask_bits(uint32_t n) { return (1u << n) - 1u; }  // n <= 31
+// x & mask_bits(n) in one instruction (SGXT.U32); n >= 32 keeps x
+#if defined(BROTLI_B200_HOSTSIM)
+static inline uint32_t low_bits(uint32_t x, uint32_t n) { return n >= 32 ? x : x & ((1u << n) - 1u); }
+#else
+BD_DEV uint32_t low_bits(uint32_t x, uint32_t n) { uint32_t r; asm("szext.clamp.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+#endif
 
 #if !defined(BROTLI_B200_HOSTSIM)
 // LUTs read by all lanes of the CTA (filled by the kernel before its first __syncthreads()).  At namespace scope so
@@ -803,7 +809,8 @@ BD_HD XDictLayout xdict_layout() {
   x.total = off;
   return x;
 }
-// word info [len]: (xdict_base(len) / 4) << 4 | size bits;  transform info [t]: prefix length | suffix length << 4 | type << 8
+// word info [len]: (xdict_base(len) / 4) << 4 | size bits;  transform info [t]: prefix length | suffix length << 4 |
+// (bytes the transform cuts from the word: omit-first / omit-last count) << 8
 BD_DEV uint32_t pack_word_info(const XDictLayout& x, uint32_t len) {
   return ((x.base[len] >> 2) << 4) | dict_size_bits(len);
 }
@@ -813,7 +820,9 @@ BD_DEV uint32_t pack_transform_info(uint32_t t) {
   uint32_t plen = 0, slen = 0;
   while (prefix[plen]) plen++;
   while (suffix[slen]) slen++;
-  return plen | (slen << 4) | ((uint32_t)tbl::kBrotliTransforms[t * 3 + 1] << 8);
+  const uint32_t type = tbl::kBrotliTransforms[t * 3 + 1];
+  const uint32_t cut = type <= tbl::BROTLI_TRANSFORM_OMIT_LAST_9 ? type : (type < tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 ? 0u : type - (tbl::BROTLI_TRANSFORM_OMIT_FIRST_1 - 1));
+  return plen | (slen << 4) | (cut << 8);
 }
 // Bytes of the word itself that survive transform `type` (omit-first / omit-last).
 BD_DEV uint32_t transformed_word_length(uint32_t len, uint32_t type) {
@@ -992,12 +1001,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_DECODE(TV, TR, BITS, LEN, SYM)                                                        \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
-    const uint32_t v_ = (TV) + (BITS & mask_bits(TR));                                           \
+    const uint32_t v_ = (TV) + low_bits(BITS, TR);                                           \
     uint32_t e_ = vlds16(stab + ((v_ < E ? v_ : 0u) << 1));                                      \
     ld16_if(v_ >= E, gtab + (v_ - E), e_);  /* root outside the shared slot */                    \
     const bool need2_ = (e_ & 15u) > (TR);                                                       \
     const uint32_t sub_ = need2_ ? (e_ & 15u) - (TR) : 0u;                                       \
-    ld16_if(need2_, gtab + ((e_ >> 4) << 2) + ((BITS >> (TR)) & mask_bits(sub_)), e_);           \
+    ld16_if(need2_, gtab + ((e_ >> 4) << 2) + low_bits(BITS >> (TR), sub_), e_);           \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
 // request the next copy chunk: min(crem, 16) bytes from csrc on; only 16-byte blocks that hold source bytes
@@ -1019,21 +1028,20 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const uint32_t pw0_ = vlds32(sw_), pw1_ = vlds32(sw_ + 4), pw2_ = vlds32(sw_ + 8); \
     uint32_t v0_ = hw::funnelshift_r(pw0_, pw1_, s8_);                     \
     uint32_t v1_ = hw::funnelshift_r(pw1_, pw2_, s8_);                     \
-    const uint32_t n0_ = pend_n < 8 ? pend_n : 8u;                         \
-    if (n0_ < 4) v0_ &= mask_bits(8 * n0_);                                \
-    if (n0_ <= 4) v1_ = 0;                                                 \
-    else if (n0_ < 8) v1_ &= mask_bits(8 * (n0_ - 4));                     \
-    append8(out_al, bias, hist, posb, acc, v0_, v1_, n0_);                 \
+    /* byte masks without branches: low_bits keeps everything from 32 bits on and nothing at 0 bits */ \
+    const uint32_t b0_ = 8u * (pend_n < 8 ? pend_n : 8u);                  \
+    v0_ = low_bits(v0_, b0_);                                              \
+    v1_ = low_bits(v1_, b0_ - (b0_ < 32 ? b0_ : 32u));                     \
+    append8(out_al, bias, hist, posb, acc, v0_, v1_, b0_ >> 3);            \
     if (pend_n > 8) {                                                      \
       BD_LANE_COUNT(3);                                                    \
       const uint32_t pw3_ = vlds32(sw_ + 12), pw4_ = vlds32(sw_ + 16);     \
       uint32_t v2_ = hw::funnelshift_r(pw2_, pw3_, s8_);                   \
       uint32_t v3_ = hw::funnelshift_r(pw3_, pw4_, s8_);                   \
-      const uint32_t n1_ = pend_n - 8;                                     \
-      if (n1_ < 4) v2_ &= mask_bits(8 * n1_);                              \
-      if (n1_ <= 4) v3_ = 0;                                               \
-      else if (n1_ < 8) v3_ &= mask_bits(8 * (n1_ - 4));                   \
-      append8(out_al, bias, hist, posb, acc, v2_, v3_, n1_);               \
+      const uint32_t b1_ = 8u * (pend_n - 8);                              \
+      v2_ = low_bits(v2_, b1_);                                            \
+      v3_ = low_bits(v3_, b1_ - (b1_ < 32 ? b1_ : 32u));                   \
+      append8(out_al, bias, hist, posb, acc, v2_, v3_, b1_ >> 3);          \
     }                                                                      \
     pend_n = 0;                                                            \
   } while (0)
@@ -1046,12 +1054,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_LOOKAHEAD(TV, TR, SLOT, PV, PE, PSEL)                                                 \
   do {                                                                                           \
     const uint32_t bits_ = LN_PEEK();                                                            \
-    const uint32_t v_ = (TV) + (bits_ & mask_bits(TR));                                          \
+    const uint32_t v_ = (TV) + low_bits(bits_, TR);                                          \
     const bool in_ = v_ < E;                                                                     \
     const uint32_t e_ = vlds16(stab + ((in_ ? v_ : 0u) << 1));                                   \
     const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
     const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
-    const uint32_t i2_ = ((e_ >> 4) << 2) + ((bits_ >> (TR)) & mask_bits(sub_));                 \
+    const uint32_t i2_ = ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);                 \
     LN_CP16_IF_KEEP(two_, stage + (SLOT), gtab + (i2_ & ~7u));                                   \
     PV = in_; PE = two_ ? 0x80000000u : e_; PSEL = two_ ? (i2_ & 7u) << 1 : PSEL;                \
   } while (0)
@@ -1114,7 +1122,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           if (trivial) {
             for (uint32_t rep = 0; rep < kMaxExtraLiterals; rep++) {
               if (ins == 0 || bl_l == 0 || nskip + r_lit > 32) break;
-              const uint32_t v2 = lit_tv + ((bits >> nskip) & mask_bits(r_lit));
+              const uint32_t v2 = lit_tv + low_bits(bits >> nskip, r_lit);
               const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
               if (v2 >= E || (e2 & 15u) > r_lit) break;
               bl_l--;
@@ -1135,15 +1143,15 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           const uint32_t ie = (lut.x >> 16) & 0xFFu, ce = lut.y >> 16;
           if (BD_LIKELY(len + ie + ce <= 32)) {  // symbol and both extra fields from the one 32-bit peek
             const uint32_t x = bits >> len;
-            ins += x & mask_bits(ie);
-            copy_len += (x >> ie) & mask_bits(ce);
+            ins += low_bits(x, ie);
+            copy_len += low_bits(x >> ie, ce);
             nskip = len + ie + ce;
           } else {
             BD_LANE_COUNT(4);
             LN_SKIP(len);
-            if (ie) { ins += LN_PEEK() & mask_bits(ie); LN_SKIP(ie); }
+            if (ie) { ins += low_bits(LN_PEEK(), ie); LN_SKIP(ie); }
             bits = LN_PEEK();  // (the literals below continue from this peek)
-            copy_len += bits & mask_bits(ce);
+            copy_len += low_bits(bits, ce);
             nskip = ce;
           }
           bl_c--;
@@ -1159,7 +1167,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             if (kCmdLiterals != 0 && trivial && mlen >= 0 && ins + pend_n <= capb - posb) {
               for (uint32_t rep = 0; rep < kCmdLiterals; rep++) {
                 if (ins == 0 || bl_l == 0 || nskip + r_lit > 32) break;
-                const uint32_t v2 = lit_tv + ((bits >> nskip) & mask_bits(r_lit));
+                const uint32_t v2 = lit_tv + low_bits(bits >> nskip, r_lit);
                 const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
                 if (v2 >= E || (e2 & 15u) > r_lit) break;
                 bl_l--;
@@ -1221,15 +1229,15 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         const uint32_t hcode = distval >> npostfix;
         const uint32_t nbits = (longcode && !direct) ? (hcode >> 1) + 1 : 0u;
         const uint32_t base = direct ? sym - 15u
-                                     : ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + (distval & mask_bits(npostfix)) + ndirect - 15u;
+                                     : ((((2u + (hcode & 1u)) << nbits) - 4u) << npostfix) + low_bits(distval, npostfix) + ndirect - 15u;
         uint32_t extra, nskip = len + nbits;
         if (BD_UNLIKELY(nskip > 32)) {
           BD_LANE_COUNT(5);
           LN_SKIP(len);
-          extra = LN_PEEK() & mask_bits(nbits);
+          extra = low_bits(LN_PEEK(), nbits);
           nskip = nbits;
         } else {
-          extra = (bits >> len) & mask_bits(nbits);
+          extra = low_bits(bits >> len, nbits);
         }
         LN_SKIP(nskip);
         // last distances (sym 0..3) and last / second-to-last distance -3..+3 (sym 4..15), :2017-2049
@@ -1283,11 +1291,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
             ev = kStBail;
           } else {
             const uint32_t ti = vlds32(transform_info + t * 4u);
-            const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + transformed_word_length(copy_len, ti >> 8);
+            const uint32_t cut = ti >> 8;  // == copy_len - transformed_word_length(copy_len, type), saturated
+            const uint32_t n = (ti & 15u) + ((ti >> 4) & 15u) + (copy_len > cut ? copy_len - cut : 0u);
             if (n > capb - posb || n == 0) {  // (an empty word makes no progress: left to the exact decoder)
               ev = kStBail;
             } else {
-              csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)((word_id & mask_bits(shift)) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
+              csrc = xdict + ((size_t)(wi >> 4) << 2) + (size_t)(low_bits(word_id, shift) * BROTLI_NUM_TRANSFORMS + t) * xdict_stride(copy_len);
               crem = n;
               mlen -= (int32_t)n;
             }
@@ -1315,7 +1324,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
               uint32_t n4 = dd < 4 ? dd : 4u;
               if (n4 > left) n4 = left;
               uint32_t v = recent4(hist, posb, acc, posb - dd);
-              if (n4 < 4) v &= mask_bits(8 * n4);
+              if (n4 < 4) v = low_bits(v, 8 * n4);
               append(out_al, bias, hist, posb, acc, v, n4);
               left -= n4;
               if (dd < 4) dd += ud;
