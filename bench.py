@@ -39,8 +39,8 @@ METRIC = "decompressed GB/s on 256Kx64KiB brotli batch"
 N_STREAMS = 262144
 STREAM_BYTES = 65536
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per stream of the dominant kernel, from the committed
-# `ncu --set full` capture of a headline-shaped launch (profiles/r01/*ncu_lane_kernel*); None = no capture yet.
-NCU_TRAFFIC_BYTES_PER_STREAM = 1268340  # profiles/r01/z_ncu_lane_kernel_raw.csv: (155.21 + 11.03) GB over a 131 072-stream launch
+# `ncu --set full` capture of a headline-shaped launch (profiles/r01/zz_ncu_lane_kernel*); None = no capture yet.
+NCU_TRAFFIC_BYTES_PER_STREAM = 1267320  # profiles/r01/zz_ncu_lane_kernel_raw.csv: (155.07 + 11.04) GB over a 131 072-stream launch
 
 
 def parse_args():
