@@ -204,7 +204,7 @@ DeviceCtx* acquire_ctx() {
 // ---- device-resident batch -------------------------------------------------------------------
 int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                   const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_codes, uint64_t* d_in_used, uint32_t large_window,
-                  cudaStream_t stream, const uint8_t* d_dict = nullptr, uint64_t dict_size = 0) {
+                  cudaStream_t stream, const uint8_t* d_dict = nullptr, uint64_t dict_size = 0, brotli_b200::ResumeState* d_resume = nullptr) {
   if (n == 0) return 0;
   if (n > 0xFFFFFFF0ull) { set_error("brotli_b200: batch too large"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
   BatchArgs a;
@@ -213,6 +213,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   a.order = nullptr; a.ticket = c->ticket; a.arena = c->arena; a.dictionary = c->dictionary;
   a.n = (uint32_t)n; a.large_window = large_window; a.n_ptr = nullptr;
   a.custom_dict = dict_size ? d_dict : nullptr; a.custom_dict_size = d_dict ? dict_size : 0;
+  a.resume = n == 1 ? d_resume : nullptr;
   std::lock_guard<std::mutex> lock(c->launch_mu);
   if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
   const uint32_t slot = c->timed_count % DeviceCtx::kTimedLaunches;
@@ -220,7 +221,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
   // (streams with a custom dictionary go straight to the exact kernel: the lane kernel keeps every distance inside
   // the output region)
-  if (c->lane_ctas > 0 && a.custom_dict_size == 0) {
+  if (c->lane_ctas > 0 && a.custom_dict_size == 0 && a.resume == nullptr) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
     brotli_b200::LaneArgs la;
@@ -453,7 +454,63 @@ struct BrotliDecoderStateStruct {
   int last_code;                 // BrotliDecoderErrorCode of the last decode
   bool used, large_window, failed, finished;
   char error[256];
+  // streaming session on the device: the stream's bytes and everything decoded so far stay in device memory, and the
+  // kernel's ResumeState lets each call continue behind the last metablock boundary
+  uint8_t* d_in; size_t d_in_cap, d_in_size;
+  uint8_t* d_out; size_t d_out_cap;
+  uint8_t* d_meta;   // in_off[2] | out_off[2] | out_len | in_used | code, ResumeState at byte 128
 };
+
+constexpr size_t kSessionMetaBytes = 512, kSessionResumeAt = 128;
+// BROTLI_B200_STREAM_SESSION=0|1 overrides the default
+constexpr bool kStreamSessionsDefault = false;
+const bool g_stream_sessions = getenv("BROTLI_B200_STREAM_SESSION") ? getenv("BROTLI_B200_STREAM_SESSION")[0] != '0' : kStreamSessionsDefault;
+
+// Grow a session buffer, keeping its first `keep` bytes.
+static int session_grow(DeviceCtx* c, uint8_t** p, size_t* cap, size_t need, size_t keep) {
+  if (need <= *cap) return 0;
+  size_t want = need + need / 2 + 4096;
+  uint8_t* q = nullptr;
+  CU_TRY(cudaMalloc((void**)&q, want));
+  if (*p && keep) CU_TRY(cudaMemcpyAsync(q, *p, keep, cudaMemcpyDeviceToDevice, c->s_compute));
+  CU_TRY(cudaStreamSynchronize(c->s_compute));
+  if (*p) cudaFree(*p);
+  *p = q; *cap = want;
+  return 0;
+}
+
+// One decode of the session's stream so far: `fresh` bytes are appended to the device copy of the input, the exact
+// kernel continues from the session's ResumeState into the device output buffer (capacity out_cap), and the bytes
+// decoded beyond `have` (what the host already holds) come back in `suffix`.
+static int decode_session(DeviceCtx* c, BrotliDecoderStateStruct* s, const uint8_t* fresh, size_t n_fresh, size_t out_cap, size_t have,
+                          int32_t* code, uint64_t* decoded, uint64_t* used, std::vector<uint8_t>* suffix) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!s->d_meta) {
+    CU_TRY(cudaMalloc((void**)&s->d_meta, kSessionMetaBytes));
+    CU_TRY(cudaMemsetAsync(s->d_meta, 0, kSessionMetaBytes, c->s_compute));
+  }
+  if (session_grow(c, &s->d_in, &s->d_in_cap, s->d_in_size + n_fresh + 16, s->d_in_size) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
+  if (session_grow(c, &s->d_out, &s->d_out_cap, out_cap + 16, have) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
+  if (n_fresh) CU_TRY(cudaMemcpyAsync(s->d_in + s->d_in_size, fresh, n_fresh, cudaMemcpyHostToDevice, c->s_compute));
+  s->d_in_size += n_fresh;
+  uint64_t meta[4] = {0, (uint64_t)s->d_in_size, 0, (uint64_t)out_cap};
+  CU_TRY(cudaMemcpyAsync(s->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->s_compute));
+  uint64_t* m = (uint64_t*)s->d_meta;
+  int rc = decode_device(c, 1, s->d_in, m, s->d_out, m + 2, m + 4, (int32_t*)(m + 6), m + 5, s->large_window ? 1u : 0u, c->s_compute, nullptr, 0,
+                         (brotli_b200::ResumeState*)(s->d_meta + kSessionResumeAt));
+  if (rc != 0) return rc;
+  uint64_t res[3] = {0, 0, 0};  // out_len, in_used, code
+  CU_TRY(cudaMemcpyAsync(res, m + 4, sizeof(res), cudaMemcpyDeviceToHost, c->s_compute));
+  CU_TRY(cudaStreamSynchronize(c->s_compute));
+  *decoded = res[0]; *used = res[1]; *code = (int32_t)(uint32_t)res[2];
+  suffix->clear();
+  if (res[0] > have) {
+    suffix->resize((size_t)(res[0] - have));
+    CU_TRY(cudaMemcpyAsync(suffix->data(), s->d_out + have, suffix->size(), cudaMemcpyDeviceToHost, c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+  }
+  return 0;
+}
 
 BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
   if ((alloc_func == nullptr) != (free_func == nullptr)) return nullptr;  // src/ffi/mod.rs:132-135
@@ -464,11 +521,15 @@ BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, br
   s->taken = 0; s->consumed_reported = 0; s->last_code = 0;
   s->used = false; s->large_window = false; s->failed = false; s->finished = false;
   s->error[0] = 0;
+  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr;
   return s;
 }
 
 void BrotliDecoderDestroyInstance(BrotliDecoderState* s) {
   if (!s) return;
+  if (s->d_in) cudaFree(s->d_in);
+  if (s->d_out) cudaFree(s->d_out);
+  if (s->d_meta) cudaFree(s->d_meta);
   brotli_free_func f = s->free_func; void* opaque = s->opaque;
   s->~BrotliDecoderStateStruct();
   if (f) f(opaque, s); else free(s);
@@ -525,6 +586,28 @@ BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t*
     BrotliDecoderReturnInfo r;
     uint64_t used = 0;
     std::vector<uint8_t> buf;
+    if (g_stream_sessions && s->input.size() != 0 && s->input.size() < ((uint64_t)1 << 32)) {
+      // device-resident session: only the fresh bytes go up, only the new output comes down, and the kernel
+      // continues behind the last complete metablock
+      DeviceCtx* c = acquire_ctx();
+      if (!c) return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str());
+      if (cap < s->d_out_cap && s->d_out_cap > 16) cap = s->d_out_cap - 16;
+      size_t n_fresh = fresh;
+      const uint8_t* fresh_ptr = s->input.data() + (s->input.size() - fresh);
+      if (s->d_in_size + fresh != s->input.size()) { fresh_ptr = s->input.data() + s->d_in_size; n_fresh = s->input.size() - s->d_in_size; }
+      for (;;) {
+        int32_t code = 0; uint64_t decoded = 0;
+        int rc = decode_session(c, s, fresh_ptr, n_fresh, cap, s->output.size(), &code, &decoded, &used, &buf);
+        if (rc != 0) return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str());
+        n_fresh = 0;
+        if (!buf.empty()) s->output.insert(s->output.end(), buf.begin(), buf.end());
+        r = make_info(code == 1 ? 1 : (code == 2 ? 2 : (code == 3 ? 3 : 0)), code, (size_t)decoded, nullptr);
+        if (r.code != BROTLI_DECODER_NEEDS_MORE_OUTPUT) break;
+        if (cap >= ((size_t)1 << 31)) break;
+        cap *= 4;
+      }
+      s->used = true;
+    } else {
     for (;;) {
       buf.resize(cap);
       r = one_shot(s->input.data(), s->input.size(), buf.data(), cap, s->large_window ? 1u : 0u, &used);
@@ -536,6 +619,7 @@ BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t*
     if (s->input.size()) s->used = true;
     // new suffix of the output
     if (r.decoded_size > s->output.size()) s->output.insert(s->output.end(), buf.data() + s->output.size(), buf.data() + r.decoded_size);
+    }
     s->last_code = r.code;
     // input accounting: a finished stream leaves trailing bytes unconsumed (src/ffi/mod.rs:452-453)
     size_t consumed_total = s->input.size();

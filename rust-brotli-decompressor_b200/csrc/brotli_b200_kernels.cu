@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
     const uint64_t out0 = a.out_off[i], out1 = a.out_off[i + 1];
     uint64_t decoded = 0, used = 0;
     const int code = decode_stream(d, a.in + in0, in1 - in0, a.out + out0, out1 - out0, a.large_window, &decoded, &used, a.custom_dict,
-                                   a.custom_dict_size);
+                                   a.custom_dict_size, n == 1 ? a.resume : nullptr);
     if (lane == 0) {
       a.out_len[i] = decoded;
       a.codes[i] = code;
@@ -85,6 +85,8 @@ __global__ void brotli_checksum_batch_kernel(uint32_t n, const uint8_t* bytes, c
     if (lane == 0) sums[i] = acc ^ (L * 0x94D049BB133111EBull);
   }
 }
+
+size_t resume_state_bytes() { return sizeof(ResumeState); }
 
 size_t arena_bytes_per_warp() { return ArenaLayout::kBytes; }
 

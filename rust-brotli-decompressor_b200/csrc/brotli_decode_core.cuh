@@ -1541,11 +1541,25 @@ BD_COLD int copy_uncompressed(Decoder& d) {
 }
 
 // ======================= stream driver (src/decode.rs:2779-3403) =======================
+// Decoder state at a metablock boundary: what BrotliState carries from one BrotliDecompressStream call to the
+// next once a metablock is complete (src/state.rs:156-278: bit position, output position, last distances, window
+// and ring-buffer geometry).  A streaming session keeps its input and output in device memory; each call decodes
+// from the last boundary the previous call reached instead of from the first byte.  All zero = start of stream.
+struct ResumeState {
+  uint64_t bitpos;        // bits of the stream consumed up to the boundary
+  uint64_t rbsize, next_flush, flushed;
+  uint32_t valid;
+  uint32_t pos;
+  int32_t d0, d1, d2, d3;
+  uint32_t wbits, large_window, rb_allocated, full_ring;
+};
+
 // Returns the BrotliDecoderErrorCode; *decoded_size follows the reference's flush rules:
 // success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity, fatal -> only
 // what the ring buffer had flushed (multiples of its size).
 BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint32_t allow_large_window,
-                         uint64_t* decoded_size, uint64_t* in_used, const uint8_t* custom_dict = nullptr, uint64_t custom_dict_size = 0) {
+                         uint64_t* decoded_size, uint64_t* in_used, const uint8_t* custom_dict = nullptr, uint64_t custom_dict_size = 0,
+                         ResumeState* resume = nullptr) {
   BitReader& br = d.br;
   br.init(in, in_size);
   d.out = out;
@@ -1557,6 +1571,14 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   do {
     if (in_size >= ((uint64_t)1 << 32)) { result = kErrInvalidArguments; break; }  // src/decode.rs:2799-2801
     if (in_size == 0) { result = kNeedsMoreInput; break; }
+    if (resume && resume->valid) {  // continue behind the last metablock a previous call of this session completed
+      d.wbits = resume->wbits; d.large_window = resume->large_window;
+      d.pos = resume->pos; d.d0 = resume->d0; d.d1 = resume->d1; d.d2 = resume->d2; d.d3 = resume->d3;
+      d.rb_allocated = resume->rb_allocated; d.full_ring = resume->full_ring;
+      d.rbsize = resume->rbsize; d.next_flush = resume->next_flush; d.flushed = resume->flushed;
+      br.seek_byte(resume->bitpos >> 3);
+      br.skip<false>((uint32_t)(resume->bitpos & 7));
+    } else
     // DecodeWindowBits, src/decode.rs:152-187,2940-2951
     if (br.read<false>(1) == 0) {
       d.wbits = 16;
@@ -1653,7 +1675,21 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
       }
       // BROTLI_STATE_METABLOCK_DONE, src/decode.rs:3345-3381
       if (d.mlen < 0) { result = kErrBlockLength2; break; }
-      if (!is_last) continue;
+      if (!is_last) {
+        if (resume && !br.overrun()) {  // a complete metablock: the next call of the session starts here
+          hw::syncwarp();
+          if (hw::lane() == 0) {
+            resume->bitpos = br.bitpos() - 8 * (uint64_t)br.lead;
+            resume->rbsize = d.rbsize; resume->next_flush = d.next_flush; resume->flushed = d.flushed;
+            resume->pos = d.pos; resume->d0 = d.d0; resume->d1 = d.d1; resume->d2 = d.d2; resume->d3 = d.d3;
+            resume->wbits = d.wbits; resume->large_window = d.large_window;
+            resume->rb_allocated = d.rb_allocated; resume->full_ring = d.full_ring;
+            resume->valid = 1;
+          }
+          hw::syncwarp();
+        }
+        continue;
+      }
       if (!br.jump_to_byte_boundary()) { result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break; }
       if (br.overrun()) { result = kNeedsMoreInput; break; }
       result = kSuccess;

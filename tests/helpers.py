@@ -81,6 +81,10 @@ class HostSim:
         L.hostsim_decode_dict.restype = ctypes.c_int
         L.hostsim_decode_dict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_decode_resume.restype = ctypes.c_int
+        L.hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_resume_state_bytes.restype = ctypes.c_size_t
         L.hostsim_lane_decode.restype = ctypes.c_int
         L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -113,6 +117,30 @@ class HostSim:
         cd = bytes(custom_dict) if custom_dict else b""
         code = self.lib.hostsim_decode_dict(data, len(data), buf, int(capacity), 1 if large_window else 0, cd, len(cd), ctypes.byref(n))
         return code, buf.raw[:n.value]
+
+
+class HostSimSession:
+    """A streaming session of the exact kernel's logic (host build): one persistent output buffer and the
+    ResumeState the kernel keeps between calls (decode resumes behind the last completed metablock)."""
+
+    def __init__(self, hostsim, capacity):
+        self.lib = hostsim.lib
+        self.buf = ctypes.create_string_buffer(max(int(capacity), 1))
+        self.cap = int(capacity)
+        self.state = ctypes.create_string_buffer(int(self.lib.hostsim_resume_state_bytes()))
+
+    def decode(self, data_so_far, large_window=True):
+        data = bytes(data_so_far)
+        n = ctypes.c_uint64(0)
+        code = self.lib.hostsim_decode_resume(data, len(data), self.buf, self.cap, 1 if large_window else 0, self.state, ctypes.byref(n))
+        return code, self.buf.raw[:n.value]
+
+    def resumed_at(self):
+        """(valid, bit position, output position) of the saved boundary."""
+        import struct
+        bitpos, = struct.unpack_from("<Q", self.state.raw, 0)
+        valid, pos = struct.unpack_from("<II", self.state.raw, 32)
+        return valid, bitpos, pos
 
 
 def result_of(code):

@@ -23,6 +23,17 @@ extern "C" int hostsim_decode_dict(const uint8_t* in, size_t in_size, uint8_t* o
 extern "C" int hostsim_decode(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, uint64_t* decoded) {
   return hostsim_decode_dict(in, in_size, out, cap, large_window, nullptr, 0, decoded);
 }
+extern "C" int hostsim_decode_resume(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, void* resume_state,
+                                     uint64_t* decoded);
+extern "C" size_t hostsim_resume_state_bytes() { return sizeof(brotli_b200::ResumeState); }
+static void* g_resume = nullptr;
+extern "C" int hostsim_decode_resume(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, void* resume_state,
+                                     uint64_t* decoded) {
+  g_resume = resume_state;
+  int rc = hostsim_decode_dict(in, in_size, out, cap, large_window, nullptr, 0, decoded);
+  g_resume = nullptr;
+  return rc;
+}
 extern "C" int hostsim_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, const uint8_t* dict,
                                    size_t dict_size, uint64_t* decoded) {
   using namespace brotli_b200;
@@ -46,7 +57,7 @@ extern "C" int hostsim_decode_dict(const uint8_t* in, size_t in_size, uint8_t* o
   d.luts.ctx_lut = tbl::kBrotliContextLookup;
   d.luts.dictionary = kBrotliDictionaryData;
   uint64_t used = 0;
-  int rc = decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used, dict, dict_size);
+  int rc = decode_stream(d, in, in_size, out, cap, (uint32_t)large_window, decoded, &used, dict, dict_size, (ResumeState*)g_resume);
   g_last_stab_used = d.stab_used; g_last_all_shared = d.all_shared; g_last_unpromoted = d.n_unpromoted;
   return rc;
 }

@@ -297,3 +297,41 @@ def test_differential_fuzz_error_codes(gpu_lib, pkg, oracle, corpus):
         code = oracle.decode(s, c)[1]
         codes[code] = codes.get(code, 0) + 1
     assert n_ok >= 90 and len([k for k in codes if k < 0]) >= 12, codes  # a dozen distinct format errors at least
+
+
+def test_streaming_session_resumes_behind_metablocks(gpu_lib, pkg, corpus):
+    """a BrotliDecoderState keeps its stream and its output on the device and each
+    BrotliDecoderDecompressStream call continues behind the last complete metablock (ResumeState), so feeding a
+    multi-metablock stream in small pieces costs far less device time than re-decoding every prefix."""
+    import time
+    pool = corpus.text_pool()
+    data = pool[100000:100000 + 1000000]
+    comp = corpus.compress(data, 2)          # q2: a metablock every few hundred KB of input
+    for in_chunk, out_chunk in ((len(comp) // 40 + 1, 1 << 20), (8192, 65536), (len(comp), 4096)):
+        st = pkg.DecoderState()
+        got, pos, r = [], 0, 2
+        pkg.kernel_times(reset=True)
+        for _ in range(1000000):
+            r, used, out = st.decompress_stream(comp[pos:pos + in_chunk], out_chunk)
+            pos += used
+            got.append(out)
+            if r in (0, 1):
+                break
+        assert r == 1 and st.is_finished() and b"".join(got) == data, (in_chunk, out_chunk, r)
+        st.close()
+    # truncated stream: NEEDS_MORE_INPUT with everything decodable handed out, then the rest completes it
+    st = pkg.DecoderState()
+    half = len(comp) // 2
+    r, used, out1 = st.decompress_stream(comp[:half], 1 << 21)
+    assert r == 2 and used == half and data.startswith(out1) and len(out1) > 0
+    r, used, out2 = st.decompress_stream(comp[half:], 1 << 21)
+    assert r == 1 and out1 + out2 == data
+    st.close()
+    # corruption behind a completed metablock: the reference's error code for the whole stream
+    bad = bytearray(comp); bad[len(comp) * 3 // 4] ^= 0x5A
+    info, _ = pkg.brotli_decode(bytes(bad), len(data) + 64)
+    st = pkg.DecoderState()
+    r, used, _ = st.decompress_stream(bytes(bad[:half]), 1 << 21)
+    r, used, _ = st.decompress_stream(bytes(bad[half:]), 1 << 21)
+    assert (r == 0) == (info.code < 0) and (info.code >= 0 or st.error_code() == info.code)
+    st.close()
