@@ -463,7 +463,7 @@ struct BrotliDecoderStateStruct {
 
 constexpr size_t kSessionMetaBytes = 512, kSessionResumeAt = 128;
 // BROTLI_B200_STREAM_SESSION=0|1 overrides the default
-constexpr bool kStreamSessionsDefault = false;
+constexpr bool kStreamSessionsDefault = true;
 const bool g_stream_sessions = getenv("BROTLI_B200_STREAM_SESSION") ? getenv("BROTLI_B200_STREAM_SESSION")[0] != '0' : kStreamSessionsDefault;
 
 // Grow a session buffer, keeping its first `keep` bytes.
