@@ -219,14 +219,15 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   const uint32_t slot = c->timed_count % DeviceCtx::kTimedLaunches;
   for (int e = 0; e < 3; e++) if (!c->ev_t[slot][e]) CU_TRY(cudaEventCreate(&c->ev_t[slot][e]));
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
-  // (streams with a custom dictionary go straight to the exact kernel: the lane kernel keeps every distance inside
-  // the output region)
-  if (c->lane_ctas > 0 && a.custom_dict_size == 0 && a.resume == nullptr) {
+  // (a streaming session is one stream: exact kernel; a batch with a custom dictionary takes the lane kernel's dictionary
+  // instance when the configured geometry has one)
+  if (c->lane_ctas > 0 && a.resume == nullptr && (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
     brotli_b200::LaneArgs la;
     la.arena = c->lane_arena; la.bail_count = c->bail_count; la.bail_list = (uint32_t*)c->bail_list.p;
     la.slot_bytes = c->lane_slot_bytes; la.xdict = c->xdict;
+    la.cdict = a.custom_dict; la.cdict_len = a.custom_dict_size;
     // small batches: fewer streams per warp, spread over all resident warps
     const size_t total_warps = (size_t)c->lane_ctas * c->lane_warps;
     const size_t per_warp = (n + total_warps - 1) / total_warps;
@@ -264,8 +265,8 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lock(c->mu);
   if (dict_size) {
-    CU_TRY(c->cdict.reserve(dict_size));
-    CU_TRY(cudaMemcpyAsync(c->cdict.p, dict, dict_size, cudaMemcpyHostToDevice, c->s_h2d));  // ordered before the first chunk's h2d event
+    CU_TRY(c->cdict.reserve(dict_size + 64));  // 32 bytes of slack on either side: the lane kernel reads whole aligned 16-byte blocks
+    CU_TRY(cudaMemcpyAsync((uint8_t*)c->cdict.p + 32, dict, dict_size, cudaMemcpyHostToDevice, c->s_h2d));  // ordered before the first chunk's h2d event
   }
   const uint64_t in_base = in_off[0], out_base = out_off[0];
   const uint64_t in_total = in_off[n] - in_base, out_total = out_off[n] - out_base;
@@ -325,7 +326,7 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     if (e != cudaSuccess) { set_error(std::string("brotli_b200: H2D stage failed: ") + cudaGetErrorString(e)); rc = BROTLI_DECODER_ERROR_UNREACHABLE; break; }
     rc = decode_device(c, k.e - k.b, d_in, (const uint64_t*)c->in_off.p + k.b, d_out, (const uint64_t*)c->out_off.p + k.b,
                        (uint64_t*)c->out_len.p + k.b, (int32_t*)c->codes.p + k.b, in_used ? (uint64_t*)c->in_used.p + k.b : nullptr,
-                       large_window, c->s_compute, dict_size ? (const uint8_t*)c->cdict.p : nullptr, dict_size);
+                       large_window, c->s_compute, dict_size ? (const uint8_t*)c->cdict.p + 32 : nullptr, dict_size);
     if (rc != 0) break;
     if (ci + 1 == chunks.size()) cudaEventRecord(c->ev_k1, c->s_compute);
     e = cudaEventRecord(k.done, c->s_compute);

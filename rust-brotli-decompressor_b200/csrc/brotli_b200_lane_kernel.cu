@@ -13,7 +13,8 @@ namespace brotli_b200 {
 
 // One persistent CTA per SM.  Static shared memory: the command LUT and the literal-context LUT, read by
 // all lanes.  Dynamic shared memory: one private slot per lane (slot header + root tables).
-template <int WARPS>
+// DICT: the batch carries a custom LZ77 dictionary (its own instance: batches without one run the code they always ran).
+template <int WARPS, bool DICT = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(BatchArgs a, LaneArgs la) {
   uint2* const s_cmd_lut = lane::g_cmd_lut;
   uint8_t* const s_ctx_lut = lane::g_ctx_lut;
@@ -53,6 +54,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   c.xdict = la.xdict;
   c.word_info = hw::to_sref(s_word_info);
   c.transform_info = hw::to_sref(s_transform_info);
+  c.cdict = DICT ? la.cdict : nullptr;
+  c.cdict_len = DICT ? la.cdict_len : 0;
 
   const uint32_t chunk = la.chunk;  // streams a warp takes per ticket (32 unless the batch is small)
   for (;;) {
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
     }
     uint64_t decoded = 0, used = 0;
     // the whole warp decodes together: one stream per lane, one prefix-code symbol per lane and iteration
-    const uint32_t r = lane::decode_streams<WARPS * 32 * 16>(c, active, a.in + in0, in1 - in0, a.out + out0, out1 - out0, &decoded, &used);
+    const uint32_t r = lane::decode_streams<WARPS * 32 * 16, DICT>(c, active, a.in + in0, in1 - in0, a.out + out0, out1 - out0, &decoded, &used);
     if (active) {
       if (r == lane::kStDone) {
         a.out_len[i] = decoded;
@@ -176,7 +179,11 @@ int query_lane_resident_ctas(int device, int warps) {
   return per_sm * sms;
 }
 
+// the dictionary instance exists for the default geometry only
+bool lane_kernel_takes_dictionary(int warps) { return warps == 14; }
+
 cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream) {
+  if (la.cdict_len != 0 && !lane_kernel_takes_dictionary(warps)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
@@ -186,7 +193,14 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
     case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;
     case 12: brotli_decode_lane_kernel<12><<<ctas, 384, dyn, stream>>>(a, la); break;
-    case 14: brotli_decode_lane_kernel<14><<<ctas, 448, dyn, stream>>>(a, la); break;
+    case 14:
+      if (la.cdict_len != 0) {
+        if (cudaFuncSetAttribute(brotli_decode_lane_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return cudaGetLastError();
+        brotli_decode_lane_kernel<14, true><<<ctas, 448, dyn, stream>>>(a, la);
+      } else {
+        brotli_decode_lane_kernel<14><<<ctas, 448, dyn, stream>>>(a, la);
+      }
+      break;
     case 16: brotli_decode_lane_kernel<16><<<ctas, 512, dyn, stream>>>(a, la); break;
     case 20: brotli_decode_lane_kernel<20><<<ctas, 640, dyn, stream>>>(a, la); break;
     case 24: brotli_decode_lane_kernel<24><<<ctas, 768, dyn, stream>>>(a, la); break;

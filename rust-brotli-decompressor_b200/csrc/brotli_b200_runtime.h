@@ -61,6 +61,8 @@ struct LaneArgs {
   const uint8_t* xdict;  // expanded static dictionary, xdict_bytes(), filled by launch_build_xdict
   uint32_t slot_bytes;   // shared-memory slot per lane
   uint32_t chunk;        // streams a warp takes per ticket (1..32)
+  const uint8_t* cdict;  // custom LZ77 dictionary of the batch or nullptr; 16 readable bytes on either side
+  uint64_t cdict_len;
 };
 
 size_t arena_bytes_per_warp();
@@ -74,6 +76,7 @@ cudaError_t launch_order_by_size(uint32_t n, const uint64_t* in_off, uint32_t* s
 size_t xdict_bytes();
 cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream);
 int query_lane_resident_ctas(int device, int warps);
+bool lane_kernel_takes_dictionary(int warps);
 cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream);
 cudaError_t launch_checksum_batch(uint32_t n, const uint8_t* bytes, const uint64_t* off, const uint64_t* len, uint64_t* sums,
                                   cudaStream_t stream);

@@ -220,6 +220,8 @@ struct LaneCtx {
   const uint8_t* dictionary;  // RFC 7932 dictionary (source of the expanded table)
   const uint8_t* xdict;  // expanded static dictionary (every word under every transform), see xdict_layout
   hw::sref_t word_info;       // shared: u32[25], pack_word_info
+  const uint8_t* cdict;       // custom LZ77 dictionary of the batch (kDict instances only; 16 readable bytes on either side)
+  uint64_t cdict_len;
   hw::sref_t transform_info;  // shared: u32[121], pack_transform_info
 };
 
@@ -255,6 +257,10 @@ struct Lane {
   uint32_t posb, acc, bias, capb;
   // stream / metablock
   uint32_t wbits, max_backward, is_last;
+  // custom dictionary as this stream's window sees it (src/decode.rs:1831-1838, :2954-2955), kDict instances only
+  const uint8_t* cdict_end;  // one past the dictionary's last byte
+  uint32_t cdict_size;       // reachable bytes: min(length, max_backward)
+  int32_t cdict_limit;       // positions below it have max_distance = pos + cdict_size
   int32_t mlen;
   int32_t d0, d1, d2, d3;
   uint32_t bl[3], nbt[3], rb[6];   // category order: 0 literal, 1 command, 2 distance (reference order)
@@ -879,7 +885,8 @@ enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a
 // (metablock complete) or kStBail for every lane that ran.
 // kStride: distance between the two 16-byte blocks of a lane's block-interleaved input ring (16 x the CTA's
 // threads), a compile-time constant of the kernel instance.
-template <uint32_t kStride>
+// kDict: the batch has a custom LZ77 dictionary (a separate kernel instance, so that streams without one pay nothing).
+template <uint32_t kStride, bool kDict>
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
   // register copies of the hot state
   const uint8_t* gin = nullptr;
@@ -892,6 +899,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
   uint32_t bl_l = 0, bl_c = 0, bl_d = 0;
   uint32_t max_backward = 0, npostfix = 0, ndirect = 0;
+  const uint8_t* cdict_end = nullptr;
+  uint32_t cdict_size = 0;
+  int32_t cdict_limit = 0;
   uint32_t r_lit = 0, r_cmd = 0, r_dist = 0, root_lit = 0;
   uint32_t cmd_tv = 0, lit_tv = 0, trivial = 0;  // trees of the current command / literal block type
   hw::sref_t ctx_lut = 0, ctx_map = 0;
@@ -926,6 +936,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     d0 = L.d0; d1 = L.d1; d2 = L.d2; d3 = L.d3;
     bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];
     max_backward = L.max_backward; npostfix = L.npostfix; ndirect = L.ndirect;
+    if (kDict) { cdict_end = L.cdict_end; cdict_size = L.cdict_size; cdict_limit = L.cdict_limit; }
     r_lit = L.rbits[0]; r_cmd = L.rbits[1]; r_dist = L.rbits[2]; root_lit = L.root[0];
     LN_TREES();
   }
@@ -1101,7 +1112,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           uint32_t tv = is_lit ? lit_tv : cmd_tv;
           const uint32_t tr = is_lit ? r_lit : r_cmd;
           if (is_lit && !trivial) {  // tree by the context of the last two bytes (:2500-2507)
-            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
+            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; if (kDict && posb - bias < 2) { p1 = 0; p2 = 0; } }
             const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
             tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
           }
@@ -1261,7 +1272,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (next_cmd ? bl_c != 0 : (next_lit && bl_l != 0)) {
         uint32_t tv = next_cmd ? cmd_tv : lit_tv;
         if (!next_cmd && !trivial) {  // tree by the context of the last two bytes (:2500-2507); phase P is over
-          if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; }
+          if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; if (kDict && posb - bias < 2) { p1 = 0; p2 = 0; } }
           const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
           tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
         }
@@ -1275,7 +1286,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     if (go && ev == kStCommands) {
       BD_LANE_COUNT(8);
       const uint32_t pos = posb - bias;
-      const uint32_t max_distance = pos < max_backward ? pos : max_backward;
+      // src/decode.rs:2583-2589 (with a dictionary: pos + its reachable size until that passes max_backward)
+      const uint32_t max_distance = kDict ? ((int32_t)pos < cdict_limit ? pos + cdict_size : max_backward) : (pos < max_backward ? pos : max_backward);
       crem = 0;
       if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
         // static dictionary: the transformed word is an entry of the expanded table
@@ -1310,6 +1322,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           mlen -= (int32_t)copy_len;
           crem = copy_len;
           uint32_t ud = (uint32_t)dist;
+          if (kDict && ud > pos) {
+            // the source starts in the custom dictionary, which logically precedes the output: a plain copy from the
+            // dictionary's tail when it also ends there; a copy that runs on into the output is the exact kernel's
+            if (ud - pos < copy_len) { ev = kStBail; crem = 0; }
+            csrc = cdict_end - (ud - pos);
+          } else {
           if (BD_UNLIKELY(ud < 20)) {
             BD_LANE_COUNT(0);
             // Short period: copy byte-wise until the period can be widened to >= 20 (a copy at distance d
@@ -1335,6 +1353,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           // Everything below the current output word is in memory, and a distance >= 20 keeps the sixteen
           // source bytes of every chunk below that word at the time the chunk is loaded.
           csrc = out_al + (posb - ud);
+          }
         }
       }
       if (ev == kStCommands) {
@@ -1427,6 +1446,9 @@ BD_DEV uint32_t stream_begin(const LaneCtx& c, Lane& L, const uint8_t* in, uint6
     }
   }
   L.max_backward = (1u << L.wbits) - 16;
+  L.cdict_size = c.cdict_len > L.max_backward ? L.max_backward : (uint32_t)c.cdict_len;
+  L.cdict_end = c.cdict + c.cdict_len;
+  L.cdict_limit = c.cdict_len > L.max_backward ? 0 : (int32_t)(L.max_backward - (uint32_t)c.cdict_len);
   return kStHeader;
 }
 
@@ -1444,7 +1466,7 @@ BD_DEV uint32_t stream_finish(Lane& L, uint64_t* decoded, uint64_t* used) {
 
 // One stream per lane, the whole warp together (lanes without a stream pass active == false).
 // Returns kStDone (decoded; sizes written) or kStBail (hand the stream to the exact kernel).
-template <uint32_t kStride>
+template <uint32_t kStride, bool kDict>
 BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap,
                                uint64_t* decoded, uint64_t* used) {
   Lane L;
@@ -1458,7 +1480,7 @@ BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in,
     }
     warp_sync();
     if (!warp_any(st == kStCommands)) break;
-    run_commands<kStride>(c, L, bt, st == kStCommands, st);
+    run_commands<kStride, kDict>(c, L, bt, st == kStCommands, st);
     // METABLOCK_DONE, src/decode.rs:3345-3381: BLOCK_LENGTH_2 (:3356-3359) / truncated input
     if (st == kStHeader && (L.mlen < 0 || L.overrun())) st = kStBail;
     if (st == kStHeader && L.is_last) st = kStFinish;

@@ -81,6 +81,9 @@ class HostSim:
         L.hostsim_decode_dict.restype = ctypes.c_int
         L.hostsim_decode_dict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_lane_decode_dict.restype = ctypes.c_int
+        L.hostsim_lane_decode_dict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                               ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
         L.hostsim_decode_resume.restype = ctypes.c_int
         L.hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
@@ -92,7 +95,7 @@ class HostSim:
 
     LANE_BAIL = 1000
 
-    def lane_decode(self, data, capacity, table_entries=178, misalign=0):
+    def lane_decode(self, data, capacity, table_entries=178, misalign=0, custom_dict=None):
         """Lane-per-stream (optimistic) path -> (code, bytes, input bytes used); code 1 = decoded, LANE_BAIL = the
         path gave the stream up (the exact kernel decodes it on the device; bytes are then meaningless).
         table_entries = u16 entries of the lane's shared-memory slot; misalign = output address modulo 32 (the
@@ -104,7 +107,9 @@ class HostSim:
         off = addr - ctypes.addressof(buf)
         n = ctypes.c_uint64(0)
         used = ctypes.c_uint64(0)
-        code = self.lib.hostsim_lane_decode(data, len(data), addr, int(capacity), int(table_entries), ctypes.byref(n), ctypes.byref(used))
+        cd = bytes(custom_dict) if custom_dict else b""
+        code = self.lib.hostsim_lane_decode_dict(data, len(data), addr, int(capacity), int(table_entries), ctypes.byref(n), ctypes.byref(used),
+                                                 cd, len(cd))
         raw = buf.raw
         assert raw[:off] == bytes(off) and raw[off + int(capacity):] == bytes(len(raw) - off - int(capacity)), "wrote outside the region"
         return code, raw[off:off + n.value], used.value

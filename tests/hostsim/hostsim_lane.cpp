@@ -10,8 +10,14 @@
 
 extern "C" const uint8_t kBrotliDictionaryData[];
 
+extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, uint32_t table_entries, uint64_t* decoded,
+                                        uint64_t* used, const uint8_t* dict, size_t dict_size);
 extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, uint32_t table_entries, uint64_t* decoded,
                                    uint64_t* used) {
+  return hostsim_lane_decode_dict(in, in_size, out, cap, table_entries, decoded, used, nullptr, 0);
+}
+extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, uint32_t table_entries, uint64_t* decoded,
+                                        uint64_t* used, const uint8_t* dict, size_t dict_size) {
   using namespace brotli_b200;
   static std::vector<uint2> cmd_lut;
   if (cmd_lut.empty()) { cmd_lut.resize(704); for (uint32_t i = 0; i < 704; i++) cmd_lut[i] = pack_cmd_lut(i); }
@@ -64,7 +70,12 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
   c.word_info = hw::to_sref(word_info);
   c.transform_info = hw::to_sref(transform_info);
   uint64_t d = 0, u = 0;
-  const uint32_t r = lane::decode_streams<16>(c, true, in, in_size, out, cap, &d, &u);
+  std::vector<uint8_t> dict_padded(dict_size + 64);
+  if (dict_size) memcpy(dict_padded.data() + 32, dict, dict_size);
+  c.cdict = dict_padded.data() + 32;
+  c.cdict_len = dict_size;
+  const uint32_t r = dict_size ? lane::decode_streams<16, true>(c, true, in, in_size, out, cap, &d, &u)
+                               : lane::decode_streams<16, false>(c, true, in, in_size, out, cap, &d, &u);
   *decoded = d;
   if (used) *used = u;
   return r == lane::kStDone ? 1 : 1000;

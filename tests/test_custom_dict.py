@@ -138,3 +138,45 @@ def test_gpu_custom_dictionary_batch(gpu_lib, pkg, oracle, corpus):
     plain = [corpus.compress(o, 5) for o in origs[:40]]
     res = pkg.decompress_batch(plain, [len(o) for o in origs[:40]])
     assert all(r[1] == 1 and r[2] == o for r, o in zip(res, origs[:40]))
+
+
+def test_lane_core_with_dictionary(oracle, hostsim, corpus):
+    """The lane kernel's dictionary instance (host build): it decodes a stream exactly as the oracle does or gives it up
+    (copies that start in the dictionary and run on into the output, anything malformed) -- and it must decode most
+    well-formed streams itself."""
+    rng = np.random.default_rng(31)
+    decoded = total = 0
+    for comp, d, data in dict_cases(corpus, 30, 40):
+        total += 1
+        code, out, used = hostsim.lane_decode(comp, len(data), int(rng.choice([146, 178])), int(rng.integers(0, 4)), custom_dict=d)
+        if code == 1:
+            assert out == data and used == len(comp)
+            decoded += 1
+        else:
+            assert code == hostsim.LANE_BAIL
+        for m in helpers.mutations(comp, rng, 10):
+            cap = len(data) + int(rng.integers(0, 32))
+            code, out, _ = hostsim.lane_decode(m, cap, 178, int(rng.integers(0, 4)), custom_dict=d)
+            if code == 1:
+                _, ocode, oout = oracle.decode(m, cap, True, d)
+                assert ocode == 1 and out == oout
+    for v in VEC:
+        data, d, want = (bytes.fromhex(v[k]) for k in ("input_hex", "dict_hex", "output_hex"))
+        code, out, _ = hostsim.lane_decode(data, 1024, 178, 0, custom_dict=d)
+        assert code == hostsim.LANE_BAIL or out == want
+    # dictionaries longer than the window and the zero context seed (q10/q11 model literal contexts from byte 0)
+    pool = corpus.text_pool()
+    tail = pool[300000:320000]
+    payload = pool[310000:319000]
+    comp = corpus.compress_with_dictionary(payload, tail, 9, 16)
+    for pad in (0, 65520 - len(tail), 200000):
+        dd = pool[:pad] + tail
+        _, ocode, oout = oracle.decode(comp, len(payload), True, dd)
+        code, out, _ = hostsim.lane_decode(comp, len(payload), 178, 0, custom_dict=dd)
+        assert code == hostsim.LANE_BAIL or (ocode == 1 and out == oout), pad
+    for q in (10, 11):
+        d = pool[1000:4000]; payload = pool[8000:14000]
+        comp = corpus.compress_with_dictionary(payload, d, q)
+        code, out, _ = hostsim.lane_decode(comp, len(payload), 178, 0, custom_dict=d)
+        assert code == hostsim.LANE_BAIL or out == payload
+    assert decoded >= total * 3 // 4, (decoded, total)
