@@ -202,6 +202,12 @@ BROTLI_B200_API int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in
 BROTLI_B200_API BrotliDecoderReturnInfo BrotliB200DecompressWithDictionary(size_t encoded_size, const uint8_t* encoded_buffer,
                                                                            size_t decoded_size, uint8_t* decoded_buffer,
                                                                            const uint8_t* dictionary, size_t dictionary_size);
+/* Streaming form: attaches a custom dictionary to a decoder state before its first input byte -- what
+ * Decompressor::new_with_custom_dict (src/reader.rs:105) and DecompressorWriter::new_with_custom_dictionary
+ * (src/writer.rs:117) do through BrotliState::new_with_custom_dictionary.  The bytes are copied.  Returns 1, or 0 if the
+ * state has been used already or the arguments are invalid. */
+BROTLI_B200_API int BrotliB200DecoderSetCustomDictionary(BrotliDecoderState* state, const uint8_t* dictionary,
+                                                         size_t dictionary_size);
 /* BrotliB200DecompressBatchPacked with one custom dictionary (host memory) shared by all streams of the batch. */
 BROTLI_B200_API int BrotliB200DecompressBatchPackedWithDictionary(size_t n, const uint8_t* in_bytes, const uint64_t* in_off,
                                                                   uint8_t* out_bytes, const uint64_t* out_off, uint64_t* out_len,

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "BrotliDecoderGetErrorString", "BrotliDecoderErrorString", "BrotliDecoderVersion", "BrotliDecoderMallocU8",
     "BrotliDecoderFreeU8", "BrotliDecoderMallocUsize", "BrotliDecoderFreeUsize", "BrotliB200DecompressBatchDevice",
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
-    "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary",
+    "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary", "BrotliB200DecoderSetCustomDictionary",
     "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
     "BrotliB200Shutdown",
 ]
@@ -97,6 +97,8 @@ def lib():
     L.BrotliB200DecompressWithDictionary.argtypes = [sz, vp, sz, vp, vp, sz]
     L.BrotliB200DecompressBatchPackedWithDictionary.restype = ctypes.c_int
     L.BrotliB200DecompressBatchPackedWithDictionary.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
+    L.BrotliB200DecoderSetCustomDictionary.restype = ctypes.c_int
+    L.BrotliB200DecoderSetCustomDictionary.argtypes = [vp, vp, sz]
     L.BrotliB200ChecksumBatchDevice.restype = ctypes.c_int
     L.BrotliB200ChecksumBatchDevice.argtypes = [sz, vp, vp, vp, vp, vp]
     L.BrotliB200KernelLaunchCount.restype = ctypes.c_uint64
@@ -173,12 +175,16 @@ def BrotliDecoderDecompress(data, capacity):
 class DecoderState:
     """BrotliDecoderState driven through BrotliDecoderDecompressStream (src/ffi/mod.rs:389-463)."""
 
-    def __init__(self, large_window=False):
+    def __init__(self, large_window=False, custom_dict=None):
         self._s = lib().BrotliDecoderCreateInstance(None, None, None)
         if not self._s:
             raise BrotliB200Error("BrotliDecoderCreateInstance failed")
         if large_window:
             lib().BrotliDecoderSetParameter(self._s, 1, 1)
+        if custom_dict:  # BrotliState::new_with_custom_dictionary, src/state.rs:400-411
+            cd = bytes(custom_dict)
+            if not lib().BrotliB200DecoderSetCustomDictionary(self._s, cd, len(cd)):
+                raise BrotliB200Error("BrotliB200DecoderSetCustomDictionary failed")
 
     def close(self):
         if self._s:
@@ -224,10 +230,11 @@ class Decompressor:
     ``ValueError("Invalid Data")`` for a corrupt stream or, on the read after the end, when
     bytes remain after the final metablock (src/reader.rs:299-350)."""
 
-    def __init__(self, reader, buffer_size=4096):
+    def __init__(self, reader, buffer_size=4096, custom_dict=None):
+        """``custom_dict``: ``Decompressor::new_with_custom_dict(r, buffer_size, dict)`` (src/reader.rs:105)."""
         self._r = reader
         self._bufsize = max(int(buffer_size), 1)
-        self._state = DecoderState()
+        self._state = DecoderState(custom_dict=custom_dict)
         self._pending = b""
         self._eof = False
         self._done = False

@@ -460,6 +460,9 @@ struct BrotliDecoderStateStruct {
   uint8_t* d_in; size_t d_in_cap, d_in_size;
   uint8_t* d_out; size_t d_out_cap;
   uint8_t* d_meta;   // in_off[2] | out_off[2] | out_len | in_used | code, ResumeState at byte 128
+  // custom LZ77 dictionary of this state (BrotliState::new_with_custom_dictionary, src/state.rs:400-411)
+  std::vector<uint8_t> dict;
+  uint8_t* d_dict;   // device copy, 32 bytes of slack on either side
 };
 
 constexpr size_t kSessionMetaBytes = 512, kSessionResumeAt = 128;
@@ -492,13 +495,17 @@ static int decode_session(DeviceCtx* c, BrotliDecoderStateStruct* s, const uint8
   }
   if (session_grow(c, &s->d_in, &s->d_in_cap, s->d_in_size + n_fresh + 16, s->d_in_size) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
   if (session_grow(c, &s->d_out, &s->d_out_cap, out_cap + 16, have) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
+  if (!s->dict.empty() && !s->d_dict) {
+    CU_TRY(cudaMalloc((void**)&s->d_dict, s->dict.size() + 64));
+    CU_TRY(cudaMemcpyAsync(s->d_dict + 32, s->dict.data(), s->dict.size(), cudaMemcpyHostToDevice, c->s_compute));
+  }
   if (n_fresh) CU_TRY(cudaMemcpyAsync(s->d_in + s->d_in_size, fresh, n_fresh, cudaMemcpyHostToDevice, c->s_compute));
   s->d_in_size += n_fresh;
   uint64_t meta[4] = {0, (uint64_t)s->d_in_size, 0, (uint64_t)out_cap};
   CU_TRY(cudaMemcpyAsync(s->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->s_compute));
   uint64_t* m = (uint64_t*)s->d_meta;
-  int rc = decode_device(c, 1, s->d_in, m, s->d_out, m + 2, m + 4, (int32_t*)(m + 6), m + 5, s->large_window ? 1u : 0u, c->s_compute, nullptr, 0,
-                         (brotli_b200::ResumeState*)(s->d_meta + kSessionResumeAt));
+  int rc = decode_device(c, 1, s->d_in, m, s->d_out, m + 2, m + 4, (int32_t*)(m + 6), m + 5, s->large_window ? 1u : 0u, c->s_compute,
+                         s->d_dict ? s->d_dict + 32 : nullptr, s->dict.size(), (brotli_b200::ResumeState*)(s->d_meta + kSessionResumeAt));
   if (rc != 0) return rc;
   uint64_t res[3] = {0, 0, 0};  // out_len, in_used, code
   CU_TRY(cudaMemcpyAsync(res, m + 4, sizeof(res), cudaMemcpyDeviceToHost, c->s_compute));
@@ -522,7 +529,7 @@ BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, br
   s->taken = 0; s->consumed_reported = 0; s->last_code = 0;
   s->used = false; s->large_window = false; s->failed = false; s->finished = false;
   s->error[0] = 0;
-  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr;
+  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr; s->d_dict = nullptr;
   return s;
 }
 
@@ -531,6 +538,7 @@ void BrotliDecoderDestroyInstance(BrotliDecoderState* s) {
   if (s->d_in) cudaFree(s->d_in);
   if (s->d_out) cudaFree(s->d_out);
   if (s->d_meta) cudaFree(s->d_meta);
+  if (s->d_dict) cudaFree(s->d_dict);
   brotli_free_func f = s->free_func; void* opaque = s->opaque;
   s->~BrotliDecoderStateStruct();
   if (f) f(opaque, s); else free(s);
@@ -611,7 +619,7 @@ BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t*
     } else {
     for (;;) {
       buf.resize(cap);
-      r = one_shot(s->input.data(), s->input.size(), buf.data(), cap, s->large_window ? 1u : 0u, &used);
+      r = one_shot(s->input.data(), s->input.size(), buf.data(), cap, s->large_window ? 1u : 0u, &used, s->dict.empty() ? nullptr : s->dict.data(), s->dict.size());
       if (r.code != BROTLI_DECODER_NEEDS_MORE_OUTPUT) break;
       if (cap >= ((size_t)1 << 31)) break;
       cap *= 4;
@@ -734,6 +742,15 @@ int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in, const size_t* 
 }
 
 // ---- custom LZ77 dictionary (BrotliState::new_with_custom_dictionary, src/state.rs:400-411; src/lib.rs:105-131) ----
+// Streaming form: the dictionary belongs to the state, as in Decompressor::new_with_custom_dict (src/reader.rs:105) and
+// DecompressorWriter::new_with_custom_dictionary (src/writer.rs:117).  Only before the first input byte.
+int BrotliB200DecoderSetCustomDictionary(BrotliDecoderState* s, const uint8_t* dictionary, size_t dictionary_size) {
+  if (!s || s->used || (dictionary_size && !dictionary)) return 0;
+  try { s->dict.assign(dictionary, dictionary + dictionary_size); } catch (...) { return 0; }
+  if (s->d_dict) { cudaFree(s->d_dict); s->d_dict = nullptr; }
+  return 1;
+}
+
 BrotliDecoderReturnInfo BrotliB200DecompressWithDictionary(size_t encoded_size, const uint8_t* encoded_buffer, size_t decoded_size,
                                                            uint8_t* decoded_buffer, const uint8_t* dictionary, size_t dictionary_size) {
   try {

@@ -88,6 +88,8 @@ class HostSim:
         L.hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.hostsim_resume_state_bytes.restype = ctypes.c_size_t
+        L.hostsim_session_dictionary.restype = None
+        L.hostsim_session_dictionary.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.hostsim_lane_decode.restype = ctypes.c_int
         L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -128,8 +130,9 @@ class HostSimSession:
     """A streaming session of the exact kernel's logic (host build): one persistent output buffer and the
     ResumeState the kernel keeps between calls (decode resumes behind the last completed metablock)."""
 
-    def __init__(self, hostsim, capacity):
+    def __init__(self, hostsim, capacity, custom_dict=None):
         self.lib = hostsim.lib
+        self.dict = bytes(custom_dict) if custom_dict else b""
         self.buf = ctypes.create_string_buffer(max(int(capacity), 1))
         self.cap = int(capacity)
         self.state = ctypes.create_string_buffer(int(self.lib.hostsim_resume_state_bytes()))
@@ -137,7 +140,9 @@ class HostSimSession:
     def decode(self, data_so_far, large_window=True):
         data = bytes(data_so_far)
         n = ctypes.c_uint64(0)
+        self.lib.hostsim_session_dictionary(self.dict if self.dict else None, len(self.dict))
         code = self.lib.hostsim_decode_resume(data, len(data), self.buf, self.cap, 1 if large_window else 0, self.state, ctypes.byref(n))
+        self.lib.hostsim_session_dictionary(None, 0)
         return code, self.buf.raw[:n.value]
 
     def resumed_at(self):

@@ -27,10 +27,13 @@ extern "C" int hostsim_decode_resume(const uint8_t* in, size_t in_size, uint8_t*
                                      uint64_t* decoded);
 extern "C" size_t hostsim_resume_state_bytes() { return sizeof(brotli_b200::ResumeState); }
 static void* g_resume = nullptr;
+static const uint8_t* g_resume_dict = nullptr;
+static size_t g_resume_dict_size = 0;
+extern "C" void hostsim_session_dictionary(const uint8_t* dict, size_t dict_size) { g_resume_dict = dict; g_resume_dict_size = dict_size; }
 extern "C" int hostsim_decode_resume(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, int large_window, void* resume_state,
                                      uint64_t* decoded) {
   g_resume = resume_state;
-  int rc = hostsim_decode_dict(in, in_size, out, cap, large_window, nullptr, 0, decoded);
+  int rc = hostsim_decode_dict(in, in_size, out, cap, large_window, g_resume_dict, g_resume_dict_size, decoded);
   g_resume = nullptr;
   return rc;
 }

@@ -180,3 +180,35 @@ def test_lane_core_with_dictionary(oracle, hostsim, corpus):
         code, out, _ = hostsim.lane_decode(comp, len(payload), 178, 0, custom_dict=d)
         assert code == hostsim.LANE_BAIL or out == payload
     assert decoded >= total * 3 // 4, (decoded, total)
+
+
+@pytest.mark.gpu
+def test_gpu_streaming_with_custom_dictionary(gpu_lib, pkg, oracle, corpus):
+    """Decompressor::new_with_custom_dict / BrotliDecompressCustomDict semantics through the streaming state."""
+    import io
+    pool = corpus.text_pool()
+    d = pool[600000:650000]
+    data = pool[610000:610000 + 500000]
+    comp = corpus.compress_with_dictionary(data, d, 2)
+    st = pkg.DecoderState(custom_dict=d)
+    got, pos, r = [], 0, 2
+    while r not in (0, 1):
+        r, used, out = st.decompress_stream(comp[pos:pos + 30000], 1 << 18)
+        pos += used
+        got.append(out)
+    assert r == 1 and b"".join(got) == data
+    st.close()
+    rd = pkg.Decompressor(io.BytesIO(comp), 4096, custom_dict=d)
+    out = b""
+    while True:
+        b = rd.read(100000)
+        if not b:
+            break
+        out += b
+    assert out == data
+    for v in VEC:  # the reference's own dictionary tests run through a streaming state (src/test.rs:120-150)
+        st = pkg.DecoderState(custom_dict=bytes.fromhex(v["dict_hex"]))
+        r, used, out = st.decompress_stream(bytes.fromhex(v["input_hex"]), 1024)
+        assert r == 1 and out == bytes.fromhex(v["output_hex"])
+        assert not pkg.lib().BrotliB200DecoderSetCustomDictionary(st._s, b"x", 1)  # only before the first byte
+        st.close()

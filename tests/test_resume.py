@@ -67,3 +67,22 @@ def test_resume_after_output_growth_and_errors(oracle, hostsim, corpus):
     code3, out3 = sess.decode(bytes(bad))
     _, ocode, oout = oracle.decode(bytes(bad), len(data) + 64)
     assert (code3, out3) == (ocode, oout)
+
+
+def test_resume_with_custom_dictionary(oracle, hostsim, corpus):
+    """A session whose state carries a custom dictionary (Decompressor::new_with_custom_dict): multi-metablock stream,
+    arbitrary chunking, every call equal to a from-scratch decode with the same dictionary."""
+    rng = np.random.default_rng(78)
+    pool = corpus.text_pool()
+    d = pool[600000:650000]
+    data = pool[610000:610000 + 700000]
+    comp = corpus.compress_with_dictionary(data, d, 2)
+    assert oracle.decode(comp, len(data), True, d)[1:] == (1, data)
+    for _ in range(3):
+        sess = helpers.HostSimSession(hostsim, len(data) + 9, custom_dict=d)
+        cuts = sorted(set(int(x) for x in rng.integers(1, len(comp), size=9)) | {len(comp)})
+        for c in cuts:
+            code, out = sess.decode(comp[:c])
+            _, ocode, oout = oracle.decode(comp[:c], len(data) + 9, True, d)
+            assert (code, out) == (ocode, oout), c
+        assert code == 1 and out == data and sess.resumed_at()[0] == 1
