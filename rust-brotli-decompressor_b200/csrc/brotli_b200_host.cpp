@@ -463,6 +463,7 @@ struct BrotliDecoderStateStruct {
   // custom LZ77 dictionary of this state (BrotliState::new_with_custom_dictionary, src/state.rs:400-411)
   std::vector<uint8_t> dict;
   uint8_t* d_dict;   // device copy, 32 bytes of slack on either side
+  int session_device;  // CUDA device that owns the session buffers (-1: none yet)
 };
 
 constexpr size_t kSessionMetaBytes = 512, kSessionResumeAt = 128;
@@ -529,7 +530,7 @@ BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, br
   s->taken = 0; s->consumed_reported = 0; s->last_code = 0;
   s->used = false; s->large_window = false; s->failed = false; s->finished = false;
   s->error[0] = 0;
-  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr; s->d_dict = nullptr;
+  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr; s->d_dict = nullptr; s->session_device = -1;
   return s;
 }
 
@@ -600,6 +601,9 @@ BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t*
       // continues behind the last complete metablock
       DeviceCtx* c = acquire_ctx();
       if (!c) return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str());
+      if (s->session_device < 0) s->session_device = c->device;
+      if (s->session_device != c->device)  // the session's buffers live on the device of its first call
+        return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, "brotli_b200: decoder state used from another CUDA device");
       if (cap < s->d_out_cap && s->d_out_cap > 16) cap = s->d_out_cap - 16;
       size_t n_fresh = fresh;
       const uint8_t* fresh_ptr = s->input.data() + (s->input.size() - fresh);
