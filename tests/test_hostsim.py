@@ -90,3 +90,30 @@ def test_generated_and_mutated(oracle, hostsim, corpus, q):
                 n_fail += 1
             same(oracle, hostsim, m, max(len(orig) - 7, 0), roomy=False)
     assert n_fail > 10
+
+
+def test_differential_fuzz_both_cores(oracle, hostsim, corpus):
+    """Host builds of BOTH kernels' logic against the oracle on a few thousand seeded mutations of streams of every
+    family and quality: the exact core must reproduce code and decoded bytes (up to the documented corrupt-and-too-small
+    deviation, see `same`), the lane core must either decode exactly what the oracle decodes or give the stream up."""
+    n = lane_ok = tolerated = 0
+    for seed in range(2):
+        rng = np.random.default_rng(7000 + seed)
+        for cfg, cnt, size in (("C5", 22, int(rng.integers(3000, 30000))), ("C3", 16, 4096), ("headline", 3, 65536)):
+            comp, orig, _ = corpus.make_config(cfg, cnt, size=size, seed=900 + seed)
+            for c, o in zip(comp, orig):
+                for m in [c] + helpers.mutations(c, rng, 20):
+                    cap = len(o) + int(rng.integers(0, 40)) if rng.random() < 0.8 else int(rng.integers(0, len(o) + 1))
+                    _, ocode, oout = oracle.decode(m, cap)
+                    hcode, hout = hostsim.decode(m, cap)
+                    n += 1
+                    if (hcode, hout) != (ocode, oout):
+                        assert hcode == 3 and ocode not in (1, 3), (cfg, len(m), cap, hcode, ocode)
+                        tolerated += 1
+                    lcode, lout, _ = hostsim.lane_decode(m, cap, int(rng.choice([146, 178, 230])), int(rng.integers(0, 4)))
+                    if lcode == 1:
+                        assert ocode == 1 and lout == oout, (cfg, len(m), cap)
+                        lane_ok += 1
+                    else:
+                        assert lcode == hostsim.LANE_BAIL
+    assert n > 1500 and lane_ok > 200 and tolerated < n // 5, (n, lane_ok, tolerated)
