@@ -321,8 +321,19 @@ BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint3
 BD_COLD void store_head_bytes(uint8_t* out_al, uint32_t bias, uint32_t wpos, uint32_t word) {
   for (uint32_t j = 0; j < 4; j++) if (wpos + j >= bias) out_al[wpos + j] = (uint8_t)(word >> (8 * j));
 }
+// Experiment prepared for the next round, OFF (the default build is instruction-for-instruction what was measured):
+// BD_LANE_HEAD_PER_ROUND=1 takes the unaligned-head test out of every output store.  The stores skip the region's
+// first word when the region starts inside it, and the command loop writes that word's bytes (from the history ring)
+// right after the phase that completed it -- LN_HEAD_CHECK, three places per round instead of every store site.
+#ifndef BD_LANE_HEAD_PER_ROUND
+#define BD_LANE_HEAD_PER_ROUND 0
+#endif
 BD_DEV void store_word_if(bool cond, uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
   sts32_if(cond, hist + (wpos & 28u), word);
+#if BD_LANE_HEAD_PER_ROUND
+  st32_if(cond && wpos >= bias, out_al + wpos, word);
+  return;
+#endif
   if (BD_UNLIKELY(cond && wpos < bias)) {
     store_head_bytes(out_al, bias, wpos, word);
   } else {
@@ -970,6 +981,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #endif
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
+#if BD_LANE_HEAD_PER_ROUND
+// the region's first word was completed since position P0 (fewer than 32 bytes ago: it is still in the history ring)
+#define LN_HEAD_CHECK(P0) do { if (BD_UNLIKELY(bias != 0 && (P0) < 4 && posb >= 4)) store_head_bytes(out_al, bias, 0, vlds32(hist)); } while (0)
+#else
+#define LN_HEAD_CHECK(P0) ((void)0)
+#endif
 // Bits consumed; on a word boundary the window takes word k + 2 from the ring.  When that word starts a new
 // 16-byte block, the block after it is requested with cp.async -- not committed here: the round's convergent
 // commit covers it, and the convergent wait at the start of the next round completes it long before its words
@@ -1091,6 +1108,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
     bool blk_seen = false;       // this lane has requested an input block in this round (see LN_SKIP)
+#if BD_LANE_HEAD_PER_ROUND
+    const uint32_t posb0 = posb;
+#endif
     uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
     // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
     cp_async_wait_all_but_latest();
@@ -1209,6 +1229,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     if (kCmdLiterals != 0 && run) {  // literals decoded in their command's round (phase A); nothing happens for lit_n == 0
       append(out_al, bias, hist, posb, acc, lit_pack, lit_n);
     }
+#if BD_LANE_HEAD_PER_ROUND
+    if (run) LN_HEAD_CHECK(posb0);  // phases A and P append at most 19 bytes
+#endif
     // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
     if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
     warp_sync();
@@ -1361,6 +1384,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         else ph = kPhCopy;
       }
     }
+#if BD_LANE_HEAD_PER_ROUND
+    if (go) LN_HEAD_CHECK(posb0);  // the short-distance path (distance <= position < 4: at most 21 bytes)
+#endif
     warp_sync();
     LN_ISSUE_CHUNK(run && crem != 0 && ev != kStBail);
     cp_async_commit();  // group: the copy chunk
@@ -1375,7 +1401,13 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     // the metablock's last copy may still be in flight
     while (pend_n != 0) {
       cp_async_wait_all();
+#if BD_LANE_HEAD_PER_ROUND
+      const uint32_t posb1 = posb;
+#endif
       LN_RETIRE_CHUNK();
+#if BD_LANE_HEAD_PER_ROUND
+      LN_HEAD_CHECK(posb1);
+#endif
       LN_ISSUE_CHUNK(crem != 0);
       cp_async_commit();
     }
@@ -1383,6 +1415,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
   if (ran) LN_SAVE();
 #undef LN_PEEK
+#undef LN_HEAD_CHECK
 #undef LN_CP16_IF_KEEP
 #undef LN_CP16_IF_STREAM
 #undef LN_CP16_IF_SRC
