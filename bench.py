@@ -127,7 +127,7 @@ def run_reference(args, rank, world):
     """CPU port of the reference decode path (oracle/), all host threads, bounded sample per step."""
     if rank != 0:
         return
-    corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+    corpus = importlib.import_module("tools.corpus")
     oracle = load_oracle()
     threads = os.cpu_count() or 1
     n_unique = min(args.unique, 1024)
@@ -227,7 +227,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module("rust-brotli-decompressor_b200")
-    corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+    corpus = importlib.import_module("tools.corpus")
     pkg.lib()
 
     # ---- workload ----

@@ -349,7 +349,7 @@ enum RunningState { /* src/state.rs:68-94 */
   ST_UNINITED, ST_LARGE_WINDOW_BITS, ST_INITIALIZE, ST_METABLOCK_BEGIN, ST_METABLOCK_HEADER, ST_METABLOCK_HEADER_2,
   ST_CONTEXT_MODES, ST_COMMAND_BEGIN, ST_COMMAND_INNER, ST_COMMAND_POST_DECODE_LITERALS, ST_COMMAND_POST_WRAP_COPY,
   ST_UNCOMPRESSED, ST_METADATA, ST_COMMAND_INNER_WRITE, ST_METABLOCK_DONE, ST_COMMAND_POST_WRITE_1,
-  ST_COMMAND_POST_WRITE_2, ST_HUFFMAN_CODE_0, ST_CONTEXT_MAP_1, ST_CONTEXT_MAP_2, ST_TREE_GROUP, ST_DONE
+  ST_COMMAND_POST_WRITE_2, ST_HUFFMAN_CODE_0, ST_HUFFMAN_CODE_1, ST_HUFFMAN_CODE_2, ST_HUFFMAN_CODE_3, ST_CONTEXT_MAP_1, ST_CONTEXT_MAP_2, ST_TREE_GROUP, ST_DONE
 };
 
 typedef struct HGroup { /* HuffmanTreeGroup, src/huffman/mod.rs:51-72 */
@@ -390,6 +390,13 @@ typedef struct State {
   uint32_t window_bits; int large_window, canny_ringbuffer_allocation, should_wrap_ringbuffer;
   uint32_t num_literal_htrees; uint8_t *context_map, *context_modes;
   uint32_t trivial_literal_contexts[8];
+  /* sub-states that let every header function resume where NeedsMoreInput interrupted it, src/state.rs:96-154,160-178 */
+  int substate_decode_uint8, substate_metablock_header, substate_huffman, substate_tree_group, substate_context_map,
+      substate_read_block_length;
+  uint32_t sub_loop_counter, htree_index, htree_next_offset, context_index, max_run_length_prefix, code, block_length_index;
+  /* carry-over of an interrupted read across calls, src/state.rs:169-170 */
+  uint8_t buffer[8]; uint32_t buffer_length;
+  int error_code;
 } State;
 #define SYMBOL_LISTS_INDEX (HUFFMAN_MAX_CODE_LENGTH + 1) /* src/state.rs:352 */
 
@@ -447,54 +454,91 @@ static int DecodeWindowBits(int* s_large_window, uint32_t* window_bits, BR* br) 
   if (n != 0) { *window_bits = 8 + n; return E_SUCCESS; }
   *window_bits = 17; return E_SUCCESS;
 }
-/* DecodeVarLenUint8, :193-241 */
+/* DecodeVarLenUint8, :193-241 (sub-states BROTLI_STATE_DECODE_UINT8_{NONE,SHORT,LONG}) */
 static int DecodeVarLenUint8(State* s, uint32_t* value) {
   uint32_t bits;
-  if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  if (bits == 0) { *value = 0; return E_SUCCESS; }
-  if (!SafeReadBits(&s->br, 3, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  if (bits == 0) { *value = 1; return E_SUCCESS; }
-  *value = bits;
-  if (!SafeReadBits(&s->br, *value, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  *value = (1u << *value) + bits;
-  return E_SUCCESS;
+  for (;;) {
+    switch (s->substate_decode_uint8) {
+      case 0:
+        if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+        if (bits == 0) { *value = 0; return E_SUCCESS; }
+        s->substate_decode_uint8 = 1;
+        /* fall through */
+      case 1:
+        if (!SafeReadBits(&s->br, 3, &bits, s->input)) { s->substate_decode_uint8 = 1; return E_NEEDS_MORE_INPUT; }
+        if (bits == 0) { *value = 1; s->substate_decode_uint8 = 0; return E_SUCCESS; }
+        *value = bits; /* the output value is the temporary storage and persists across calls */
+        s->substate_decode_uint8 = 2;
+        /* fall through */
+      default:
+        if (!SafeReadBits(&s->br, *value, &bits, s->input)) { s->substate_decode_uint8 = 2; return E_NEEDS_MORE_INPUT; }
+        *value = (1u << *value) + bits;
+        s->substate_decode_uint8 = 0;
+        return E_SUCCESS;
+    }
+  }
 }
-/* DecodeMetaBlockLength, :243-372 */
+/* DecodeMetaBlockLength, :243-372 (sub-states BROTLI_STATE_METABLOCK_HEADER_*) */
+enum { MH_NONE, MH_EMPTY, MH_NIBBLES, MH_SIZE, MH_UNCOMPRESSED, MH_RESERVED, MH_BYTES, MH_METADATA };
 static int DecodeMetaBlockLength(State* s) {
   uint32_t bits; int i;
-  if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  s->is_last_metablock = (uint8_t)bits; s->meta_block_remaining_len = 0; s->is_uncompressed = 0; s->is_metadata = 0;
-  if (s->is_last_metablock) {
-    if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* ISLASTEMPTY */
-    if (bits) return E_SUCCESS;
-  }
-  if (!SafeReadBits(&s->br, 2, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* MNIBBLES */
-  s->size_nibbles = (uint8_t)(bits + 4);
-  if (bits == 3) {
-    s->is_metadata = 1;
-    if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-    if (bits != 0) return E_RESERVED;
-    if (!SafeReadBits(&s->br, 2, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* MSKIPBYTES */
-    if (bits == 0) return E_SUCCESS;
-    s->size_nibbles = (uint8_t)bits;
-    for (i = 0; i < s->size_nibbles; i++) {
-      if (!SafeReadBits(&s->br, 8, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-      if (i + 1 == s->size_nibbles && s->size_nibbles > 1 && bits == 0) return E_EXUBERANT_META_NIBBLE;
-      s->meta_block_remaining_len |= (int)(bits << (i * 8));
+  for (;;) {
+    switch (s->substate_metablock_header) {
+      case MH_NONE:
+        if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+        s->is_last_metablock = (uint8_t)bits; s->meta_block_remaining_len = 0; s->is_uncompressed = 0; s->is_metadata = 0;
+        if (!s->is_last_metablock) { s->substate_metablock_header = MH_NIBBLES; continue; }
+        s->substate_metablock_header = MH_EMPTY;
+        /* fall through */
+      case MH_EMPTY:
+        if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* ISLASTEMPTY */
+        if (bits) { s->substate_metablock_header = MH_NONE; return E_SUCCESS; }
+        s->substate_metablock_header = MH_NIBBLES;
+        /* fall through */
+      case MH_NIBBLES:
+        if (!SafeReadBits(&s->br, 2, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* MNIBBLES */
+        s->size_nibbles = (uint8_t)(bits + 4);
+        s->loop_counter = 0;
+        if (bits == 3) { s->is_metadata = 1; s->substate_metablock_header = MH_RESERVED; continue; }
+        s->substate_metablock_header = MH_SIZE;
+        /* fall through */
+      case MH_SIZE:
+        for (i = s->loop_counter; i < s->size_nibbles; i++) {
+          if (!SafeReadBits(&s->br, 4, &bits, s->input)) { s->loop_counter = i; return E_NEEDS_MORE_INPUT; }
+          if (i + 1 == s->size_nibbles && s->size_nibbles > 4 && bits == 0) return E_EXUBERANT_NIBBLE;
+          s->meta_block_remaining_len |= (int)(bits << (i * 4));
+        }
+        s->substate_metablock_header = MH_UNCOMPRESSED;
+        /* fall through */
+      case MH_UNCOMPRESSED:
+        if (!s->is_last_metablock && !s->is_metadata) {
+          if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+          s->is_uncompressed = (uint8_t)bits;
+        }
+        s->meta_block_remaining_len += 1;
+        s->substate_metablock_header = MH_NONE;
+        return E_SUCCESS;
+      case MH_RESERVED:
+        if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+        if (bits != 0) return E_RESERVED;
+        s->substate_metablock_header = MH_BYTES;
+        /* fall through */
+      case MH_BYTES:
+        if (!SafeReadBits(&s->br, 2, &bits, s->input)) return E_NEEDS_MORE_INPUT; /* MSKIPBYTES */
+        if (bits == 0) { s->substate_metablock_header = MH_NONE; return E_SUCCESS; }
+        s->size_nibbles = (uint8_t)bits;
+        s->substate_metablock_header = MH_METADATA;
+        /* fall through */
+      default: /* MH_METADATA */
+        for (i = s->loop_counter; i < s->size_nibbles; i++) {
+          if (!SafeReadBits(&s->br, 8, &bits, s->input)) { s->loop_counter = i; return E_NEEDS_MORE_INPUT; }
+          if (i + 1 == s->size_nibbles && s->size_nibbles > 1 && bits == 0) return E_EXUBERANT_META_NIBBLE;
+          s->meta_block_remaining_len |= (int)(bits << (i * 8));
+        }
+        s->substate_metablock_header = MH_UNCOMPRESSED;
+        continue;
     }
-  } else {
-    for (i = 0; i < s->size_nibbles; i++) {
-      if (!SafeReadBits(&s->br, 4, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-      if (i + 1 == s->size_nibbles && s->size_nibbles > 4 && bits == 0) return E_EXUBERANT_NIBBLE;
-      s->meta_block_remaining_len |= (int)(bits << (i * 4));
-    }
   }
-  if (!s->is_last_metablock && !s->is_metadata) {
-    if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-    s->is_uncompressed = (uint8_t)bits;
-  }
-  s->meta_block_remaining_len += 1;
-  return E_SUCCESS;
 }
 /* DecodeSymbol :377-391, ReadSymbol :395-398 */
 static inline uint32_t DecodeSymbol(uint32_t bits, const HC* table, BR* br) {
@@ -541,12 +585,13 @@ static int SafeReadSymbol(const HC* table, BR* br, uint32_t* result, const uint8
 }
 static uint32_t Log2Floor(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++; } return r; } /* :502-509 */
 
-/* ReadSimpleHuffmanSymbols, :516-556 */
+/* ReadSimpleHuffmanSymbols, :516-556 (resumes at sub_loop_counter) */
+enum { HS_NONE, HS_SIMPLE_SIZE, HS_SIMPLE_READ, HS_SIMPLE_BUILD, HS_COMPLEX, HS_LENGTH_SYMBOLS };
 static int ReadSimpleHuffmanSymbols(uint32_t alphabet_size, uint32_t max_symbol, State* s) {
   uint32_t max_bits = Log2Floor(alphabet_size - 1), i, k, num_symbols = s->symbol;
-  for (i = 0; i <= num_symbols; i++) {
+  for (i = s->sub_loop_counter; i <= num_symbols; i++) {
     uint32_t v;
-    if (!SafeReadBits(&s->br, max_bits, &v, s->input)) return E_NEEDS_MORE_INPUT;
+    if (!SafeReadBits(&s->br, max_bits, &v, s->input)) { s->sub_loop_counter = i; s->substate_huffman = HS_SIMPLE_READ; return E_NEEDS_MORE_INPUT; }
     if (v >= max_symbol) return E_SIMPLE_HUFFMAN_ALPHABET;
     s->symbols_lists_array[i] = (uint16_t)v;
   }
@@ -644,16 +689,19 @@ static int SafeReadSymbolCodeLengths(uint32_t alphabet_size, State* s) {
   }
   return E_SUCCESS;
 }
-/* ReadCodeLengthCodeLengths, :801-853.  sub_loop_counter holds HSKIP on entry. */
-static int ReadCodeLengthCodeLengths(State* s, uint32_t hskip) {
+/* ReadCodeLengthCodeLengths, :801-853.  sub_loop_counter holds HSKIP on entry and the resume index afterwards. */
+static int ReadCodeLengthCodeLengths(State* s) {
   uint32_t num_codes = s->repeat, space = s->space, i;
-  for (i = hskip; i < CODE_LENGTH_CODES; i++) {
+  for (i = s->sub_loop_counter; i < CODE_LENGTH_CODES; i++) {
     uint8_t code_len_idx = kCodeLengthCodeOrder[i];
     uint32_t ix = 0, v;
     if (!SafeGetBits(&s->br, 4, &ix, s->input)) {
       uint32_t available_bits = GetAvailableBits(&s->br);
       ix = available_bits != 0 ? ((uint32_t)GetBitsUnmasked(&s->br) & 0xF) : 0;
-      if (kCodeLengthPrefixLength[ix] > available_bits) return E_NEEDS_MORE_INPUT;
+      if (kCodeLengthPrefixLength[ix] > available_bits) {
+        s->sub_loop_counter = i; s->repeat = num_codes; s->space = space; s->substate_huffman = HS_COMPLEX;
+        return E_NEEDS_MORE_INPUT;
+      }
     }
     v = kCodeLengthPrefixValue[ix];
     DropBits(&s->br, kCodeLengthPrefixLength[ix]);
@@ -666,56 +714,82 @@ static int ReadCodeLengthCodeLengths(State* s, uint32_t hskip) {
   if (!(num_codes == 1 || space == 0)) return E_CL_SPACE;
   return E_SUCCESS;
 }
-/* ReadHuffmanCode, :868-1013 */
+/* ReadHuffmanCode, :868-1013 (sub-states BROTLI_STATE_HUFFMAN_*) */
 static int ReadHuffmanCode(uint32_t alphabet_size, uint32_t max_symbol, HC* table, uint32_t* opt_table_size, State* s) {
-  uint32_t hskip, table_size; int r, i;
+  uint32_t table_size; int r, i;
   alphabet_size &= 0x7ff;
-  if (!SafeReadBits(&s->br, 2, &hskip, s->input)) return E_NEEDS_MORE_INPUT;
-  if (hskip == 1) { /* simple code */
-    if (!SafeReadBits(&s->br, 2, &s->symbol, s->input)) return E_NEEDS_MORE_INPUT; /* NSYM-1 */
-    r = ReadSimpleHuffmanSymbols(alphabet_size, max_symbol, s);
-    if (r != E_SUCCESS) return r;
-    if (s->symbol == 3) {
-      uint32_t bits;
-      if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-      s->symbol += bits;
+  for (;;) {
+    switch (s->substate_huffman) {
+      case HS_NONE:
+        if (!SafeReadBits(&s->br, 2, &s->sub_loop_counter, s->input)) return E_NEEDS_MORE_INPUT;
+        if (s->sub_loop_counter != 1) { /* 0: no skipping, 2 / 3: skip that many code lengths */
+          s->space = 32; s->repeat = 0;
+          memset(s->code_length_histo, 0, sizeof(uint16_t) * (HUFFMAN_MAX_CODE_LENGTH_CODE_LENGTH + 1));
+          memset(s->code_length_code_lengths, 0, sizeof(s->code_length_code_lengths));
+          s->substate_huffman = HS_COMPLEX;
+          continue;
+        }
+        s->substate_huffman = HS_SIMPLE_SIZE;
+        /* fall through */
+      case HS_SIMPLE_SIZE:
+        if (!SafeReadBits(&s->br, 2, &s->symbol, s->input)) { s->substate_huffman = HS_SIMPLE_SIZE; return E_NEEDS_MORE_INPUT; } /* NSYM-1 */
+        s->sub_loop_counter = 0;
+        s->substate_huffman = HS_SIMPLE_READ;
+        /* fall through */
+      case HS_SIMPLE_READ:
+        r = ReadSimpleHuffmanSymbols(alphabet_size, max_symbol, s);
+        if (r != E_SUCCESS) return r;
+        s->substate_huffman = HS_SIMPLE_BUILD;
+        /* fall through */
+      case HS_SIMPLE_BUILD:
+        if (s->symbol == 3) {
+          uint32_t bits;
+          if (!SafeReadBits(&s->br, 1, &bits, s->input)) { s->substate_huffman = HS_SIMPLE_BUILD; return E_NEEDS_MORE_INPUT; }
+          s->symbol += bits;
+        }
+        table_size = oracle_build_simple_huffman_table(table, HUFFMAN_TABLE_BITS, s->symbols_lists_array,
+                                                       sizeof(s->symbols_lists_array) / sizeof(uint16_t), s->symbol);
+        if (opt_table_size) *opt_table_size = table_size;
+        s->substate_huffman = HS_NONE;
+        return E_SUCCESS;
+      case HS_COMPLEX:
+        r = ReadCodeLengthCodeLengths(s);
+        if (r != E_SUCCESS) return r;
+        oracle_build_code_lengths_huffman_table(s->table, s->code_length_code_lengths, s->code_length_histo);
+        memset(s->code_length_histo, 0, sizeof(s->code_length_histo));
+        for (i = 0; i <= HUFFMAN_MAX_CODE_LENGTH; i++) {
+          s->next_symbol[i] = i - (HUFFMAN_MAX_CODE_LENGTH + 1);
+          s->symbols_lists_array[SYMBOL_LISTS_INDEX + i - (HUFFMAN_MAX_CODE_LENGTH + 1)] = 0xFFFF;
+        }
+        s->symbol = 0; s->prev_code_len = kDefaultCodeLength; s->repeat = 0; s->repeat_code_len = 0; s->space = 32768;
+        s->substate_huffman = HS_LENGTH_SYMBOLS;
+        /* fall through */
+      default: /* HS_LENGTH_SYMBOLS */
+        r = ReadSymbolCodeLengths(max_symbol, s);
+        if (r == E_NEEDS_MORE_INPUT) r = SafeReadSymbolCodeLengths(max_symbol, s);
+        if (r != E_SUCCESS) return r;
+        if (s->space != 0) return E_HUFFMAN_SPACE;
+        table_size = oracle_build_huffman_table(table, HUFFMAN_TABLE_BITS, s->symbols_lists_array, SYMBOL_LISTS_INDEX, s->code_length_histo);
+        if (opt_table_size) *opt_table_size = table_size;
+        s->substate_huffman = HS_NONE;
+        return E_SUCCESS;
     }
-    table_size = oracle_build_simple_huffman_table(table, HUFFMAN_TABLE_BITS, s->symbols_lists_array,
-                                                   sizeof(s->symbols_lists_array) / sizeof(uint16_t), s->symbol);
-    if (opt_table_size) *opt_table_size = table_size;
-    return E_SUCCESS;
   }
-  s->space = 32; s->repeat = 0;
-  memset(s->code_length_histo, 0, sizeof(uint16_t) * (HUFFMAN_MAX_CODE_LENGTH_CODE_LENGTH + 1));
-  memset(s->code_length_code_lengths, 0, sizeof(s->code_length_code_lengths));
-  r = ReadCodeLengthCodeLengths(s, hskip);
-  if (r != E_SUCCESS) return r;
-  oracle_build_code_lengths_huffman_table(s->table, s->code_length_code_lengths, s->code_length_histo);
-  memset(s->code_length_histo, 0, sizeof(s->code_length_histo));
-  for (i = 0; i <= HUFFMAN_MAX_CODE_LENGTH; i++) {
-    s->next_symbol[i] = i - (HUFFMAN_MAX_CODE_LENGTH + 1);
-    s->symbols_lists_array[SYMBOL_LISTS_INDEX + i - (HUFFMAN_MAX_CODE_LENGTH + 1)] = 0xFFFF;
-  }
-  s->symbol = 0; s->prev_code_len = kDefaultCodeLength; s->repeat = 0; s->repeat_code_len = 0; s->space = 32768;
-  r = ReadSymbolCodeLengths(max_symbol, s);
-  if (r == E_NEEDS_MORE_INPUT) r = SafeReadSymbolCodeLengths(max_symbol, s);
-  if (r != E_SUCCESS) return r;
-  if (s->space != 0) return E_HUFFMAN_SPACE;
-  table_size = oracle_build_huffman_table(table, HUFFMAN_TABLE_BITS, s->symbols_lists_array, SYMBOL_LISTS_INDEX, s->code_length_histo);
-  if (opt_table_size) *opt_table_size = table_size;
-  return E_SUCCESS;
 }
 /* ReadBlockLength :1016-1026 */
 static inline uint32_t ReadBlockLength(const HC* table, BR* br, const uint8_t* in) {
   uint32_t code = ReadSymbol(table, br, in);
   return kBrotliBlockLengthOffset[code] + ReadBits(br, kBrotliBlockLengthNBits[code], in);
 }
-/* SafeReadBlockLength{Index,FromIndex} :1031-1070 (no suffix sub-state: one-shot never resumes) */
-static int SafeReadBlockLength(uint32_t* result, const HC* table, BR* br, const uint8_t* in) {
+/* SafeReadBlockLength{Index,FromIndex} :1031-1070: the index survives a failed read of the extra bits
+ * (BROTLI_STATE_READ_BLOCK_LENGTH_SUFFIX) */
+static int SafeReadBlockLength(State* s, uint32_t* result, const HC* table, BR* br, const uint8_t* in) {
   uint32_t index, bits;
-  if (!SafeReadSymbol(table, br, &index, in)) return 0;
-  if (!SafeReadBits(br, kBrotliBlockLengthNBits[index], &bits, in)) return 0;
+  if (s->substate_read_block_length == 0) { if (!SafeReadSymbol(table, br, &index, in)) return 0; }
+  else index = s->block_length_index;
+  if (!SafeReadBits(br, kBrotliBlockLengthNBits[index], &bits, in)) { s->block_length_index = index; s->substate_read_block_length = 1; return 0; }
   *result = kBrotliBlockLengthOffset[index] + bits;
+  s->substate_read_block_length = 0;
   return 1;
 }
 /* InverseMoveToFrontTransform :1096-1128 */
@@ -733,48 +807,77 @@ static void InverseMoveToFrontTransform(uint8_t* v, uint32_t v_len, uint8_t* mtf
   }
   *mtf_upper_bound = upper_bound;
 }
-/* HuffmanTreeGroupDecode :1130-1219 */
+/* HuffmanTreeGroupDecode :1130-1219 (resumes at htree_index / htree_next_offset) */
 static int HuffmanTreeGroupDecode(HGroup* g, State* s) {
-  uint32_t next_offset = 0, i;
-  for (i = 0; i < g->num_htrees; i++) {
+  if (s->substate_tree_group == 0) { s->htree_next_offset = 0; s->htree_index = 0; s->substate_tree_group = 1; }
+  while (s->htree_index < g->num_htrees) {
     uint32_t table_size = 0;
-    int r = ReadHuffmanCode(g->alphabet_size, g->max_symbol, g->codes + next_offset, &table_size, s);
+    int r = ReadHuffmanCode(g->alphabet_size, g->max_symbol, g->codes + s->htree_next_offset, &table_size, s);
     if (r != E_SUCCESS) return r;
-    g->htrees[i] = next_offset;
-    next_offset += table_size;
+    g->htrees[s->htree_index] = s->htree_next_offset;
+    s->htree_next_offset += table_size;
+    s->htree_index++;
   }
+  s->substate_tree_group = 0;
   return E_SUCCESS;
 }
-/* DecodeContextMap(Inner) :1272-1465 */
+/* DecodeContextMap(Inner) :1272-1465 (sub-states BROTLI_STATE_CONTEXT_MAP_*) */
+enum { CM_NONE, CM_READ_PREFIX, CM_HUFFMAN, CM_DECODE, CM_TRANSFORM };
 static int DecodeContextMap(uint32_t context_map_size, uint32_t* num_htrees, uint8_t** context_map_arg, State* s) {
-  uint32_t context_index = 0, max_run_length_prefix, bits, alphabet_size;
-  uint8_t* context_map; int r;
-  r = DecodeVarLenUint8(s, num_htrees);
-  if (r != E_SUCCESS) return r;
-  (*num_htrees)++;
-  free(*context_map_arg);
-  *context_map_arg = context_map = (uint8_t*)calloc(context_map_size ? context_map_size : 1, 1);
-  if (!context_map) return E_ALLOC_CONTEXT_MAP;
-  if (*num_htrees <= 1) return E_SUCCESS;
-  if (!SafeGetBits(&s->br, 5, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  if (bits & 1) { max_run_length_prefix = (bits >> 1) + 1; DropBits(&s->br, 5); }
-  else { max_run_length_prefix = 0; DropBits(&s->br, 1); }
-  alphabet_size = *num_htrees + max_run_length_prefix;
-  r = ReadHuffmanCode(alphabet_size, alphabet_size, s->context_map_table, NULL, s);
-  if (r != E_SUCCESS) return r;
-  while (context_index < context_map_size) {
-    uint32_t code, reps;
-    if (!SafeReadSymbol(s->context_map_table, &s->br, &code, s->input)) return E_NEEDS_MORE_INPUT;
-    if (code == 0) { context_map[context_index++] = 0; continue; }
-    if (code > max_run_length_prefix) { context_map[context_index++] = (uint8_t)(code - max_run_length_prefix); continue; }
-    if (!SafeReadBits(&s->br, code, &reps, s->input)) return E_NEEDS_MORE_INPUT;
-    reps += 1u << code;
-    if (context_index + reps > context_map_size) return E_CONTEXT_MAP_REPEAT;
-    do { context_map[context_index++] = 0; } while (--reps);
+  uint32_t bits, alphabet_size; int r;
+  for (;;) {
+    switch (s->substate_context_map) {
+      case CM_NONE:
+        r = DecodeVarLenUint8(s, num_htrees);
+        if (r != E_SUCCESS) return r;
+        (*num_htrees)++;
+        s->context_index = 0;
+        free(*context_map_arg);
+        *context_map_arg = (uint8_t*)calloc(context_map_size ? context_map_size : 1, 1);
+        if (!*context_map_arg) return E_ALLOC_CONTEXT_MAP;
+        if (*num_htrees <= 1) return E_SUCCESS;
+        s->substate_context_map = CM_READ_PREFIX;
+        /* fall through */
+      case CM_READ_PREFIX:
+        if (!SafeGetBits(&s->br, 5, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+        if (bits & 1) { s->max_run_length_prefix = (bits >> 1) + 1; DropBits(&s->br, 5); }
+        else { s->max_run_length_prefix = 0; DropBits(&s->br, 1); }
+        s->substate_context_map = CM_HUFFMAN;
+        /* fall through */
+      case CM_HUFFMAN:
+        alphabet_size = *num_htrees + s->max_run_length_prefix;
+        r = ReadHuffmanCode(alphabet_size, alphabet_size, s->context_map_table, NULL, s);
+        if (r != E_SUCCESS) return r;
+        s->code = 0xFFFF;
+        s->substate_context_map = CM_DECODE;
+        /* fall through */
+      case CM_DECODE: {
+        uint32_t context_index = s->context_index, max_run_length_prefix = s->max_run_length_prefix, code = s->code;
+        uint8_t* context_map = *context_map_arg;
+        int rle_code_goto = code != 0xFFFF; /* an RLE code whose extra bits were cut off by the end of the input */
+        while (rle_code_goto || context_index < context_map_size) {
+          uint32_t reps;
+          if (!rle_code_goto) {
+            if (!SafeReadSymbol(s->context_map_table, &s->br, &code, s->input)) { s->code = 0xFFFF; s->context_index = context_index; return E_NEEDS_MORE_INPUT; }
+            if (code == 0) { context_map[context_index++] = 0; continue; }
+            if (code > max_run_length_prefix) { context_map[context_index++] = (uint8_t)(code - max_run_length_prefix); continue; }
+          }
+          rle_code_goto = 0;
+          if (!SafeReadBits(&s->br, code, &reps, s->input)) { s->code = code; s->context_index = context_index; return E_NEEDS_MORE_INPUT; }
+          reps += 1u << code;
+          if (context_index + reps > context_map_size) return E_CONTEXT_MAP_REPEAT;
+          do { context_map[context_index++] = 0; } while (--reps);
+        }
+        s->substate_context_map = CM_TRANSFORM;
+      }
+        /* fall through */
+      default: /* CM_TRANSFORM */
+        if (!SafeReadBits(&s->br, 1, &bits, s->input)) { s->substate_context_map = CM_TRANSFORM; return E_NEEDS_MORE_INPUT; }
+        if (bits) InverseMoveToFrontTransform(*context_map_arg, context_map_size, s->mtf, &s->mtf_upper_bound);
+        s->substate_context_map = CM_NONE;
+        return E_SUCCESS;
+    }
   }
-  if (!SafeReadBits(&s->br, 1, &bits, s->input)) return E_NEEDS_MORE_INPUT;
-  if (bits) InverseMoveToFrontTransform(context_map, context_map_size, s->mtf, &s->mtf_upper_bound);
-  return E_SUCCESS;
 }
 /* DecodeBlockTypeAndLength :1469-1524 */
 static int DecodeBlockTypeAndLength(int safe, State* s, int tree_type) {
@@ -790,7 +893,7 @@ static int DecodeBlockTypeAndLength(int safe, State* s, int tree_type) {
     BRState memento = BRSave(&s->br);
     uint32_t block_length_out = 0;
     if (!SafeReadSymbol(type_tree, &s->br, &block_type, s->input)) return 0;
-    if (!SafeReadBlockLength(&block_length_out, len_tree, &s->br, s->input)) { BRRestore(&s->br, &memento); return 0; }
+    if (!SafeReadBlockLength(s, &block_length_out, len_tree, &s->br, s->input)) { s->substate_read_block_length = 0; BRRestore(&s->br, &memento); return 0; }
     s->block_length[tree_type] = block_length_out;
   }
   if (block_type == 1) block_type = rb[1] + 1;
@@ -903,11 +1006,11 @@ static int AllocateRingBuffer(State* s) {
   if (s->custom_dict_size) memcpy(s->ringbuffer + ((size_t)(-s->custom_dict_size) & (size_t)s->ringbuffer_mask), custom_dict, (size_t)s->custom_dict_size);
   return 1;
 }
-/* ReadContextModes :1991-2015 */
+/* ReadContextModes :1991-2015 (resumes at loop_counter) */
 static int ReadContextModes(State* s) {
   uint32_t i, bits;
-  for (i = 0; i < s->num_block_types[0]; i++) {
-    if (!SafeReadBits(&s->br, 2, &bits, s->input)) return E_NEEDS_MORE_INPUT;
+  for (i = (uint32_t)s->loop_counter; i < s->num_block_types[0]; i++) {
+    if (!SafeReadBits(&s->br, 2, &bits, s->input)) { s->loop_counter = (int)i; return E_NEEDS_MORE_INPUT; }
     s->context_modes[i] = (uint8_t)bits;
   }
   return E_SUCCESS;
@@ -1139,16 +1242,72 @@ static uint32_t MaxDistanceSymbol(uint32_t ndirect, uint32_t npostfix) {
   return bound[npostfix] + diff[npostfix] + postfix;
 }
 
-/* BrotliDecompressStream :2779-3403, specialised to one call with all input (buffer_length == 0). */
-static int DecompressStream(State* s, size_t available_in) {
+/* BrotliBitReaderUnload, src/bit_reader/mod.rs:295-306 */
+static void BitReaderUnload(BR* br) {
+  uint32_t unused_bytes = GetAvailableBits(br) >> 3, unused_bits = unused_bytes << 3;
+  br->avail_in += unused_bytes; br->next_in -= unused_bytes;
+  if (unused_bits == 64) br->val_ = 0; else br->val_ <<= unused_bits;
+  br->bit_pos_ += unused_bits;
+}
+
+/* BrotliDecompressStream :2779-3403.  Resumable: everything the decoder needs to continue lives in State, including
+ * the 8-byte carry-over of an interrupted read (s->buffer, :2813-2833,:2848-2916).  *input_offset / *available_in and
+ * *output_offset / *available_out / *total_out move exactly as the reference moves them. */
+static int DecompressStream(State* s, size_t* available_in, size_t* input_offset, const uint8_t* xinput,
+                            size_t* available_out, size_t* output_offset, uint8_t* output, size_t* total_out) {
   int result = E_SUCCESS;
-  if ((uint64_t)available_in >= ((uint64_t)1 << 32)) return E_INVALID_ARGUMENTS; /* :2799-2812 */
-  s->br.avail_in = (uint32_t)available_in; s->br.next_in = 0;
+  if (s->error_code < 0) return s->error_code; /* is_fatal: sticky, :2796-2798 (error_code is not touched) */
+  if ((uint64_t)*available_in >= ((uint64_t)1 << 32) || (uint64_t)*input_offset >= ((uint64_t)1 << 32)) { /* :2799-2804 */
+    s->error_code = E_INVALID_ARGUMENTS; return E_INVALID_ARGUMENTS;
+  }
+  s->output = output; s->available_out = *available_out; s->output_offset = *output_offset; s->total_out = *total_out;
+  if (s->buffer_length == 0) {
+    s->input = xinput; s->br.avail_in = (uint32_t)*available_in; s->br.next_in = (uint32_t)*input_offset;
+  } else { /* :2818-2832: bytes are added to the carry-over one at a time below; they are copied up front */
+    size_t copy_len = sizeof(s->buffer) - s->buffer_length;
+    result = E_NEEDS_MORE_INPUT;
+    if (copy_len > *available_in) copy_len = *available_in;
+    if (copy_len) memcpy(s->buffer + s->buffer_length, xinput + *input_offset, copy_len);
+    s->input = s->buffer; s->br.next_in = 0;
+  }
+#define STREAM_SYNC_OUT() do { *available_out = s->available_out; *output_offset = s->output_offset; *total_out = s->total_out; } while (0)
   for (;;) {
     if (result != E_SUCCESS) {
-      if (result == E_NEEDS_MORE_INPUT && s->ringbuffer) { /* :2834-2846 flush what was decoded */
-        int r = WriteRingBuffer(s, 1);
-        if (r < 0) result = r;
+      if (result == E_NEEDS_MORE_INPUT) {
+        if (s->ringbuffer) { /* :2838-2850 flush what was decoded; only a fatal outcome replaces the result */
+          int r = WriteRingBuffer(s, 1);
+          if (r < 0) { result = r; break; }
+        }
+        if (s->buffer_length != 0) { /* reading from the carry-over, :2851-2886 */
+          if (s->br.avail_in == 0) { /* the interrupted read is complete: back to the caller's input */
+            s->buffer_length = 0;
+            result = E_SUCCESS;
+            s->input = xinput; s->br.avail_in = (uint32_t)*available_in; s->br.next_in = (uint32_t)*input_offset;
+            continue;
+          } else if (*available_in != 0) { /* one more byte from the caller and retry */
+            result = E_SUCCESS;
+            s->buffer[s->buffer_length] = xinput[*input_offset];
+            s->buffer_length++;
+            s->br.avail_in = s->buffer_length;
+            (*input_offset)++; (*available_in)--;
+            continue;
+          }
+          break; /* cannot finish the read and there is no more input */
+        } else { /* :2887-2899 the caller's input ran out: its unread tail goes to the carry-over */
+          *input_offset = s->br.next_in; *available_in = s->br.avail_in;
+          while (*available_in != 0) {
+            s->buffer[s->buffer_length] = xinput[*input_offset];
+            s->buffer_length++; (*input_offset)++; (*available_in)--;
+          }
+          break;
+        }
+      } else { /* failure or NeedsMoreOutput, :2902-2915 */
+        if (s->buffer_length != 0) {
+          s->buffer_length = 0; /* the carry-over was consumed and produced output */
+        } else {
+          BitReaderUnload(&s->br);
+          *available_in = s->br.avail_in; *input_offset = s->br.next_in;
+        }
       }
       break;
     }
@@ -1200,21 +1359,34 @@ static int DecompressStream(State* s, size_t available_in) {
         }
         if (result == E_SUCCESS) s->state = ST_METABLOCK_DONE;
         break;
-      case ST_HUFFMAN_CODE_0: { /* :3046-3140 (HUFFMAN_CODE_0..3) */
-        int k = s->loop_counter; uint32_t alphabet_size, block_length_out;
+      case ST_HUFFMAN_CODE_0: { /* :3046-3070 */
+        int k = s->loop_counter;
         if (k >= 3) { s->state = ST_METABLOCK_HEADER_2; break; }
         result = DecodeVarLenUint8(s, &s->num_block_types[k]);
         if (result != E_SUCCESS) break;
         s->num_block_types[k]++;
         if (s->num_block_types[k] < 2) { s->loop_counter++; break; }
-        alphabet_size = s->num_block_types[k] + 2;
-        result = ReadHuffmanCode(alphabet_size, alphabet_size, &s->block_type_trees[k * HUFFMAN_MAX_TABLE_SIZE], NULL, s);
+        s->state = ST_HUFFMAN_CODE_1;
+        break;
+      }
+      case ST_HUFFMAN_CODE_1: { /* :3071-3092 */
+        uint32_t alphabet_size = s->num_block_types[s->loop_counter] + 2;
+        result = ReadHuffmanCode(alphabet_size, alphabet_size, &s->block_type_trees[s->loop_counter * HUFFMAN_MAX_TABLE_SIZE], NULL, s);
         if (result != E_SUCCESS) break;
-        result = ReadHuffmanCode(kNumBlockLengthCodes, kNumBlockLengthCodes, &s->block_len_trees[k * HUFFMAN_MAX_TABLE_SIZE], NULL, s);
+        s->state = ST_HUFFMAN_CODE_2;
+        break;
+      }
+      case ST_HUFFMAN_CODE_2: /* :3093-3111 */
+        result = ReadHuffmanCode(kNumBlockLengthCodes, kNumBlockLengthCodes, &s->block_len_trees[s->loop_counter * HUFFMAN_MAX_TABLE_SIZE], NULL, s);
         if (result != E_SUCCESS) break;
-        if (!SafeReadBlockLength(&block_length_out, &s->block_len_trees[k * HUFFMAN_MAX_TABLE_SIZE], &s->br, s->input)) { result = E_NEEDS_MORE_INPUT; break; }
-        s->block_length[k] = block_length_out;
+        s->state = ST_HUFFMAN_CODE_3;
+        break;
+      case ST_HUFFMAN_CODE_3: { /* :3112-3139 */
+        uint32_t block_length_out = 0;
+        if (!SafeReadBlockLength(s, &block_length_out, &s->block_len_trees[s->loop_counter * HUFFMAN_MAX_TABLE_SIZE], &s->br, s->input)) { result = E_NEEDS_MORE_INPUT; break; }
+        s->block_length[s->loop_counter] = block_length_out;
         s->loop_counter++;
+        s->state = ST_HUFFMAN_CODE_0;
         break;
       }
       case ST_METABLOCK_HEADER_2: { /* :3141-3163 */
@@ -1223,6 +1395,7 @@ static int DecompressStream(State* s, size_t available_in) {
         s->distance_postfix_bits = bits & 3; bits >>= 2;
         s->num_direct_distance_codes = NUM_DISTANCE_SHORT_CODES + (bits << s->distance_postfix_bits);
         s->distance_postfix_mask = (int)BitMask(s->distance_postfix_bits);
+        free(s->context_modes);
         s->context_modes = (uint8_t*)calloc(s->num_block_types[0], 1);
         if (!s->context_modes) { result = E_ALLOC_CONTEXT_MODES; break; }
         s->loop_counter = 0;
@@ -1250,7 +1423,7 @@ static int DecompressStream(State* s, size_t available_in) {
         if (!HGroupInit(&s->literal_hgroup, kNumLiteralCodes, kNumLiteralCodes, (uint16_t)s->num_literal_htrees) ||
             !HGroupInit(&s->insert_copy_hgroup, kNumInsertAndCopyCodes, kNumInsertAndCopyCodes, (uint16_t)s->num_block_types[1]) ||
             !HGroupInit(&s->distance_hgroup, (uint16_t)num_distance_codes, (uint16_t)max_distance_symbol, (uint16_t)s->num_dist_htrees)) {
-          return E_UNREACHABLE;
+          s->error_code = E_UNREACHABLE; STREAM_SYNC_OUT(); return E_UNREACHABLE;
         }
         s->loop_counter = 0;
         s->state = ST_TREE_GROUP;
@@ -1289,37 +1462,57 @@ static int DecompressStream(State* s, size_t available_in) {
         StateCleanupAfterMetablock(s);
         if (!s->is_last_metablock) { s->state = ST_METABLOCK_BEGIN; break; }
         if (!JumpToByteBoundary(&s->br)) { result = E_PADDING_2; break; }
+        if (s->buffer_length == 0) { /* :3374-3378 hand the unread whole bytes back */
+          BitReaderUnload(&s->br);
+          *available_in = s->br.avail_in; *input_offset = s->br.next_in;
+        }
         s->state = ST_DONE;
         break;
       case ST_DONE: /* :3382-3397 */
         if (s->ringbuffer) { result = WriteRingBuffer(s, 1); if (result != E_SUCCESS) break; }
+        s->error_code = result; STREAM_SYNC_OUT();
         return result;
       default:
+        s->error_code = E_UNREACHABLE; STREAM_SYNC_OUT();
         return E_UNREACHABLE;
     }
   }
+  s->error_code = result; /* SaveErrorCode!, :89-102 */
+  STREAM_SYNC_OUT();
   return result;
+#undef STREAM_SYNC_OUT
 }
 
-/* brotli_decode (src/lib.rs:446-468) + BrotliDecoderReturnInfo::new (src/lib.rs:344-369) */
-OracleReturnInfo oracle_brotli_decode_ex(const uint8_t* input, size_t input_len, uint8_t* output, size_t output_cap,
-                                         int large_window, const uint8_t* custom_dict, size_t custom_dict_len) {
-  OracleReturnInfo ret; State* s = (State*)calloc(1, sizeof(State)); int code; const char* msg;
-  memset(&ret, 0, sizeof(ret));
-  if (!s) { ret.result = ORACLE_RESULT_FAILURE; ret.error_code = E_UNREACHABLE; return ret; }
-  /* make_brotli_state!, src/state.rs:279-388 */
-  s->state = ST_UNINITED; s->input = input; s->output = output; s->available_out = output_cap;
+/* make_brotli_state!, src/state.rs:279-388 (+ new_with_custom_dictionary :400-411, new_strict :413-420) */
+static State* StateCreate(int large_window, const uint8_t* custom_dict, size_t custom_dict_len) {
+  State* s = (State*)calloc(1, sizeof(State));
+  if (!s) return NULL;
+  s->state = ST_UNINITED;
   s->dist_rb[0] = 16; s->dist_rb[1] = 15; s->dist_rb[2] = 11; s->dist_rb[3] = 4;
   s->context_lookup = &kBrotliContextLookup[0];
   s->mtf_upper_bound = 255; s->canny_ringbuffer_allocation = 1; s->large_window = large_window;
   s->custom_dict = custom_dict; s->custom_dict_size = (ptrdiff_t)custom_dict_len; s->custom_dict_avoid_context_seed = custom_dict_len != 0;
   s->context_map_table = (HC*)calloc(HUFFMAN_MAX_TABLE_SIZE, sizeof(HC));
   s->br.val_ = 0; s->br.bit_pos_ = 64; /* BrotliInitBitReader, bit_reader:424-427 */
-  code = s->context_map_table ? DecompressStream(s, input_len) : E_UNREACHABLE;
+  if (!s->context_map_table) { free(s); return NULL; }
+  return s;
+}
+static int ResultOfCode(int code) { /* SaveErrorCode!, :89-102 */
+  return code == E_SUCCESS ? ORACLE_RESULT_SUCCESS : code == E_NEEDS_MORE_INPUT ? ORACLE_NEEDS_MORE_INPUT
+       : code == E_NEEDS_MORE_OUTPUT ? ORACLE_NEEDS_MORE_OUTPUT : ORACLE_RESULT_FAILURE;
+}
+
+/* brotli_decode (src/lib.rs:446-468) + BrotliDecoderReturnInfo::new (src/lib.rs:344-369) */
+OracleReturnInfo oracle_brotli_decode_ex(const uint8_t* input, size_t input_len, uint8_t* output, size_t output_cap,
+                                         int large_window, const uint8_t* custom_dict, size_t custom_dict_len) {
+  OracleReturnInfo ret; State* s = StateCreate(large_window, custom_dict, custom_dict_len); int code; const char* msg;
+  size_t available_in = input_len, input_offset = 0, available_out = output_cap, output_offset = 0, total_out = 0;
+  memset(&ret, 0, sizeof(ret));
+  if (!s) { ret.result = ORACLE_RESULT_FAILURE; ret.error_code = E_UNREACHABLE; return ret; }
+  code = DecompressStream(s, &available_in, &input_offset, input, &available_out, &output_offset, output, &total_out);
   ret.error_code = code;
-  ret.result = code == E_SUCCESS ? ORACLE_RESULT_SUCCESS : code == E_NEEDS_MORE_INPUT ? ORACLE_NEEDS_MORE_INPUT
-             : code == E_NEEDS_MORE_OUTPUT ? ORACLE_NEEDS_MORE_OUTPUT : ORACLE_RESULT_FAILURE; /* SaveErrorCode!, :89-102 */
-  ret.decoded_size = s->output_offset;
+  ret.result = ResultOfCode(code);
+  ret.decoded_size = output_offset;
   msg = oracle_error_string(code);
   strncpy(ret.error, msg, sizeof(ret.error) - 1);
   StateCleanup(s);
@@ -1328,6 +1521,26 @@ OracleReturnInfo oracle_brotli_decode_ex(const uint8_t* input, size_t input_len,
 }
 OracleReturnInfo oracle_brotli_decode(const uint8_t* input, size_t input_len, uint8_t* output, size_t output_cap) {
   return oracle_brotli_decode_ex(input, input_len, output, output_cap, 1, NULL, 0);
+}
+
+/* ---- the streaming call: one State across many BrotliDecompressStream calls (src/decode.rs:2779-2790) ---- */
+struct OracleStream { State* s; uint8_t* dict; };
+OracleStream* oracle_stream_create(int large_window, const uint8_t* custom_dict, size_t custom_dict_len) {
+  OracleStream* o = (OracleStream*)calloc(1, sizeof(OracleStream));
+  if (!o) return NULL;
+  if (custom_dict_len) { o->dict = (uint8_t*)malloc(custom_dict_len); if (!o->dict) { free(o); return NULL; } memcpy(o->dict, custom_dict, custom_dict_len); }
+  o->s = StateCreate(large_window, o->dict, custom_dict_len);
+  if (!o->s) { free(o->dict); free(o); return NULL; }
+  return o;
+}
+int oracle_stream_decompress(OracleStream* o, size_t* available_in, size_t* input_offset, const uint8_t* input,
+                             size_t* available_out, size_t* output_offset, uint8_t* output, size_t* total_out) {
+  return ResultOfCode(DecompressStream(o->s, available_in, input_offset, input, available_out, output_offset, output, total_out));
+}
+int oracle_stream_error_code(const OracleStream* o) { return o->s->error_code; }
+void oracle_stream_destroy(OracleStream* o) {
+  if (!o) return;
+  StateCleanup(o->s); free(o->s); free(o->dict); free(o);
 }
 
 /* ---- threaded batch driver (CPU baseline only) ---- */

@@ -52,6 +52,17 @@ OracleReturnInfo oracle_brotli_decode_ex(const uint8_t* input, size_t input_len,
 int oracle_brotli_decode_batch(size_t n, const uint8_t* in, const uint64_t* in_off, uint8_t* out,
                                const uint64_t* out_off, uint64_t* out_len, int32_t* codes, int threads);
 
+/* The reference's resumable call: one BrotliState across many BrotliDecompressStream calls (src/decode.rs:2779-2790;
+ * BrotliState persists between calls, src/state.rs:156-278).  The arguments move exactly as the reference moves them:
+ * *input_offset / *available_in by the bytes consumed, *output_offset / *available_out by the bytes produced,
+ * *total_out = bytes produced since the start of the stream.  Returns a BrotliResult. */
+typedef struct OracleStream OracleStream;
+OracleStream* oracle_stream_create(int large_window, const uint8_t* custom_dict, size_t custom_dict_len);
+int oracle_stream_decompress(OracleStream* o, size_t* available_in, size_t* input_offset, const uint8_t* input,
+                             size_t* available_out, size_t* output_offset, uint8_t* output, size_t* total_out);
+int oracle_stream_error_code(const OracleStream* o); /* BrotliDecoderErrorCode of the last call */
+void oracle_stream_destroy(OracleStream* o);
+
 const char* oracle_error_string(int code); /* BrotliDecoderErrorStr, src/state.rs:533-578 */
 
 /* ---- pieces exported for the reference's known-answer tests ---- */

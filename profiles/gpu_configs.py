@@ -7,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("rust-brotli-decompressor_b200")
-corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+corpus = importlib.import_module("tools.corpus")
 pkg.lib()
 for cfg, n_unique, n, size in (("C3", 4096, 1 << 20, 4096), ("C5", 2200, 131072, 65536), ("C4", 8, 2048, 4 << 20)):
     comp, orig, desc = corpus.make_config(cfg, n_unique, size=size)

@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("rust-brotli-decompressor_b200")
-corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+corpus = importlib.import_module("tools.corpus")
 pool = corpus.text_pool()
 d = pool[500000:560000]
 rng = np.random.default_rng(5)

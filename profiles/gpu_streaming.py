@@ -6,7 +6,7 @@ import importlib, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("rust-brotli-decompressor_b200")
-corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+corpus = importlib.import_module("tools.corpus")
 pool = corpus.text_pool()
 data = (pool * 4)[:4000000]
 comp = corpus.compress(data, 2)

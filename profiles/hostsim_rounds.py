@@ -8,7 +8,7 @@ import ctypes, importlib, os, subprocess, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+corpus = importlib.import_module("tools.corpus")
 cfg = sys.argv[1] if len(sys.argv) > 1 else "headline"
 n_unique = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 d = os.path.join(ROOT, "build_tmp")

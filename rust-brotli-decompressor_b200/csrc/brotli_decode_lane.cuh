@@ -326,7 +326,7 @@ BD_COLD void store_head_bytes(uint8_t* out_al, uint32_t bias, uint32_t wpos, uin
 // first word when the region starts inside it, and the command loop writes that word's bytes (from the history ring)
 // right after the phase that completed it -- LN_HEAD_CHECK, three places per round instead of every store site.
 #ifndef BD_LANE_HEAD_PER_ROUND
-#define BD_LANE_HEAD_PER_ROUND 0
+#define BD_LANE_HEAD_PER_ROUND 1
 #endif
 BD_DEV void store_word_if(bool cond, uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t wpos, uint32_t word) {
   sts32_if(cond, hist + (wpos & 28u), word);

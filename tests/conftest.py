@@ -22,7 +22,7 @@ def pkg():
 
 @pytest.fixture(scope="session")
 def corpus():
-    return importlib.import_module("rust-brotli-decompressor_b200.corpus")
+    return importlib.import_module("tools.corpus")
 
 
 @pytest.fixture(scope="session")

@@ -43,7 +43,21 @@ class Oracle:
         L.oracle_brotli_decode_batch.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
         L.oracle_error_string.restype = ctypes.c_char_p
         L.oracle_error_string.argtypes = [ctypes.c_int]
+        L.oracle_stream_create.restype = ctypes.c_void_p
+        L.oracle_stream_create.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+        L.oracle_stream_decompress.restype = ctypes.c_int
+        L.oracle_stream_decompress.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p,
+                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p,
+                                               ctypes.POINTER(ctypes.c_size_t)]
+        L.oracle_stream_error_code.restype = ctypes.c_int
+        L.oracle_stream_error_code.argtypes = [ctypes.c_void_p]
+        L.oracle_stream_destroy.restype = None
+        L.oracle_stream_destroy.argtypes = [ctypes.c_void_p]
         self.lib = L
+
+    def stream(self, large_window=False, custom_dict=None):
+        """A resumable decoder state: the reference's BrotliDecompressStream call by call (OracleStream)."""
+        return OracleStream(self.lib, large_window, custom_dict)
 
     def decode(self, data, capacity, large_window=True, custom_dict=None):
         data = bytes(data)
@@ -59,6 +73,65 @@ class Oracle:
         n = len(out_len)
         return self.lib.oracle_brotli_decode_batch(n, in_bytes.ctypes.data, in_off.ctypes.data, out_bytes.ctypes.data, out_off.ctypes.data,
                                                    out_len.ctypes.data, codes.ctypes.data, int(threads))
+
+
+class OracleStream:
+    """One BrotliState of the oracle across many BrotliDecompressStream calls (src/decode.rs:2779-2790).
+    call(data, out_cap) feeds `data` with an output buffer of out_cap bytes and returns
+    (result, consumed, produced_bytes, total_out) exactly as the reference moves its arguments."""
+
+    def __init__(self, lib, large_window=False, custom_dict=None):
+        self.lib = lib
+        cd = bytes(custom_dict) if custom_dict else None
+        self.h = lib.oracle_stream_create(1 if large_window else 0, cd, len(cd) if cd else 0)
+        self.total_out = ctypes.c_size_t(0)
+
+    def call(self, data, out_cap):
+        data = bytes(data)
+        buf = ctypes.create_string_buffer(max(int(out_cap), 1))
+        ain, ioff = ctypes.c_size_t(len(data)), ctypes.c_size_t(0)
+        aout, ooff = ctypes.c_size_t(int(out_cap)), ctypes.c_size_t(0)
+        r = self.lib.oracle_stream_decompress(self.h, ctypes.byref(ain), ctypes.byref(ioff), data, ctypes.byref(aout), ctypes.byref(ooff), buf,
+                                              ctypes.byref(self.total_out))
+        assert ioff.value + ain.value == len(data) and ooff.value + aout.value == int(out_cap)
+        return r, ioff.value, buf.raw[:ooff.value], self.total_out.value
+
+    def error_code(self):
+        return self.lib.oracle_stream_error_code(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def drive_stream(call, comp, in_chunk, out_chunk, max_calls=10_000_000):
+    """The reference's own streaming driver (decompress_internal, src/bin/integration_tests.rs:122-216) over any
+    decoder exposing call(data, out_cap) -> (result, consumed, produced, total_out): new input (<= in_chunk bytes)
+    only after NeedsMoreInput, a fresh out_chunk-byte output buffer for every call.
+    Returns (final result, output bytes, trace) with trace = [(result, consumed, n_produced, total_out), ...]."""
+    comp = bytes(comp)
+    pos = 0
+    pending = b""
+    result = 2
+    out = bytearray()
+    trace = []
+    for _ in range(max_calls):
+        if result == 2:
+            if pos >= len(comp):
+                return 2, bytes(out), trace  # "Read EOF"
+            pending = comp[pos:pos + in_chunk]
+            pos += len(pending)
+        elif result != 3:
+            break
+        result, consumed, produced, total = call(pending, out_chunk)
+        trace.append((result, consumed, len(produced), total))
+        pending = pending[consumed:]
+        out += produced
+    return result, bytes(out), trace
 
 
 class HostSim:

@@ -57,7 +57,7 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import helpers
     sh = importlib.import_module("rust-brotli-decompressor_b200.sharding")
-    corpus = importlib.import_module("rust-brotli-decompressor_b200.corpus")
+    corpus = importlib.import_module("tools.corpus")
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
