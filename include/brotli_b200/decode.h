@@ -204,10 +204,19 @@ BROTLI_B200_API BrotliDecoderReturnInfo BrotliB200DecompressWithDictionary(size_
                                                                            const uint8_t* dictionary, size_t dictionary_size);
 /* Streaming form: attaches a custom dictionary to a decoder state before its first input byte -- what
  * Decompressor::new_with_custom_dict (src/reader.rs:105) and DecompressorWriter::new_with_custom_dictionary
- * (src/writer.rs:117) do through BrotliState::new_with_custom_dictionary.  The bytes are copied.  Returns 1, or 0 if the
- * state has been used already or the arguments are invalid. */
+ * (src/writer.rs:117) do through BrotliState::new_with_custom_dictionary, which also accepts large-window streams
+ * (src/state.rs:400-411).  The bytes are copied.  Returns 1, or 0 if the state has been used already or the arguments
+ * are invalid. */
 BROTLI_B200_API int BrotliB200DecoderSetCustomDictionary(BrotliDecoderState* state, const uint8_t* dictionary,
                                                          size_t dictionary_size);
+/* Multiplexed streaming: the i-th element of every array is one BrotliDecoderDecompressStream call (src/ffi/mod.rs:389-463)
+ * on states[i] -- same argument movement, same result, call by call -- and ONE decode launch serves all n states (each
+ * state keeps a sliding window of its stream, its prefix-code tables and the decoder's checkpoint in device memory, so a
+ * call continues where the previous one stopped, inside a metablock included).  total_out may be NULL.  A state must not
+ * appear twice in one call.  Returns 0, or a negative code for an argument or CUDA failure (the affected states fail). */
+BROTLI_B200_API int BrotliB200DecoderDecompressStreamBatch(size_t n, BrotliDecoderState* const* states, size_t* available_in,
+                                                           const uint8_t** next_in, size_t* available_out, uint8_t** next_out,
+                                                           size_t* total_out, BrotliDecoderResult* results);
 /* BrotliB200DecompressBatchPacked with one custom dictionary (host memory) shared by all streams of the batch. */
 BROTLI_B200_API int BrotliB200DecompressBatchPackedWithDictionary(size_t n, const uint8_t* in_bytes, const uint64_t* in_off,
                                                                   uint8_t* out_bytes, const uint64_t* out_off, uint64_t* out_len,

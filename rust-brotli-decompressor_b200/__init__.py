@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "BrotliDecoderFreeU8", "BrotliDecoderMallocUsize", "BrotliDecoderFreeUsize", "BrotliB200DecompressBatchDevice",
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
     "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary", "BrotliB200DecoderSetCustomDictionary",
+    "BrotliB200DecoderDecompressStreamBatch",
     "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
     "BrotliB200Shutdown",
 ]
@@ -99,6 +100,8 @@ def lib():
     L.BrotliB200DecompressBatchPackedWithDictionary.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
     L.BrotliB200DecoderSetCustomDictionary.restype = ctypes.c_int
     L.BrotliB200DecoderSetCustomDictionary.argtypes = [vp, vp, sz]
+    L.BrotliB200DecoderDecompressStreamBatch.restype = ctypes.c_int
+    L.BrotliB200DecoderDecompressStreamBatch.argtypes = [sz] + [vp] * 7
     L.BrotliB200ChecksumBatchDevice.restype = ctypes.c_int
     L.BrotliB200ChecksumBatchDevice.argtypes = [sz, vp, vp, vp, vp, vp]
     L.BrotliB200KernelLaunchCount.restype = ctypes.c_uint64
@@ -205,7 +208,13 @@ class DecoderState:
         r = lib().BrotliDecoderDecompressStream(self._s, ctypes.byref(avail_in), ctypes.byref(next_in), ctypes.byref(avail_out),
                                                 ctypes.byref(next_out), ctypes.byref(total))
         produced = int(out_capacity) - avail_out.value
+        self.total_out = total.value
         return r, len(data) - avail_in.value, outbuf.raw[:produced]
+
+    def call(self, data, out_capacity):
+        """decompress_stream with the running total: (result, consumed, produced_bytes, total_out)."""
+        r, used, out = self.decompress_stream(data, out_capacity)
+        return r, used, out, self.total_out
 
     def is_finished(self):
         return bool(lib().BrotliDecoderIsFinished(self._s))
@@ -223,6 +232,32 @@ class DecoderState:
         return lib().BrotliDecoderGetErrorString(self._s).decode()
 
 
+def decompress_stream_batch(states, datas, out_capacities):
+    """One BrotliDecoderDecompressStream call on each of ``states`` (DecoderState objects), served by ONE decode launch
+    (BrotliB200DecoderDecompressStreamBatch).  Returns [(result, consumed, produced_bytes, total_out), ...]."""
+    n = len(states)
+    if n == 0:
+        return []
+    datas = [bytes(d) for d in datas]
+    inbufs = [ctypes.create_string_buffer(d, max(len(d), 1)) for d in datas]
+    outbufs = [ctypes.create_string_buffer(max(int(c), 1)) for c in out_capacities]
+    handles = (ctypes.c_void_p * n)(*[s._s for s in states])
+    avail_in = (ctypes.c_size_t * n)(*[len(d) for d in datas])
+    avail_out = (ctypes.c_size_t * n)(*[int(c) for c in out_capacities])
+    next_in = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in inbufs])
+    next_out = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in outbufs])
+    total = (ctypes.c_size_t * n)()
+    results = (ctypes.c_int * n)()
+    _check(lib().BrotliB200DecoderDecompressStreamBatch(n, handles, avail_in, next_in, avail_out, next_out, total, results),
+           "BrotliB200DecoderDecompressStreamBatch")
+    out = []
+    for i in range(n):
+        produced = int(out_capacities[i]) - avail_out[i]
+        states[i].total_out = total[i]
+        out.append((results[i], len(datas[i]) - avail_in[i], outbufs[i].raw[:produced], total[i]))
+    return out
+
+
 class Decompressor:
     """``Decompressor<R: Read>`` (src/reader.rs:91-130): wraps a reader of compressed bytes.
 
@@ -234,7 +269,9 @@ class Decompressor:
         """``custom_dict``: ``Decompressor::new_with_custom_dict(r, buffer_size, dict)`` (src/reader.rs:105)."""
         self._r = reader
         self._bufsize = max(int(buffer_size), 1)
-        self._state = DecoderState(custom_dict=custom_dict)
+        # the reference builds this state with BrotliState::new_with_custom_dictionary (src/reader.rs:226), which accepts
+        # large-window streams (src/state.rs:400-411)
+        self._state = DecoderState(large_window=True, custom_dict=custom_dict)
         self._pending = b""
         self._eof = False
         self._done = False

@@ -20,6 +20,9 @@
 
 #include "../../include/brotli_b200/decode.h"
 #include "brotli_b200_runtime.h"
+// the kernel's session record (ResumeState, SessionCopy) and the session logic
+#include "brotli_b200_session_types.h"
+#include "brotli_b200_session.h"
 
 extern "C" const uint8_t kBrotliDictionaryData[];  // tables/brotli_dictionary.c (122 784 bytes)
 
@@ -81,7 +84,8 @@ struct DevBuf {
     p = nullptr; cap = 0;
     size_t want = n + n / 8 + 4096;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, n); want = n; }  // (clear the failed attempt from the runtime's last-error slot)
+    if (e != cudaSuccess) cudaGetLastError();
     if (e == cudaSuccess) cap = want;
     return e;
   }
@@ -117,6 +121,8 @@ struct DeviceCtx {
   bool arena_busy = false;
   DevBuf in, out, in_off, out_off, out_len, codes, in_used;
   DevBuf cdict;            // custom LZ77 dictionary of the batch in flight
+  DevBuf sess_states, sess_pieces, sess_blob;  // staging of a session launch: ResumeState[], SessionCopy[], bytes
+  DevBuf redo_out;         // output windows of the exact re-decode of NeedsMoreOutput one-shots
   void* pinned = nullptr;  // small pinned staging area for one-shot calls
   size_t pinned_cap = 0;
 };
@@ -204,16 +210,16 @@ DeviceCtx* acquire_ctx() {
 // ---- device-resident batch -------------------------------------------------------------------
 int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                   const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_codes, uint64_t* d_in_used, uint32_t large_window,
-                  cudaStream_t stream, const uint8_t* d_dict = nullptr, uint64_t dict_size = 0, brotli_b200::ResumeState* d_resume = nullptr) {
+                  cudaStream_t stream, const uint8_t* d_dict = nullptr, uint64_t dict_size = 0, brotli_b200::ResumeState* d_sessions = nullptr) {
   if (n == 0) return 0;
-  if (n > 0xFFFFFFF0ull) { set_error("brotli_b200: batch too large"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+  if (n >= ((uint64_t)1 << 31)) { set_error("brotli_b200: batch too large"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
   BatchArgs a;
   a.in = d_in; a.in_off = d_in_off; a.out = d_out; a.out_off = d_out_off; a.out_len = d_out_len; a.codes = d_codes;
   a.in_used = d_in_used;
   a.order = nullptr; a.ticket = c->ticket; a.arena = c->arena; a.dictionary = c->dictionary;
   a.n = (uint32_t)n; a.large_window = large_window; a.n_ptr = nullptr;
   a.custom_dict = dict_size ? d_dict : nullptr; a.custom_dict_size = d_dict ? dict_size : 0;
-  a.resume = n == 1 ? d_resume : nullptr;
+  a.sessions = d_sessions;
   std::lock_guard<std::mutex> lock(c->launch_mu);
   if (c->arena_busy) CU_TRY(cudaStreamWaitEvent(stream, c->ev_arena, 0));  // launches on other streams must not overlap
   const uint32_t slot = c->timed_count % DeviceCtx::kTimedLaunches;
@@ -221,7 +227,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
   // (a streaming session is one stream: exact kernel; a batch with a custom dictionary takes the lane kernel's dictionary
   // instance when the configured geometry has one)
-  if (c->lane_ctas > 0 && a.resume == nullptr && (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
+  if (c->lane_ctas > 0 && a.sessions == nullptr && (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
     brotli_b200::LaneArgs la;
@@ -259,6 +265,8 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
 // their own streams and are ordered against the decode stream with events, so the H2D of chunk
 // k+1 and the D2H of chunk k-1 overlap the decode of chunk k.  Decode kernels stay on one stream
 // because they share the per-warp scratch arena.
+int redo_needs_more_output(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const uint64_t* in_off, const uint64_t* out_off, const uint8_t* d_in,
+                           uint64_t* out_len, int32_t* codes, const uint8_t* d_dict, size_t dict_size);
 int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const uint64_t* in_off, uint8_t* out_bytes,
                        const uint64_t* out_off, uint64_t* out_len, int32_t* codes, uint64_t* in_used, uint32_t large_window,
                        const uint8_t* dict = nullptr, size_t dict_size = 0) {
@@ -348,6 +356,7 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
     rc = BROTLI_DECODER_ERROR_UNREACHABLE;
   }
   if (rc == 0 && timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) == cudaSuccess) g_last_kernel_ms.store(ms); }
+  if (rc == 0) rc = redo_needs_more_output(c, n, in_bytes, in_off, out_off, d_in, out_len, codes, dict_size ? (const uint8_t*)c->cdict.p + 32 : nullptr, dict_size);
   if (trace && rc == 0 && !chunks.empty()) {
     for (size_t ci = 0; ci < chunks.size(); ci++) {
       float th = 0, td = 0, to = 0;
@@ -360,6 +369,132 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
   }
   for (auto& k : chunks) { if (k.h2d) cudaEventDestroy(k.h2d); if (k.done) cudaEventDestroy(k.done); if (k.d2h) cudaEventDestroy(k.d2h); }
   return rc;
+}
+
+// ---- streaming sessions and exact re-decodes: the device backend of brotli_b200_session.h ----------------
+// All of it runs on s_compute under c->mu (the staging buffers are the context's).
+struct CudaDev {
+  DeviceCtx* c;
+  uint8_t* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (uint8_t*)p;
+  }
+  void release(uint8_t* p) { if (p) cudaFree(p); }
+  size_t arena_bytes() const { return brotli_b200::arena_bytes_per_warp(); }
+  int upload(uint8_t* d, const uint8_t* h, size_t n) {
+    return cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : BROTLI_DECODER_ERROR_UNREACHABLE;
+  }
+  // pieces (with their blob-relative side rebased onto the device blob) -> device, then the copy kernel
+  int copy_pieces(std::vector<brotli_b200::SessionCopy>& v) {
+    CU_TRY(c->sess_pieces.reserve(v.size() * sizeof(brotli_b200::SessionCopy)));
+    CU_TRY(cudaMemcpyAsync(c->sess_pieces.p, v.data(), v.size() * sizeof(brotli_b200::SessionCopy), cudaMemcpyHostToDevice, c->s_compute));
+    CU_TRY(brotli_b200::launch_session_copy((const brotli_b200::SessionCopy*)c->sess_pieces.p, (uint32_t)v.size(), c->s_compute));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  int run(brotli_b200::ResumeState* arr, uint32_t n, const uint8_t* blob, size_t blob_bytes, const brotli_b200::SessionCopy* scatter, uint32_t n_scatter) {
+    if (n_scatter) {
+      CU_TRY(c->sess_blob.reserve(blob_bytes + 16));
+      CU_TRY(cudaMemcpyAsync(c->sess_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, c->s_compute));
+      std::vector<brotli_b200::SessionCopy> v(scatter, scatter + n_scatter);
+      for (auto& k : v) k.src = (const uint8_t*)c->sess_blob.p + (uintptr_t)k.src;
+      int rc = copy_pieces(v);
+      if (rc != 0) return rc;
+      CU_TRY(cudaStreamSynchronize(c->s_compute));  // `v` and the caller's blob are pageable
+    }
+    CU_TRY(c->sess_states.reserve((size_t)n * sizeof(brotli_b200::ResumeState)));
+    CU_TRY(cudaMemcpyAsync(c->sess_states.p, arr, (size_t)n * sizeof(brotli_b200::ResumeState), cudaMemcpyHostToDevice, c->s_compute));
+    int rc = decode_device(c, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1u, c->s_compute, nullptr, 0,
+                           (brotli_b200::ResumeState*)c->sess_states.p);
+    if (rc != 0) return rc;
+    CU_TRY(cudaMemcpyAsync(arr, c->sess_states.p, (size_t)n * sizeof(brotli_b200::ResumeState), cudaMemcpyDeviceToHost, c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+    return 0;
+  }
+  int gather(const brotli_b200::SessionCopy* pieces, uint32_t n, uint8_t* host, size_t bytes) {
+    CU_TRY(c->sess_blob.reserve(bytes + 16));
+    std::vector<brotli_b200::SessionCopy> v(pieces, pieces + n);
+    for (auto& k : v) k.dst = (uint8_t*)c->sess_blob.p + (uintptr_t)k.dst;
+    int rc = copy_pieces(v);
+    if (rc != 0) return rc;
+    CU_TRY(cudaMemcpyAsync(host, c->sess_blob.p, bytes, cudaMemcpyDeviceToHost, c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+    return 0;
+  }
+  int move(const brotli_b200::SessionCopy* pieces, uint32_t n) {
+    std::vector<brotli_b200::SessionCopy> v(pieces, pieces + n);
+    int rc = copy_pieces(v);
+    if (rc != 0) return rc;
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+    return 0;
+  }
+};
+
+// The reference decodes a whole ring buffer ahead of the caller's buffer, so a stream that is corrupt (or ends) beyond a too
+// small output capacity reports the corruption (or NeedsMoreInput), not NeedsMoreOutput (src/decode.rs:1693-1738: the
+// capacity is only noticed at a ring flush point).  The batch kernels cannot write past a stream's region; streams they
+// leave at NeedsMoreOutput are decoded again here into scratch windows that reach the next flush point, with the
+// capacity as the decoder's budget: code and decoded_size then are exactly the reference's.  `d_in` holds the batch's
+// input (absolute offsets), results are patched in the host arrays.  Runs under c->mu.
+int redo_needs_more_output(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const uint64_t* in_off, const uint64_t* out_off, const uint8_t* d_in,
+                           uint64_t* out_len, int32_t* codes, const uint8_t* d_dict, size_t dict_size) {
+  static const bool enabled = !(getenv("BROTLI_B200_EXACT_REDO") && getenv("BROTLI_B200_EXACT_REDO")[0] == '0');
+  if (!enabled) return 0;
+  std::vector<uint32_t> idx;
+  for (size_t i = 0; i < n; i++) if (codes[i] == BROTLI_DECODER_NEEDS_MORE_OUTPUT) idx.push_back((uint32_t)i);
+  if (idx.empty()) return 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const size_t group_limit = free_b / 2 > ((size_t)4 << 30) ? ((size_t)4 << 30) : free_b / 2;  // scratch per launch
+  CudaDev dev{c};
+  size_t k = 0;
+  while (k < idx.size()) {
+    std::vector<brotli_b200::ResumeState> arr;
+    std::vector<uint32_t> who;
+    size_t scratch = 0;
+    for (; k < idx.size(); k++) {
+      const uint32_t i = idx[k];
+      const uint8_t* p = in_bytes + in_off[i];
+      const size_t sz = (size_t)(in_off[i + 1] - in_off[i]);
+      const uint64_t cap = out_off[i + 1] - out_off[i];
+      // WBITS (src/decode.rs:152-187): the ring buffer is at most 1 << wbits, flush points are its multiples
+      uint32_t wbits = 16;
+      if (sz >= 1 && (p[0] & 1)) {
+        const uint32_t n3 = (p[0] >> 1) & 7;
+        if (n3) wbits = 17 + n3;
+        else { const uint32_t m = (p[0] >> 4) & 7; wbits = m == 1 ? (sz >= 2 ? (uint32_t)(p[1] & 63) : 30u) : (m ? 8 + m : 17); }
+      }
+      if (wbits > 30) wbits = 30;
+      const uint64_t ring = (uint64_t)1 << wbits;
+      const uint64_t need = (cap / ring + 1) * ring + 64;  // first flush point beyond the capacity
+      if (need > group_limit) continue;                      // no room for the scratch window: the first pass's answer stands
+      if (scratch + need + 16 > group_limit && !arr.empty()) break;
+      brotli_b200::ResumeState r;
+      memset(&r, 0, sizeof(r));
+      r.in = d_in + in_off[i]; r.in_size = sz;
+      r.out = (uint8_t*)(uintptr_t)scratch;  // offset for now
+      r.out_cap = need; r.budget = cap;
+      r.arena = nullptr; r.dict = d_dict; r.dict_size = dict_size; r.allow_large_window = 1;
+      arr.push_back(r); who.push_back(i);
+      scratch += (need + 15) & ~(uint64_t)15;
+    }
+    if (arr.empty()) continue;
+    CU_TRY(c->redo_out.reserve(scratch + 64));
+    for (auto& r : arr) r.out = (uint8_t*)c->redo_out.p + (uintptr_t)r.out;
+    int rc = dev.run(arr.data(), (uint32_t)arr.size(), nullptr, 0, nullptr, 0);
+    if (rc != 0) return rc;
+    for (size_t j = 0; j < arr.size(); j++) {
+      const brotli_b200::ResumeState& r = arr[j];
+      const uint32_t i = who[j];
+      const uint64_t cap = out_off[i + 1] - out_off[i];
+      if (r.hit_cap) continue;  // (cannot happen: the window reaches the flush point)
+      if (r.code < 0) { codes[i] = r.code; out_len[i] = r.flushed_now < cap ? r.flushed_now : cap; }
+      else if (r.code == BROTLI_DECODER_NEEDS_MORE_INPUT) { codes[i] = r.code; out_len[i] = r.decoded < cap ? r.decoded : cap; }
+      // NeedsMoreOutput at the flush point, or the stream ends beyond the capacity: NeedsMoreOutput with a full buffer stands
+    }
+  }
+  return 0;
 }
 
 // is_valid_slice_ptr, src/ffi/mod.rs:45-60
@@ -443,83 +578,15 @@ BrotliDecoderReturnInfo BrotliDecoderDecompressPrealloc(size_t encoded_size, con
   return BrotliDecoderDecompressWithReturnInfo(encoded_size, encoded_buffer, decoded_size, decoded_buffer);
 }
 
-// ---- streaming state: GPU-backed, re-submits the bytes received so far -----------------------
+// ---- streaming state: a device-resident session (brotli_b200_session.h) ----------------------
 struct BrotliDecoderStateStruct {
   brotli_alloc_func alloc_func;
   brotli_free_func free_func;
   void* opaque;
-  std::vector<uint8_t> input;    // every byte handed in so far that belongs to the stream
-  std::vector<uint8_t> output;   // decoded bytes of the stream so far
-  size_t taken;                  // bytes of `output` already handed to the caller
-  size_t consumed_reported;      // input bytes reported as consumed to the caller
-  int last_code;                 // BrotliDecoderErrorCode of the last decode
-  bool used, large_window, failed, finished;
+  brotli_b200::Session sess;     // windows of the stream in device memory, checkpoint, pending output
+  int session_device;            // CUDA device that owns the session buffers (-1: none yet)
   char error[256];
-  // streaming session on the device: the stream's bytes and everything decoded so far stay in device memory, and the
-  // kernel's ResumeState lets each call continue behind the last metablock boundary
-  uint8_t* d_in; size_t d_in_cap, d_in_size;
-  uint8_t* d_out; size_t d_out_cap;
-  uint8_t* d_meta;   // in_off[2] | out_off[2] | out_len | in_used | code, ResumeState at byte 128
-  // custom LZ77 dictionary of this state (BrotliState::new_with_custom_dictionary, src/state.rs:400-411)
-  std::vector<uint8_t> dict;
-  uint8_t* d_dict;   // device copy, 32 bytes of slack on either side
-  int session_device;  // CUDA device that owns the session buffers (-1: none yet)
 };
-
-constexpr size_t kSessionMetaBytes = 512, kSessionResumeAt = 128;
-// BROTLI_B200_STREAM_SESSION=0|1 overrides the default
-constexpr bool kStreamSessionsDefault = true;
-const bool g_stream_sessions = getenv("BROTLI_B200_STREAM_SESSION") ? getenv("BROTLI_B200_STREAM_SESSION")[0] != '0' : kStreamSessionsDefault;
-
-// Grow a session buffer, keeping its first `keep` bytes.
-static int session_grow(DeviceCtx* c, uint8_t** p, size_t* cap, size_t need, size_t keep) {
-  if (need <= *cap) return 0;
-  size_t want = need + need / 2 + 4096;
-  uint8_t* q = nullptr;
-  CU_TRY(cudaMalloc((void**)&q, want));
-  if (*p && keep) CU_TRY(cudaMemcpyAsync(q, *p, keep, cudaMemcpyDeviceToDevice, c->s_compute));
-  CU_TRY(cudaStreamSynchronize(c->s_compute));
-  if (*p) cudaFree(*p);
-  *p = q; *cap = want;
-  return 0;
-}
-
-// One decode of the session's stream so far: `fresh` bytes are appended to the device copy of the input, the exact
-// kernel continues from the session's ResumeState into the device output buffer (capacity out_cap), and the bytes
-// decoded beyond `have` (what the host already holds) come back in `suffix`.
-static int decode_session(DeviceCtx* c, BrotliDecoderStateStruct* s, const uint8_t* fresh, size_t n_fresh, size_t out_cap, size_t have,
-                          int32_t* code, uint64_t* decoded, uint64_t* used, std::vector<uint8_t>* suffix) {
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (!s->d_meta) {
-    CU_TRY(cudaMalloc((void**)&s->d_meta, kSessionMetaBytes));
-    CU_TRY(cudaMemsetAsync(s->d_meta, 0, kSessionMetaBytes, c->s_compute));
-  }
-  if (session_grow(c, &s->d_in, &s->d_in_cap, s->d_in_size + n_fresh + 16, s->d_in_size) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
-  if (session_grow(c, &s->d_out, &s->d_out_cap, out_cap + 16, have) != 0) return BROTLI_DECODER_ERROR_UNREACHABLE;
-  if (!s->dict.empty() && !s->d_dict) {
-    CU_TRY(cudaMalloc((void**)&s->d_dict, s->dict.size() + 64));
-    CU_TRY(cudaMemcpyAsync(s->d_dict + 32, s->dict.data(), s->dict.size(), cudaMemcpyHostToDevice, c->s_compute));
-  }
-  if (n_fresh) CU_TRY(cudaMemcpyAsync(s->d_in + s->d_in_size, fresh, n_fresh, cudaMemcpyHostToDevice, c->s_compute));
-  s->d_in_size += n_fresh;
-  uint64_t meta[4] = {0, (uint64_t)s->d_in_size, 0, (uint64_t)out_cap};
-  CU_TRY(cudaMemcpyAsync(s->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->s_compute));
-  uint64_t* m = (uint64_t*)s->d_meta;
-  int rc = decode_device(c, 1, s->d_in, m, s->d_out, m + 2, m + 4, (int32_t*)(m + 6), m + 5, s->large_window ? 1u : 0u, c->s_compute,
-                         s->d_dict ? s->d_dict + 32 : nullptr, s->dict.size(), (brotli_b200::ResumeState*)(s->d_meta + kSessionResumeAt));
-  if (rc != 0) return rc;
-  uint64_t res[3] = {0, 0, 0};  // out_len, in_used, code
-  CU_TRY(cudaMemcpyAsync(res, m + 4, sizeof(res), cudaMemcpyDeviceToHost, c->s_compute));
-  CU_TRY(cudaStreamSynchronize(c->s_compute));
-  *decoded = res[0]; *used = res[1]; *code = (int32_t)(uint32_t)res[2];
-  suffix->clear();
-  if (res[0] > have) {
-    suffix->resize((size_t)(res[0] - have));
-    CU_TRY(cudaMemcpyAsync(suffix->data(), s->d_out + have, suffix->size(), cudaMemcpyDeviceToHost, c->s_compute));
-    CU_TRY(cudaStreamSynchronize(c->s_compute));
-  }
-  return 0;
-}
 
 BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
   if ((alloc_func == nullptr) != (free_func == nullptr)) return nullptr;  // src/ffi/mod.rs:132-135
@@ -527,125 +594,90 @@ BrotliDecoderState* BrotliDecoderCreateInstance(brotli_alloc_func alloc_func, br
   if (!mem) return nullptr;
   BrotliDecoderStateStruct* s = new (mem) BrotliDecoderStateStruct();
   s->alloc_func = alloc_func; s->free_func = free_func; s->opaque = opaque;
-  s->taken = 0; s->consumed_reported = 0; s->last_code = 0;
-  s->used = false; s->large_window = false; s->failed = false; s->finished = false;
+  s->sess.large_window = false;  // src/ffi/mod.rs:127
+  s->session_device = -1;
   s->error[0] = 0;
-  s->d_in = nullptr; s->d_in_cap = 0; s->d_in_size = 0; s->d_out = nullptr; s->d_out_cap = 0; s->d_meta = nullptr; s->d_dict = nullptr; s->session_device = -1;
   return s;
 }
 
 void BrotliDecoderDestroyInstance(BrotliDecoderState* s) {
   if (!s) return;
-  if (s->d_in) cudaFree(s->d_in);
-  if (s->d_out) cudaFree(s->d_out);
-  if (s->d_meta) cudaFree(s->d_meta);
-  if (s->d_dict) cudaFree(s->d_dict);
+  if (s->session_device >= 0) {
+    DeviceCtx* c = &g_ctx[s->session_device];
+    std::lock_guard<std::mutex> lock(c->mu);
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(s->session_device);
+    CudaDev dev{c};
+    brotli_b200::SessionRunner<CudaDev>(dev).destroy(s->sess);
+    cudaSetDevice(prev);
+  }
   brotli_free_func f = s->free_func; void* opaque = s->opaque;
   s->~BrotliDecoderStateStruct();
   if (f) f(opaque, s); else free(s);
 }
 
 int BrotliDecoderSetParameter(BrotliDecoderState* s, BrotliDecoderParameter param, uint32_t value) {
-  if (!s || s->used) return 0;  // src/ffi/mod.rs:163-166
+  if (!s || s->sess.used || s->sess.stop != brotli_b200::Session::kFresh) return 0;  // src/ffi/mod.rs:163-166
   switch (param) {
     case BROTLI_DECODER_PARAM_DISABLE_RING_BUFFER_REALLOCATION: return 1;  // no ring buffer exists on the GPU path
-    case BROTLI_DECODER_PARAM_LARGE_WINDOW: s->large_window = value != 0; return 1;
+    case BROTLI_DECODER_PARAM_LARGE_WINDOW: s->sess.large_window = value != 0; return 1;
     default: return 0;
   }
 }
 
 static BrotliDecoderResult stream_fail(BrotliDecoderState* s, int code, const char* msg) {
-  s->failed = true; s->last_code = code;
+  s->sess.stop = brotli_b200::Session::kFailed; s->sess.code = code;
   strncpy(s->error, msg ? msg : error_name(code), sizeof(s->error) - 1);
   return BROTLI_DECODER_RESULT_ERROR;
 }
 
-static size_t stream_drain(BrotliDecoderState* s, size_t* available_out, uint8_t** next_out, size_t* total_out) {
-  size_t n = s->output.size() - s->taken;
-  if (n > *available_out) n = *available_out;
-  if (n) {
-    memcpy(*next_out, s->output.data() + s->taken, n);
-    *next_out += n; *available_out -= n; s->taken += n;
-  }
-  if (total_out) *total_out = s->taken;
-  return n;
+// n BrotliDecoderDecompressStream calls, one per state, served by ONE decode launch (src/ffi/mod.rs:389-463 per state).
+int BrotliB200DecoderDecompressStreamBatch(size_t n, BrotliDecoderState* const* states, size_t* available_in, const uint8_t** next_in,
+                                           size_t* available_out, uint8_t** next_out, size_t* total_out, BrotliDecoderResult* results) {
+  try {
+    if (n == 0) return 0;
+    if (!states || !available_in || !next_in || !available_out || !next_out || !results) { set_error("brotli_b200: null batch array"); return BROTLI_DECODER_ERROR_INVALID_ARGUMENTS; }
+    std::vector<brotli_b200::Session*> ss; std::vector<brotli_b200::StreamCall> cs; std::vector<size_t> who;
+    DeviceCtx* c = nullptr;
+    for (size_t i = 0; i < n; i++) {
+      BrotliDecoderState* s = states[i];
+      results[i] = BROTLI_DECODER_RESULT_ERROR;
+      if (!s) continue;
+      if ((available_in[i] && !next_in[i]) || (available_out[i] && !next_out[i])) { stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr); continue; }
+      if (!c) { c = acquire_ctx(); if (!c) { for (size_t j = 0; j < n; j++) if (states[j]) stream_fail(states[j], BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str()); return BROTLI_DECODER_ERROR_UNREACHABLE; } }
+      if (s->session_device < 0) s->session_device = c->device;
+      if (s->session_device != c->device) {  // the session's buffers live on the device of its first call
+        stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, "brotli_b200: decoder state used from another CUDA device"); continue;
+      }
+      ss.push_back(&s->sess);
+      cs.push_back(brotli_b200::StreamCall{&available_in[i], &next_in[i], &available_out[i], &next_out[i], total_out ? &total_out[i] : nullptr, -1});
+      who.push_back(i);
+    }
+    if (ss.empty()) return 0;
+    int rc;
+    {
+      std::lock_guard<std::mutex> lock(c->mu);
+      CudaDev dev{c};
+      rc = brotli_b200::SessionRunner<CudaDev>(dev).stream_calls(ss.data(), cs.data(), ss.size(), BROTLI_DECODER_ERROR_UNREACHABLE);
+    }
+    for (size_t k = 0; k < who.size(); k++) {
+      BrotliDecoderState* s = states[who[k]];
+      results[who[k]] = (BrotliDecoderResult)cs[k].result;
+      if (cs[k].result == BROTLI_DECODER_RESULT_ERROR && !s->error[0])
+        strncpy(s->error, s->sess.code == BROTLI_DECODER_ERROR_UNREACHABLE && rc != 0 ? tl_error.c_str() : error_name(s->sess.code), sizeof(s->error) - 1);
+    }
+    return rc;
+  } catch (...) { set_error("brotli_b200: exception"); return BROTLI_DECODER_ERROR_UNREACHABLE; }
 }
 
 BrotliDecoderResult BrotliDecoderDecompressStream(BrotliDecoderState* s, size_t* available_in, const uint8_t** next_in,
                                                   size_t* available_out, uint8_t** next_out, size_t* total_out) {
   if (!s) return BROTLI_DECODER_RESULT_ERROR;
   try {
-    if (!available_in || !next_in || !available_out || !next_out) return stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr);
-    if ((*available_in && !*next_in) || (*available_out && !*next_out)) return stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr);
-    if (s->failed) return BROTLI_DECODER_RESULT_ERROR;  // sticky, src/decode.rs:2796-2798
-    if (s->taken < s->output.size()) {  // hand out what is pending before touching new input
-      stream_drain(s, available_out, next_out, total_out);
-      if (s->taken < s->output.size()) return BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT;
-    }
-    if (s->finished) { if (total_out) *total_out = s->taken; return BROTLI_DECODER_RESULT_SUCCESS; }
-    if (*available_in == 0 && s->used && s->last_code == BROTLI_DECODER_NEEDS_MORE_INPUT) {
-      if (total_out) *total_out = s->taken;
-      return BROTLI_DECODER_RESULT_NEEDS_MORE_INPUT;
-    }
-    const size_t fresh = *available_in;
-    s->input.insert(s->input.end(), *next_in, *next_in + fresh);
-    if (fresh) s->used = true;
-    // decode everything received so far; grow the output until it fits
-    size_t cap = s->output.capacity() > (1u << 16) ? s->output.capacity() : (1u << 16);
-    if (cap < s->input.size() * 6) cap = s->input.size() * 6;
-    BrotliDecoderReturnInfo r;
-    uint64_t used = 0;
-    std::vector<uint8_t> buf;
-    if (g_stream_sessions && s->input.size() != 0 && s->input.size() < ((uint64_t)1 << 32)) {
-      // device-resident session: only the fresh bytes go up, only the new output comes down, and the kernel
-      // continues behind the last complete metablock
-      DeviceCtx* c = acquire_ctx();
-      if (!c) return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str());
-      if (s->session_device < 0) s->session_device = c->device;
-      if (s->session_device != c->device)  // the session's buffers live on the device of its first call
-        return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, "brotli_b200: decoder state used from another CUDA device");
-      if (cap < s->d_out_cap && s->d_out_cap > 16) cap = s->d_out_cap - 16;
-      size_t n_fresh = fresh;
-      const uint8_t* fresh_ptr = s->input.data() + (s->input.size() - fresh);
-      if (s->d_in_size + fresh != s->input.size()) { fresh_ptr = s->input.data() + s->d_in_size; n_fresh = s->input.size() - s->d_in_size; }
-      for (;;) {
-        int32_t code = 0; uint64_t decoded = 0;
-        int rc = decode_session(c, s, fresh_ptr, n_fresh, cap, s->output.size(), &code, &decoded, &used, &buf);
-        if (rc != 0) return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, tl_error.c_str());
-        n_fresh = 0;
-        if (!buf.empty()) s->output.insert(s->output.end(), buf.begin(), buf.end());
-        r = make_info(code == 1 ? 1 : (code == 2 ? 2 : (code == 3 ? 3 : 0)), code, (size_t)decoded, nullptr);
-        if (r.code != BROTLI_DECODER_NEEDS_MORE_OUTPUT) break;
-        if (cap >= ((size_t)1 << 31)) break;
-        cap *= 4;
-      }
-      s->used = true;
-    } else {
-    for (;;) {
-      buf.resize(cap);
-      r = one_shot(s->input.data(), s->input.size(), buf.data(), cap, s->large_window ? 1u : 0u, &used, s->dict.empty() ? nullptr : s->dict.data(), s->dict.size());
-      if (r.code != BROTLI_DECODER_NEEDS_MORE_OUTPUT) break;
-      if (cap >= ((size_t)1 << 31)) break;
-      cap *= 4;
-    }
-    if (r.code == BROTLI_DECODER_ERROR_UNREACHABLE && strncmp(r.error, "brotli_b200", 11) == 0) return stream_fail(s, r.code, r.error);
-    if (s->input.size()) s->used = true;
-    // new suffix of the output
-    if (r.decoded_size > s->output.size()) s->output.insert(s->output.end(), buf.data() + s->output.size(), buf.data() + r.decoded_size);
-    }
-    s->last_code = r.code;
-    // input accounting: a finished stream leaves trailing bytes unconsumed (src/ffi/mod.rs:452-453)
-    size_t consumed_total = s->input.size();
-    if (r.code == BROTLI_DECODER_SUCCESS) { consumed_total = (size_t)used; s->finished = true; s->input.resize(consumed_total); }
-    const size_t newly = consumed_total > s->consumed_reported ? consumed_total - s->consumed_reported : 0;
-    const size_t adv = newly < fresh ? newly : fresh;
-    *next_in += adv; *available_in -= adv; s->consumed_reported += adv;
-    stream_drain(s, available_out, next_out, total_out);
-    if (r.code < 0) return stream_fail(s, r.code, nullptr);
-    if (s->taken < s->output.size()) return BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT;
-    if (r.code == BROTLI_DECODER_SUCCESS) return BROTLI_DECODER_RESULT_SUCCESS;
-    if (r.code == BROTLI_DECODER_NEEDS_MORE_OUTPUT) return stream_fail(s, BROTLI_DECODER_ERROR_ALLOC_RING_BUFFER_1, nullptr);
-    return BROTLI_DECODER_RESULT_NEEDS_MORE_INPUT;
+    if (!available_in || !next_in || !available_out || !next_out) return stream_fail(s, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, nullptr);  // src/ffi/mod.rs:397-407
+    BrotliDecoderResult r = BROTLI_DECODER_RESULT_ERROR;
+    BrotliDecoderState* one[1] = {s};
+    BrotliB200DecoderDecompressStreamBatch(1, one, available_in, next_in, available_out, next_out, total_out, &r);
+    return r;
   } catch (const std::exception& e) {
     return stream_fail(s, BROTLI_DECODER_ERROR_UNREACHABLE, e.what());
   } catch (...) {
@@ -660,21 +692,25 @@ BrotliDecoderResult BrotliDecoderDecompressStreaming(BrotliDecoderState* s, size
   return BrotliDecoderDecompressStream(s, available_in, &in, available_out, &out, nullptr);
 }
 
-int BrotliDecoderHasMoreOutput(const BrotliDecoderState* s) { return s && !s->failed && s->taken < s->output.size() ? 1 : 0; }
+int BrotliDecoderHasMoreOutput(const BrotliDecoderState* s) {
+  return s && s->sess.stop != brotli_b200::Session::kFailed && s->sess.pending_bytes() != 0 ? 1 : 0;
+}
 
 const uint8_t* BrotliDecoderTakeOutput(BrotliDecoderState* s, size_t* size) {
   if (!s || !size) return nullptr;
-  size_t avail = s->output.size() - s->taken;
-  size_t n = *size == 0 ? avail : (*size < avail ? *size : avail);
-  if (s->failed || n == 0) { *size = 0; return nullptr; }
-  const uint8_t* p = s->output.data() + s->taken;
-  s->taken += n; *size = n;
+  const size_t avail = s->sess.pending_bytes();
+  const size_t n = *size == 0 ? avail : (*size < avail ? *size : avail);
+  if (s->sess.stop == brotli_b200::Session::kFailed || n == 0) { *size = 0; return nullptr; }
+  const uint8_t* p = s->sess.pending.data() + s->sess.pending_off;  // stays valid until the next call on this state
+  s->sess.pending_off += n; s->sess.delivered += n; *size = n;
   return p;
 }
 
-int BrotliDecoderIsUsed(const BrotliDecoderState* s) { return s && s->used ? 1 : 0; }
-int BrotliDecoderIsFinished(const BrotliDecoderState* s) { return s && s->finished && !s->failed && s->taken == s->output.size() ? 1 : 0; }
-BrotliDecoderErrorCode BrotliDecoderGetErrorCode(const BrotliDecoderState* s) { return (BrotliDecoderErrorCode)(s ? s->last_code : 0); }
+int BrotliDecoderIsUsed(const BrotliDecoderState* s) { return s && s->sess.used ? 1 : 0; }
+int BrotliDecoderIsFinished(const BrotliDecoderState* s) {
+  return s && s->sess.stop == brotli_b200::Session::kDone && s->sess.pending_bytes() == 0 ? 1 : 0;
+}
+BrotliDecoderErrorCode BrotliDecoderGetErrorCode(const BrotliDecoderState* s) { return (BrotliDecoderErrorCode)(s ? s->sess.code : 0); }
 const char* BrotliDecoderGetErrorString(const BrotliDecoderState* s) { return s && s->error[0] ? s->error : ""; }
 const char* BrotliDecoderErrorString(BrotliDecoderErrorCode c) { return error_name((int)c); }
 uint32_t BrotliDecoderVersion(void) { return 0x1000f00; }  // src/ffi/mod.rs:588-590
@@ -749,9 +785,9 @@ int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in, const size_t* 
 // Streaming form: the dictionary belongs to the state, as in Decompressor::new_with_custom_dict (src/reader.rs:105) and
 // DecompressorWriter::new_with_custom_dictionary (src/writer.rs:117).  Only before the first input byte.
 int BrotliB200DecoderSetCustomDictionary(BrotliDecoderState* s, const uint8_t* dictionary, size_t dictionary_size) {
-  if (!s || s->used || (dictionary_size && !dictionary)) return 0;
-  try { s->dict.assign(dictionary, dictionary + dictionary_size); } catch (...) { return 0; }
-  if (s->d_dict) { cudaFree(s->d_dict); s->d_dict = nullptr; }
+  if (!s || s->sess.used || s->sess.stop != brotli_b200::Session::kFresh || s->sess.d_dict || (dictionary_size && !dictionary)) return 0;
+  try { s->sess.dict.assign(dictionary, dictionary + dictionary_size); } catch (...) { return 0; }
+  s->sess.large_window = true;  // BrotliState::new_with_custom_dictionary, src/state.rs:400-411
   return 1;
 }
 
@@ -826,7 +862,7 @@ int BrotliB200ResidentWarps(void) {
   return c ? c->ctas * brotli_b200::kWarpsPerCta : -1;
 }
 
-void BrotliB200Shutdown(void) {
+void BrotliB200Shutdown(void) {  // (open decoder states keep their own device buffers: destroy them first)
   for (int d = 0; d < kMaxDevices; d++) {
     DeviceCtx* c = &g_ctx[d];
     std::lock_guard<std::mutex> lock(c->mu);
@@ -837,6 +873,7 @@ void BrotliB200Shutdown(void) {
     if (c->xdict) cudaFree(c->xdict);
     c->xdict = nullptr;
     c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release(); c->order.release();
+    c->sess_states.release(); c->sess_pieces.release(); c->sess_blob.release(); c->redo_out.release(); c->cdict.release();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
     cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
     for (auto& t : c->ev_t) for (auto& e : t) if (e) { cudaEventDestroy(e); e = nullptr; }

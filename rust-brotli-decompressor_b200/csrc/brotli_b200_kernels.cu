@@ -49,12 +49,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
     if (lane == 0) t = atomicAdd(a.ticket, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= n) break;
+    if (a.sessions) {  // streaming sessions: stream t is described by (and reports into) its ResumeState
+      decode_session(d, a.sessions + t);
+      continue;
+    }
     const uint32_t i = a.order ? a.order[t] : t;
     const uint64_t in0 = a.in_off[i], in1 = a.in_off[i + 1];
     const uint64_t out0 = a.out_off[i], out1 = a.out_off[i + 1];
     uint64_t decoded = 0, used = 0;
     const int code = decode_stream(d, a.in + in0, in1 - in0, a.out + out0, out1 - out0, a.large_window, &decoded, &used, a.custom_dict,
-                                   a.custom_dict_size, n == 1 ? a.resume : nullptr);
+                                   a.custom_dict_size, nullptr);
     if (lane == 0) {
       a.out_len[i] = decoded;
       a.codes[i] = code;
@@ -86,6 +90,21 @@ __global__ void brotli_checksum_batch_kernel(uint32_t n, const uint8_t* bytes, c
   }
 }
 
+// Moves the pieces of a session launch: fresh input from the launch's staging blob to the sessions' input buffers
+// before the decode, new output from the sessions' windows to the staging blob after it.  One CTA per piece.
+__global__ void brotli_session_copy_kernel(const SessionCopy* pieces, uint32_t n) {
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const SessionCopy c = pieces[i];
+    for (uint64_t j = threadIdx.x; j < c.n; j += blockDim.x) c.dst[j] = c.src[j];
+  }
+}
+
+cudaError_t launch_session_copy(const SessionCopy* d_pieces, uint32_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  brotli_session_copy_kernel<<<n < 1184 ? n : 1184, 256, 0, stream>>>(d_pieces, n);
+  return cudaGetLastError();
+}
+
 size_t resume_state_bytes() { return sizeof(ResumeState); }
 
 size_t arena_bytes_per_warp() { return ArenaLayout::kBytes; }
@@ -102,6 +121,11 @@ int query_resident_ctas(int device) {
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
+  // a small batch whose size the host knows does not need every resident CTA (launch and drain cost)
+  if (!a.n_ptr) {
+    const int need = (int)((a.n + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (need < ctas) ctas = need < 1 ? 1 : need;
+  }
   brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, kDynamicSharedBytes, stream>>>(a);
   return cudaGetLastError();
 }

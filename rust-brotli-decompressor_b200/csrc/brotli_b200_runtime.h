@@ -30,7 +30,8 @@ constexpr uint32_t kDynamicSharedBytes = kWarpsPerCta * kWarpSharedBytes;
 #endif
 constexpr int kLaneWarpsPerCta = BROTLI_B200_LANE_WARPS_PER_CTA;
 
-struct ResumeState;  // brotli_decode_core.cuh: decoder state at a metablock boundary (streaming sessions)
+struct ResumeState;  // brotli_b200_session_types.h: device-side record of a streaming session (buffers, results, checkpoint)
+struct SessionCopy;  // brotli_b200_session_types.h: one piece of a session launch's staging traffic
 
 // One launch decodes streams [0, n) of a packed batch (see decode.h, "Packed layout").
 struct BatchArgs {
@@ -50,7 +51,7 @@ struct BatchArgs {
   const uint32_t* n_ptr;    // optional: the stream count lives in device memory (fallback pass over a bail list)
   const uint8_t* custom_dict;  // optional custom LZ77 dictionary shared by the batch (device memory), src/state.rs:400-411
   uint64_t custom_dict_size;
-  ResumeState* resume;      // optional, n == 1 only: streaming session, see ResumeState (device memory, zeroed = start of stream)
+  ResumeState* sessions;    // optional [n]: streaming sessions -- stream t is wholly described by sessions[t] (device memory)
 };
 
 // Extra arguments of the lane kernel.
@@ -69,6 +70,7 @@ size_t arena_bytes_per_warp();
 size_t resume_state_bytes();
 int query_resident_ctas(int device);
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream);
+cudaError_t launch_session_copy(const SessionCopy* d_pieces, uint32_t n, cudaStream_t stream);
 size_t lane_arena_bytes_per_lane();
 uint32_t lane_slot_bytes(int warps);
 size_t order_temp_bytes(uint32_t n);

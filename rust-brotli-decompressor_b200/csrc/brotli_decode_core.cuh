@@ -27,6 +27,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include "brotli_b200_session_types.h"
+
 #if defined(BROTLI_B200_HOSTSIM)
 #include <string.h>
 #define BD_DEV inline
@@ -306,6 +308,12 @@ struct Decoder {
   uint64_t flushed;       // bytes the reference would have handed to the caller before a fatal error
   uint64_t discarded;     // literals decoded past the capacity while a command overshoots MLEN (SAFE only)
   uint32_t full_ring;
+  // streaming sessions / exact re-decodes: the caller can take `budget` output bytes in total; a ring-buffer flush point
+  // beyond it stops the decoder there with NeedsMoreOutput, as WriteRingBuffer does (src/decode.rs:1693-1738)
+  uint64_t budget;
+  uint32_t at_flush;      // stopped at next_flush for lack of budget
+  uint32_t is_last;       // ISLAST of the current metablock
+  uint32_t tables_used;   // entries of the arena's table space the current metablock uses
   // last four distances, d0 most recent (src/state.rs:295-296)
   int32_t d0, d1, d2, d3;
   // block-split state per category: literal, command, distance (src/state.rs:146-154)
@@ -768,6 +776,7 @@ BD_DEV int32_t read_distance(Decoder& d, uint32_t& push_to_ring) {
 // kRetryFast so that long streams drop back to the fast loop.
 BD_DEV int flush_event(Decoder& d) {  // WriteRingBuffer at pos >= ringbuffer_size, src/decode.rs:1693-1738
   if (d.mlen < 0) return kErrBlockLength1;
+  if (d.next_flush > d.budget) { d.at_flush = 1; return kNeedsMoreOutput; }  // num_written < to_write, :1718-1729
   d.flushed = d.next_flush;
   d.next_flush = d.full_ring ? d.next_flush + d.rbsize : ~(uint64_t)0;
   return kSuccess;
@@ -1398,20 +1407,30 @@ BD_DEV void build_dist_lut(Decoder& d) {
   d.use_dist_lut = hw::all(ok) ? 1u : 0u;
 }
 
-// HuffmanTreeGroupDecode, src/decode.rs:1130-1219.  Each table is built in the global arena; while
-// it fits (keeping `reserve` entries free for the groups that follow) it is then copied into the
-// warp's shared-memory table storage and ptrs[i] points there instead.
-BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint32_t max_symbol, uint32_t* tree_off, uint32_t& next_off,
-                           const uint16_t** ptrs, uint32_t reserve) {
-  const uint32_t lane = hw::lane();
+// HuffmanTreeGroupDecode, src/decode.rs:1130-1219.  Each table is built in the arena; tree_off[i] is its offset in
+// the arena's table space.
+BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint32_t max_symbol, uint32_t* tree_off, uint32_t& next_off) {
   for (uint32_t i = 0; i < ntrees; i++) {
     uint32_t tsize = 0;
     const uint32_t room = (uint32_t)(ArenaLayout::kTableEntries - next_off);
-    uint16_t* gtab = d.tables + next_off;
-    int r = read_huffman_code(d, alphabet, max_symbol, gtab, room, tsize);
+    int r = read_huffman_code(d, alphabet, max_symbol, d.tables + next_off, room, tsize);
     if (r != kSuccess) return r;
     tree_off[i] = next_off;
     next_off += tsize;
+  }
+  hw::syncwarp();
+  return kSuccess;
+}
+
+// Tables of one group -> ptrs[]: while a table fits (keeping `reserve` entries free for the groups that follow) it is
+// copied into the warp's shared-memory table storage and ptrs[i] points there, else ptrs[i] points into the arena.
+BD_DEV void promote_tree_group(Decoder& d, uint32_t ntrees, const uint32_t* tree_off, uint32_t group_end, const uint16_t** ptrs,
+                               uint32_t reserve) {
+  const uint32_t lane = hw::lane();
+  for (uint32_t i = 0; i < ntrees; i++) {
+    const uint32_t off = tree_off[i];
+    const uint32_t tsize = (i + 1 < ntrees ? tree_off[i + 1] : group_end) - off;
+    const uint16_t* gtab = d.tables + off;
     const uint16_t* where = gtab;
     if (d.stab_used + tsize + reserve <= d.stab_cap) {
       uint16_t* stab = d.stab + d.stab_used;
@@ -1424,7 +1443,47 @@ BD_DEV int read_tree_group(Decoder& d, uint32_t ntrees, uint32_t alphabet, uint3
     ptrs[i] = where;
   }
   hw::syncwarp();
-  return kSuccess;
+}
+
+// Where the current metablock's lookup structures live (shared memory when small enough, else the arena), from what
+// the header parse left in the arena: context maps, tree offsets, tables.  Also what a streaming session re-creates
+// when it continues inside a metablock (the arena belongs to the session; shared memory does not survive a launch).
+BD_COLD void setup_metablock_views(Decoder& d) {
+  WarpShared* sh = d.sh;
+  const uint16_t** lit_ptrs = d.n_lit_trees <= WarpShared::kLitPtrs ? sh->lit_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrLit);
+  const uint16_t** cmd_ptrs = d.nbt_c <= WarpShared::kCmdPtrs ? sh->cmd_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrCmd);
+  const uint16_t** dist_ptrs = d.n_dist_trees <= WarpShared::kDistPtrs ? sh->dist_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrDist);
+  d.lit_ptrs = lit_ptrs; d.cmd_ptrs = cmd_ptrs; d.dist_ptrs = dist_ptrs;
+  d.map_lit = d.ctx_map_lit(); d.map_dist = d.ctx_map_dist();
+  const uint32_t lane = hw::lane();
+  if ((d.nbt_l << 6) <= WarpShared::kLitMapBytes) {
+    for (uint32_t i = lane; i < (d.nbt_l << 6); i += hw::kWarp) sh->lit_map[i] = d.ctx_map_lit()[i];
+    d.map_lit = sh->lit_map;
+  }
+  if ((d.nbt_d << 2) <= WarpShared::kDistMapBytes) {
+    for (uint32_t i = lane; i < (d.nbt_d << 2); i += hw::kWarp) sh->dist_map[i] = d.ctx_map_dist()[i];
+    d.map_dist = sh->dist_map;
+  }
+  d.stab_used = 0;
+  d.n_unpromoted = 0;
+  const uint32_t reserve_dist = (d.n_dist_trees < 8 ? d.n_dist_trees : 8u) * 256u;
+  const uint32_t reserve_cmd = (d.nbt_c < 2 ? d.nbt_c : 2u) * 1024u;
+  promote_tree_group(d, d.n_lit_trees, d.tree_off_lit(), d.tree_off_cmd()[0], lit_ptrs, reserve_cmd + reserve_dist);
+  promote_tree_group(d, d.nbt_c, d.tree_off_cmd(), d.tree_off_dist()[0], cmd_ptrs, reserve_dist);
+  promote_tree_group(d, d.n_dist_trees, d.tree_off_dist(), d.tables_used, dist_ptrs, 0);
+  hw::syncwarp();
+  prepare_literal_decoding(d);
+  d.dist_slice = d.rbt_d1 << 2;
+  refresh_cur_dist(d);
+  d.cmd_tree = d.cmd_ptrs[d.rbt_c1];
+  // shared-space mirrors for process_commands_shared
+  d.all_shared = d.n_unpromoted == 0 && d.map_lit == sh->lit_map && d.map_dist == sh->dist_map && lit_ptrs == sh->lit_ptrs &&
+                 cmd_ptrs == sh->cmd_ptrs && dist_ptrs == sh->dist_ptrs;
+  if (d.all_shared) {
+    for (uint32_t i = lane; i < d.n_lit_trees; i += hw::kWarp) sh->lit_s[i] = hw::to_sref(lit_ptrs[i]);
+  }
+  build_dist_lut(d);
+  hw::syncwarp();
 }
 
 // Everything between MLEN and the first command of a compressed metablock.
@@ -1448,44 +1507,14 @@ BD_COLD int read_compressed_metablock_header(Decoder& d) {
   d.dist_max_symbol = d.large_window ? max_distance_symbol(num_direct_codes, d.npostfix) : d.dist_alphabet;
   if ((r = decode_context_map(d, d.nbt_d << 2, d.ctx_map_dist(), d.n_dist_trees)) != kSuccess) return r;
   if (br.overrun()) return kNeedsMoreInput;
-  // where this metablock's lookup structures live: shared memory when small enough, else the arena
-  WarpShared* sh = d.sh;
-  const uint16_t** lit_ptrs = d.n_lit_trees <= WarpShared::kLitPtrs ? sh->lit_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrLit);
-  const uint16_t** cmd_ptrs = d.nbt_c <= WarpShared::kCmdPtrs ? sh->cmd_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrCmd);
-  const uint16_t** dist_ptrs = d.n_dist_trees <= WarpShared::kDistPtrs ? sh->dist_ptrs : (const uint16_t**)(d.arena + ArenaLayout::kPtrDist);
-  d.lit_ptrs = lit_ptrs; d.cmd_ptrs = cmd_ptrs; d.dist_ptrs = dist_ptrs;
-  d.map_lit = d.ctx_map_lit(); d.map_dist = d.ctx_map_dist();
-  const uint32_t lane = hw::lane();
-  if ((d.nbt_l << 6) <= WarpShared::kLitMapBytes) {
-    for (uint32_t i = lane; i < (d.nbt_l << 6); i += hw::kWarp) sh->lit_map[i] = d.ctx_map_lit()[i];
-    d.map_lit = sh->lit_map;
-  }
-  if ((d.nbt_d << 2) <= WarpShared::kDistMapBytes) {
-    for (uint32_t i = lane; i < (d.nbt_d << 2); i += hw::kWarp) sh->dist_map[i] = d.ctx_map_dist()[i];
-    d.map_dist = sh->dist_map;
-  }
-  d.stab_used = 0;
-  d.n_unpromoted = 0;
-  const uint32_t reserve_dist = (d.n_dist_trees < 8 ? d.n_dist_trees : 8u) * 256u;
-  const uint32_t reserve_cmd = (d.nbt_c < 2 ? d.nbt_c : 2u) * 1024u;
   uint32_t next_off = 0;
-  if ((r = read_tree_group(d, d.n_lit_trees, 256, 256, d.tree_off_lit(), next_off, lit_ptrs, reserve_cmd + reserve_dist)) != kSuccess) return r;
-  if ((r = read_tree_group(d, d.nbt_c, 704, 704, d.tree_off_cmd(), next_off, cmd_ptrs, reserve_dist)) != kSuccess) return r;
-  if ((r = read_tree_group(d, d.n_dist_trees, d.dist_alphabet, d.dist_max_symbol, d.tree_off_dist(), next_off, dist_ptrs, 0)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.n_lit_trees, 256, 256, d.tree_off_lit(), next_off)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.nbt_c, 704, 704, d.tree_off_cmd(), next_off)) != kSuccess) return r;
+  if ((r = read_tree_group(d, d.n_dist_trees, d.dist_alphabet, d.dist_max_symbol, d.tree_off_dist(), next_off)) != kSuccess) return r;
   if (br.overrun()) return kNeedsMoreInput;
+  d.tables_used = next_off;
   hw::syncwarp();
-  prepare_literal_decoding(d);
-  d.dist_slice = 0;
-  refresh_cur_dist(d);
-  d.cmd_tree = d.cmd_ptrs[0];
-  // shared-space mirrors for process_commands_shared
-  d.all_shared = d.n_unpromoted == 0 && d.map_lit == sh->lit_map && d.map_dist == sh->dist_map && lit_ptrs == sh->lit_ptrs &&
-                 cmd_ptrs == sh->cmd_ptrs && dist_ptrs == sh->dist_ptrs;
-  if (d.all_shared) {
-    for (uint32_t i = lane; i < d.n_lit_trees; i += hw::kWarp) sh->lit_s[i] = hw::to_sref(lit_ptrs[i]);
-  }
-  build_dist_lut(d);
-  hw::syncwarp();
+  setup_metablock_views(d);
   d.state = kCmdBegin;
   return kSuccess;
 }
@@ -1541,22 +1570,30 @@ BD_COLD int copy_uncompressed(Decoder& d) {
 }
 
 // ======================= stream driver (src/decode.rs:2779-3403) =======================
-// Decoder state at a metablock boundary: what BrotliState carries from one BrotliDecompressStream call to the
-// next once a metablock is complete (src/state.rs:156-278: bit position, output position, last distances, window
-// and ring-buffer geometry).  A streaming session keeps its input and output in device memory; each call decodes
-// from the last boundary the previous call reached instead of from the first byte.  All zero = start of stream.
-struct ResumeState {
-  uint64_t bitpos;        // bits of the stream consumed up to the boundary
-  uint64_t rbsize, next_flush, flushed;
-  uint32_t valid;
-  uint32_t pos;
-  int32_t d0, d1, d2, d3;
-  uint32_t wbits, large_window, rb_allocated, full_ring;
-};
+// (ResumeState -- the device-side record of a streaming session -- and SessionCopy: brotli_b200_session_types.h)
+BD_DEV void save_checkpoint(Decoder& d, ResumeState* rs, uint32_t kind) {
+  hw::syncwarp();
+  if (hw::lane() == 0) {
+    rs->kind = kind;
+    rs->bitpos = d.br.bitpos() - 8 * (uint64_t)d.br.lead;
+    rs->rbsize = d.rbsize; rs->next_flush = d.next_flush; rs->flushed = d.flushed;
+    rs->pos = d.pos; rs->mlen = d.mlen; rs->d0 = d.d0; rs->d1 = d.d1; rs->d2 = d.d2; rs->d3 = d.d3;
+    rs->wbits = d.wbits; rs->large_window = d.large_window; rs->rb_allocated = d.rb_allocated; rs->full_ring = d.full_ring;
+    rs->is_last = d.is_last;
+    if (kind == 2) {
+      rs->nbt_l = d.nbt_l; rs->nbt_c = d.nbt_c; rs->nbt_d = d.nbt_d; rs->bl_l = d.bl_l; rs->bl_c = d.bl_c; rs->bl_d = d.bl_d;
+      rs->rbt_l0 = d.rbt_l0; rs->rbt_l1 = d.rbt_l1; rs->rbt_c0 = d.rbt_c0; rs->rbt_c1 = d.rbt_c1; rs->rbt_d0 = d.rbt_d0; rs->rbt_d1 = d.rbt_d1;
+      rs->n_lit_trees = d.n_lit_trees; rs->n_dist_trees = d.n_dist_trees; rs->npostfix = d.npostfix; rs->ndirect = d.ndirect;
+      rs->dist_alphabet = d.dist_alphabet; rs->dist_max_symbol = d.dist_max_symbol; rs->tables_used = d.tables_used;
+      rs->state = d.state; rs->ins_rem = d.ins_rem; rs->copy_len = d.copy_len; rs->implicit_dist = d.implicit_dist; rs->dist_ctx = d.dist_ctx;
+    }
+  }
+  hw::syncwarp();
+}
 
 // Returns the BrotliDecoderErrorCode; *decoded_size follows the reference's flush rules:
-// success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity, fatal -> only
-// what the ring buffer had flushed (multiples of its size).
+// success / NeedsMoreInput -> everything decoded, NeedsMoreOutput -> capacity (or the flush point the budget of a
+// session cannot pass), fatal -> only what the ring buffer had flushed (multiples of its size).
 BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint32_t allow_large_window,
                          uint64_t* decoded_size, uint64_t* in_used, const uint8_t* custom_dict = nullptr, uint64_t custom_dict_size = 0,
                          ResumeState* resume = nullptr) {
@@ -1567,15 +1604,19 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   d.pos = 0; d.mlen = 0; d.rb_allocated = 0; d.rbsize = 0; d.next_flush = ~(uint64_t)0; d.flushed = 0; d.full_ring = 0; d.discarded = 0;
   d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
   d.large_window = 0;
+  d.budget = resume ? resume->budget : ~(uint64_t)0;
+  d.at_flush = 0; d.is_last = 0; d.tables_used = 0;
+  const uint32_t enter = resume ? resume->kind : 0u;  // where this launch picks the stream up
   int result;
   do {
     if (in_size >= ((uint64_t)1 << 32)) { result = kErrInvalidArguments; break; }  // src/decode.rs:2799-2801
-    if (in_size == 0) { result = kNeedsMoreInput; break; }
-    if (resume && resume->valid) {  // continue behind the last metablock a previous call of this session completed
+    if (in_size == 0 && enter == 0) { result = kNeedsMoreInput; break; }
+    if (enter != 0) {  // continue from the session's checkpoint
       d.wbits = resume->wbits; d.large_window = resume->large_window;
       d.pos = resume->pos; d.d0 = resume->d0; d.d1 = resume->d1; d.d2 = resume->d2; d.d3 = resume->d3;
       d.rb_allocated = resume->rb_allocated; d.full_ring = resume->full_ring;
       d.rbsize = resume->rbsize; d.next_flush = resume->next_flush; d.flushed = resume->flushed;
+      d.mlen = resume->mlen; d.is_last = resume->is_last;
       br.seek_byte(resume->bitpos >> 3);
       br.skip<false>((uint32_t)(resume->bitpos & 7));
     } else
@@ -1605,89 +1646,103 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
     d.cdict_size = custom_dict_size > d.max_backward ? d.max_backward : (uint32_t)custom_dict_size;
     d.cdict = custom_dict + (custom_dict_size - d.cdict_size);
     d.cdict_limit = (int64_t)d.max_backward - (int64_t)custom_dict_size;
+    uint32_t inside = enter >= 2 ? enter : 0u;  // 2 / 3: the first pass of the loop continues inside a metablock
     for (;;) {  // metablocks
-      // DecodeMetaBlockLength, src/decode.rs:243-372
-      const uint32_t is_last = br.read<false>(1);
       uint32_t is_uncompressed = 0, is_metadata = 0;
-      d.mlen = 0;
       result = kSuccess;
-      if (is_last && br.read<false>(1)) {
-        // ISLASTEMPTY: nothing else in this metablock
-      } else {
-        const uint32_t nib = br.read<false>(2);
-        if (nib == 3) {
-          is_metadata = 1;
-          if (br.read<false>(1) != 0) { result = kErrReserved; }
-          else {
-            const uint32_t nbytes = br.read<false>(2);
-            uint32_t v = 0;
-            for (uint32_t i = 0; i < nbytes; i++) {
-              const uint32_t b = br.read<false>(8);
-              if (i + 1 == nbytes && nbytes > 1 && b == 0) { result = kErrExuberantMetaNibble; break; }
-              v |= b << (i * 8);
-            }
-            if (nbytes != 0) d.mlen = (int32_t)v + 1;
-          }
+      if (inside == 0) {
+        // DecodeMetaBlockLength, src/decode.rs:243-372
+        const uint32_t is_last = br.read<false>(1);
+        d.is_last = is_last;
+        d.mlen = 0;
+        if (is_last && br.read<false>(1)) {
+          // ISLASTEMPTY: nothing else in this metablock
         } else {
-          const uint32_t nn = nib + 4;
-          uint32_t v = 0;
-          for (uint32_t i = 0; i < nn; i++) {
-            const uint32_t b = br.read<false>(4);
-            if (i + 1 == nn && nn > 4 && b == 0) { result = kErrExuberantNibble; break; }
-            v |= b << (i * 4);
-          }
-          if (result == kSuccess) {
-            if (!is_last) is_uncompressed = br.read<false>(1);
-            d.mlen = (int32_t)v + 1;
+          const uint32_t nib = br.read<false>(2);
+          if (nib == 3) {
+            is_metadata = 1;
+            if (br.read<false>(1) != 0) { result = kErrReserved; }
+            else {
+              const uint32_t nbytes = br.read<false>(2);
+              uint32_t v = 0;
+              for (uint32_t i = 0; i < nbytes; i++) {
+                const uint32_t b = br.read<false>(8);
+                if (i + 1 == nbytes && nbytes > 1 && b == 0) { result = kErrExuberantMetaNibble; break; }
+                v |= b << (i * 8);
+              }
+              if (nbytes != 0) d.mlen = (int32_t)v + 1;
+            }
+          } else {
+            const uint32_t nn = nib + 4;
+            uint32_t v = 0;
+            for (uint32_t i = 0; i < nn; i++) {
+              const uint32_t b = br.read<false>(4);
+              if (i + 1 == nn && nn > 4 && b == 0) { result = kErrExuberantNibble; break; }
+              v |= b << (i * 4);
+            }
+            if (result == kSuccess) {
+              if (!is_last) is_uncompressed = br.read<false>(1);
+              d.mlen = (int32_t)v + 1;
+            }
           }
         }
+        if (br.overrun()) result = kNeedsMoreInput;
+        if (result != kSuccess) break;
+        if ((is_metadata || is_uncompressed) && !br.jump_to_byte_boundary()) {  // src/decode.rs:2990-2994
+          result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break;
+        }
+        if (br.overrun()) { result = kNeedsMoreInput; break; }
+      } else {
+        is_uncompressed = inside == 3;
       }
-      if (br.overrun()) result = kNeedsMoreInput;
-      if (result != kSuccess) break;
-      if ((is_metadata || is_uncompressed) && !br.jump_to_byte_boundary()) {  // src/decode.rs:2990-2994
-        result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break;
-      }
-      if (br.overrun()) { result = kNeedsMoreInput; break; }
       if (is_metadata) {  // src/decode.rs:3031-3045
         const uint64_t at = br.byte_pos(), left = br.size() - at;
         if (left < (uint64_t)d.mlen) { result = kNeedsMoreInput; break; }
         br.seek_byte(at + (uint64_t)d.mlen);
         d.mlen = 0;
-      } else if (d.mlen != 0) {
-        if (!d.rb_allocated) allocate_ring_emulation(d, is_last, is_uncompressed);
+      } else if (d.mlen != 0 || inside != 0) {
+        if (!d.rb_allocated) allocate_ring_emulation(d, d.is_last, is_uncompressed);
         if (is_uncompressed) {
           result = copy_uncompressed(d);
+          if (resume && (result == kNeedsMoreInput || result == kNeedsMoreOutput)) save_checkpoint(d, resume, 3);
           if (result != kSuccess) break;
         } else {
-          result = read_compressed_metablock_header(d);
-          if (result == kSuccess && br.overrun()) result = kNeedsMoreInput;
-          if (result != kSuccess) break;
+          if (inside == 2) {  // the tables of this metablock are in the session's arena
+            d.nbt_l = resume->nbt_l; d.nbt_c = resume->nbt_c; d.nbt_d = resume->nbt_d;
+            d.bl_l = resume->bl_l; d.bl_c = resume->bl_c; d.bl_d = resume->bl_d;
+            d.rbt_l0 = resume->rbt_l0; d.rbt_l1 = resume->rbt_l1; d.rbt_c0 = resume->rbt_c0; d.rbt_c1 = resume->rbt_c1;
+            d.rbt_d0 = resume->rbt_d0; d.rbt_d1 = resume->rbt_d1;
+            d.n_lit_trees = resume->n_lit_trees; d.n_dist_trees = resume->n_dist_trees; d.npostfix = resume->npostfix; d.ndirect = resume->ndirect;
+            d.dist_alphabet = resume->dist_alphabet; d.dist_max_symbol = resume->dist_max_symbol; d.tables_used = resume->tables_used;
+            setup_metablock_views(d);
+            d.state = resume->state; d.ins_rem = resume->ins_rem; d.copy_len = resume->copy_len;
+            d.implicit_dist = resume->implicit_dist; d.dist_ctx = resume->dist_ctx;
+          } else {
+            result = read_compressed_metablock_header(d);
+            if (result == kSuccess && br.overrun()) result = kNeedsMoreInput;
+            if (result != kSuccess) break;
+          }
           for (;;) {  // ProcessCommands / SafeProcessCommands, src/decode.rs:3289-3298
             // (streams with a custom dictionary take the checked loop for every command: the register-resident
             // loops assume that every distance stays inside the output region)
-            result = d.cdict_given ? kNeedSafe : (d.all_shared ? process_commands_shared(d) : process_commands_fast(d));
-            if (result == kNeedSafe) result = process_commands<true>(d);
+            // (a session that continues in the middle of a command lets the checked loop finish that command first)
+            result = (d.cdict_given || d.state != kCmdBegin) ? kNeedSafe : (d.all_shared ? process_commands_shared(d) : process_commands_fast(d));
+            if (result == kNeedSafe) {
+              // the checked loop is where a decode can stop (end of input, ring flush point): a session continues here
+              if (resume) save_checkpoint(d, resume, 2);
+              result = process_commands<true>(d);
+            }
             if (result != kRetryFast) break;
           }
           if (result != kMetablockDone) break;
           result = kSuccess;
         }
       }
+      inside = 0;
       // BROTLI_STATE_METABLOCK_DONE, src/decode.rs:3345-3381
       if (d.mlen < 0) { result = kErrBlockLength2; break; }
-      if (!is_last) {
-        if (resume && !br.overrun()) {  // a complete metablock: the next call of the session starts here
-          hw::syncwarp();
-          if (hw::lane() == 0) {
-            resume->bitpos = br.bitpos() - 8 * (uint64_t)br.lead;
-            resume->rbsize = d.rbsize; resume->next_flush = d.next_flush; resume->flushed = d.flushed;
-            resume->pos = d.pos; resume->d0 = d.d0; resume->d1 = d.d1; resume->d2 = d.d2; resume->d3 = d.d3;
-            resume->wbits = d.wbits; resume->large_window = d.large_window;
-            resume->rb_allocated = d.rb_allocated; resume->full_ring = d.full_ring;
-            resume->valid = 1;
-          }
-          hw::syncwarp();
-        }
+      if (!d.is_last) {
+        if (resume && !br.overrun()) save_checkpoint(d, resume, 1);  // a complete metablock: the next launch starts here
         continue;
       }
       if (!br.jump_to_byte_boundary()) { result = br.overrun() ? kNeedsMoreInput : kErrPadding2; break; }
@@ -1700,12 +1755,29 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   // On NeedsMoreInput the reference flushes its ring buffer (src/decode.rs:2834-2846); that
   // flush fails with BLOCK_LENGTH_1 when the command in flight has overshot MLEN (:1709-1711).
   if (result == kNeedsMoreInput && d.rb_allocated && d.mlen < 0) result = kErrBlockLength1;
-  if (result == kSuccess || result == kNeedsMoreInput || result == kNeedsMoreOutput) *decoded_size = d.pos;
+  if (d.at_flush) *decoded_size = d.next_flush;
+  else if (result == kSuccess || result == kNeedsMoreInput || result == kNeedsMoreOutput) *decoded_size = d.pos;
   else *decoded_size = d.flushed;
   // input bytes consumed (whole bytes; on success the reference un-reads its look-ahead, src/decode.rs:3374-3376)
   uint64_t used = ((br.bitpos() + 7) >> 3) - br.lead;
   *in_used = used < in_size ? used : in_size;
+  if (resume && hw::lane() == 0) {
+    resume->code = result; resume->decoded = *decoded_size; resume->used = *in_used; resume->flushed_now = d.flushed; resume->at_flush = d.at_flush;
+    resume->hit_cap = (d.pos >= d.cap || d.discarded != 0) ? 1u : 0u;
+  }
   return result;
+}
+
+// One launch's worth of a streaming session: everything comes from (and goes back to) its ResumeState.
+BD_DEV int decode_session(Decoder& d, ResumeState* rs) {
+  uint8_t* const own_arena = d.arena;
+  if (rs->arena) d.arena = rs->arena;  // (a one-launch record -- the exact re-decode of a one-shot -- uses the warp's arena)
+  d.tables = (uint16_t*)(d.arena + ArenaLayout::kTables);
+  uint64_t decoded = 0, used = 0;
+  const int code = decode_stream(d, rs->in, rs->in_size, rs->out, rs->out_cap, rs->allow_large_window, &decoded, &used, rs->dict, rs->dict_size, rs);
+  d.arena = own_arena;
+  d.tables = (uint16_t*)(d.arena + ArenaLayout::kTables);
+  return code;
 }
 
 }  // namespace brotli_b200

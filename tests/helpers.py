@@ -157,12 +157,14 @@ class HostSim:
         L.hostsim_lane_decode_dict.restype = ctypes.c_int
         L.hostsim_lane_decode_dict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                                ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
-        L.hostsim_decode_resume.restype = ctypes.c_int
-        L.hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
-                                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
-        L.hostsim_resume_state_bytes.restype = ctypes.c_size_t
-        L.hostsim_session_dictionary.restype = None
-        L.hostsim_session_dictionary.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        L.hostsim_stream_create.restype = ctypes.c_void_p
+        L.hostsim_stream_create.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+        L.hostsim_stream_destroy.restype = None
+        L.hostsim_stream_destroy.argtypes = [ctypes.c_void_p]
+        L.hostsim_stream_calls.restype = ctypes.c_int
+        L.hostsim_stream_calls.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 10
+        L.hostsim_stream_stats.restype = None
+        L.hostsim_stream_stats.argtypes = [ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint64)]
         L.hostsim_lane_decode.restype = ctypes.c_int
         L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -199,31 +201,58 @@ class HostSim:
         return code, buf.raw[:n.value]
 
 
-class HostSimSession:
-    """A streaming session of the exact kernel's logic (host build): one persistent output buffer and the
-    ResumeState the kernel keeps between calls (decode resumes behind the last completed metablock)."""
+class HostSimStream:
+    """A streaming session of the product's host logic (csrc/brotli_b200_session.h) over the host build of the exact
+    kernel: call(data, out_cap) has BrotliDecoderDecompressStream's semantics and returns
+    (result, consumed, produced_bytes, total_out) like OracleStream.call."""
 
-    def __init__(self, hostsim, capacity, custom_dict=None):
+    def __init__(self, hostsim, large_window=False, custom_dict=None):
         self.lib = hostsim.lib
-        self.dict = bytes(custom_dict) if custom_dict else b""
-        self.buf = ctypes.create_string_buffer(max(int(capacity), 1))
-        self.cap = int(capacity)
-        self.state = ctypes.create_string_buffer(int(self.lib.hostsim_resume_state_bytes()))
+        cd = bytes(custom_dict) if custom_dict else None
+        self.h = self.lib.hostsim_stream_create(1 if large_window else 0, cd, len(cd) if cd else 0)
+        self.code = 0
 
-    def decode(self, data_so_far, large_window=True):
-        data = bytes(data_so_far)
-        n = ctypes.c_uint64(0)
-        self.lib.hostsim_session_dictionary(self.dict if self.dict else None, len(self.dict))
-        code = self.lib.hostsim_decode_resume(data, len(data), self.buf, self.cap, 1 if large_window else 0, self.state, ctypes.byref(n))
-        self.lib.hostsim_session_dictionary(None, 0)
-        return code, self.buf.raw[:n.value]
+    def call(self, data, out_cap):
+        (r,) = stream_calls(self.lib, [self], [data], [out_cap])
+        return r
 
-    def resumed_at(self):
-        """(valid, bit position, output position) of the saved boundary."""
-        import struct
-        bitpos, = struct.unpack_from("<Q", self.state.raw, 0)
-        valid, pos = struct.unpack_from("<II", self.state.raw, 32)
-        return valid, bitpos, pos
+    def error_code(self):
+        return self.code
+
+    def close(self):
+        if self.h:
+            self.lib.hostsim_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def stream_calls(lib, streams, datas, out_caps):
+    """One batched call for several HostSimStream sessions (one simulated launch)."""
+    n = len(streams)
+    datas = [bytes(d) for d in datas]
+    handles = (ctypes.c_void_p * n)(*[s.h for s in streams])
+    ins = (ctypes.c_char_p * n)(*datas)
+    in_size = (ctypes.c_size_t * n)(*[len(d) for d in datas])
+    bufs = [ctypes.create_string_buffer(max(int(c), 1)) for c in out_caps]
+    outs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    caps = (ctypes.c_size_t * n)(*[int(c) for c in out_caps])
+    consumed = (ctypes.c_size_t * n)(); produced = (ctypes.c_size_t * n)(); total = (ctypes.c_size_t * n)()
+    results = (ctypes.c_int * n)(); codes = (ctypes.c_int * n)()
+    rc = lib.hostsim_stream_calls(n, handles, ins, in_size, outs, caps, consumed, produced, total, results, codes)
+    assert rc == 0
+    out = []
+    for i in range(n):
+        streams[i].code = codes[i]
+        out.append((results[i], consumed[i], bufs[i].raw[:produced[i]], total[i]))
+    return out
+
+
+def hostsim_stream_stats(hostsim):
+    a, b, c = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_uint64(0)
+    hostsim.lib.hostsim_stream_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return {"live_bytes": a.value, "peak_bytes": b.value, "launches": c.value}
 
 
 def result_of(code):
