@@ -239,6 +239,10 @@ BROTLI_B200_API double BrotliB200LastKernelMs(void);
  * lane-per-stream kernel and of the exact warp-per-stream kernel; launches: decode calls covered; bailed: streams
  * the lane kernel handed to the exact kernel in the most recent call.  reset != 0 clears the record. */
 BROTLI_B200_API int BrotliB200KernelTimes(double* lane_ms, double* exact_ms, uint32_t* launches, uint32_t* bailed, int reset);
+/* Tuning knobs of the current device (tests and benchmarks force a decode path with them): "lane_min_streams" -- batches
+ * smaller than this skip the lane-per-stream kernel (default 6000, from the measured latency table); "small_geometry" --
+ * 0/1, the 8-warp geometry for batches below one wave; "sort_streams" -- 0/1, longest-first order.  Returns 1 if set. */
+BROTLI_B200_API int BrotliB200SetTuning(const char* name, uint64_t value);
 /* Last library-level error message of the calling thread ("" if none). */
 BROTLI_B200_API const char* BrotliB200LastError(void);
 /* Resident decoding warps per launch on the current device (148 SMs x warps per SM on a B200). */

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "BrotliDecoderFreeU8", "BrotliDecoderMallocUsize", "BrotliDecoderFreeUsize", "BrotliB200DecompressBatchDevice",
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
     "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary", "BrotliB200DecoderSetCustomDictionary",
-    "BrotliB200DecoderDecompressStreamBatch",
+    "BrotliB200DecoderDecompressStreamBatch", "BrotliB200SetTuning",
     "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
     "BrotliB200Shutdown",
 ]
@@ -102,6 +102,8 @@ def lib():
     L.BrotliB200DecoderSetCustomDictionary.argtypes = [vp, vp, sz]
     L.BrotliB200DecoderDecompressStreamBatch.restype = ctypes.c_int
     L.BrotliB200DecoderDecompressStreamBatch.argtypes = [sz] + [vp] * 7
+    L.BrotliB200SetTuning.restype = ctypes.c_int
+    L.BrotliB200SetTuning.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
     L.BrotliB200ChecksumBatchDevice.restype = ctypes.c_int
     L.BrotliB200ChecksumBatchDevice.argtypes = [sz, vp, vp, vp, vp, vp]
     L.BrotliB200KernelLaunchCount.restype = ctypes.c_uint64
@@ -230,6 +232,11 @@ class DecoderState:
 
     def error_string(self):
         return lib().BrotliDecoderGetErrorString(self._s).decode()
+
+
+def set_tuning(name, value):
+    """BrotliB200SetTuning: "lane_min_streams", "small_geometry", "sort_streams"."""
+    return bool(lib().BrotliB200SetTuning(name.encode(), int(value)))
 
 
 def decompress_stream_batch(states, datas, out_capacities):

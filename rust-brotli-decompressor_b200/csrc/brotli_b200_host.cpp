@@ -101,6 +101,10 @@ struct DeviceCtx {
   int lane_ctas = 0;           // 0: lane kernel disabled (BROTLI_B200_LANE=0): every stream takes the exact kernel
   int lane_warps = 0;          // warps per CTA of the lane kernel
   uint32_t lane_slot_bytes = 0;
+  // second geometry for batches below one wave: fewer, fuller warps with wider table slots (profiles/r02/lat_*.jsonl)
+  int small_warps = 0, small_ctas = 0;
+  uint32_t small_slot_bytes = 0;
+  size_t lane_min_streams = 0; // batches smaller than this go straight to the warp-per-stream kernel
   uint8_t* lane_arena = nullptr;
   uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
   uint32_t* bail_count = nullptr;
@@ -199,6 +203,17 @@ DeviceCtx* acquire_ctx() {
       return nullptr;
     }
     g_launches.fetch_add(1);
+    // Batch-size dependent routing, from the measured latency table (profiles/r02/lat_*.jsonl): a stream
+    // takes ~25-32 ms on a lane however few streams there are, ~5-17 ms on a warp of the exact kernel -- below ~6000
+    // streams the exact kernel alone is faster; below one wave of the default geometry 8 warps per SM with full warps
+    // beat 14 warps with half-empty ones.
+    c->lane_min_streams = getenv("BROTLI_B200_LANE_MIN") ? (size_t)atoll(getenv("BROTLI_B200_LANE_MIN")) : 6000;
+    if (!warps_env && !(getenv("BROTLI_B200_LANE_SMALL") && getenv("BROTLI_B200_LANE_SMALL")[0] == '0')) {
+      c->small_warps = 8;
+      c->small_ctas = brotli_b200::query_lane_resident_ctas(dev, c->small_warps);
+      c->small_slot_bytes = brotli_b200::lane_slot_bytes(c->small_warps);
+      if (c->small_ctas <= 0) c->small_warps = 0;
+    }
     c->bail_count = c->ticket + 16;  // same 256-byte allocation as the tickets
     const char* sort_env = getenv("BROTLI_B200_SORT");
     c->sort_streams = !(sort_env && sort_env[0] == '0');
@@ -227,15 +242,21 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
   // (a streaming session is one stream: exact kernel; a batch with a custom dictionary takes the lane kernel's dictionary
   // instance when the configured geometry has one)
-  if (c->lane_ctas > 0 && a.sessions == nullptr && (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
+  if (c->lane_ctas > 0 && a.sessions == nullptr && n >= c->lane_min_streams &&
+      (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
     CU_TRY(c->bail_list.reserve(n * sizeof(uint32_t)));
     brotli_b200::LaneArgs la;
+    int lane_warps = c->lane_warps, lane_ctas = c->lane_ctas;
+    la.slot_bytes = c->lane_slot_bytes;
+    if (c->small_warps && a.custom_dict_size == 0 && n <= (size_t)c->small_ctas * c->small_warps * 32) {
+      lane_warps = c->small_warps; lane_ctas = c->small_ctas; la.slot_bytes = c->small_slot_bytes;
+    }
     la.arena = c->lane_arena; la.bail_count = c->bail_count; la.bail_list = (uint32_t*)c->bail_list.p;
-    la.slot_bytes = c->lane_slot_bytes; la.xdict = c->xdict;
+    la.xdict = c->xdict;
     la.cdict = a.custom_dict; la.cdict_len = a.custom_dict_size;
     // small batches: fewer streams per warp, spread over all resident warps
-    const size_t total_warps = (size_t)c->lane_ctas * c->lane_warps;
+    const size_t total_warps = (size_t)lane_ctas * lane_warps;
     const size_t per_warp = (n + total_warps - 1) / total_warps;
     la.chunk = per_warp >= 32 ? 32u : (uint32_t)per_warp;
     if (c->sort_streams && n >= 64) {
@@ -245,7 +266,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
       g_launches.fetch_add(2);
       a.order = (const uint32_t*)c->order.p + 3 * n;
     }
-    CU_TRY(brotli_b200::launch_decode_lane(a, la, c->lane_ctas, c->lane_warps, stream));
+    CU_TRY(brotli_b200::launch_decode_lane(a, la, lane_ctas, lane_warps, stream));
     g_launches.fetch_add(1);
     // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
     a.order = la.bail_list; a.n_ptr = la.bail_count; a.ticket = c->ticket + 8;
@@ -521,17 +542,55 @@ BrotliDecoderReturnInfo invalid_arguments_info() {  // src/ffi/mod.rs:83-106
   return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_INVALID_ARGUMENTS, 0, nullptr);
 }
 
+// One stream, host buffers: no chunk pipeline, one launch, and only the decoded bytes come back (the caller's buffer is
+// written exactly as far as the reference writes it: c/main.c passes a capacity larger than its buffer).
+int decode_one(DeviceCtx* c, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_cap, uint64_t* out_len, int32_t* code, uint64_t* used,
+               uint32_t large_window, const uint8_t* dict, size_t dict_size) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  const uint8_t* d_dict = nullptr;
+  if (dict_size) {
+    CU_TRY(c->cdict.reserve(dict_size + 64));
+    CU_TRY(cudaMemcpyAsync((uint8_t*)c->cdict.p + 32, dict, dict_size, cudaMemcpyHostToDevice, c->s_compute));
+    d_dict = (const uint8_t*)c->cdict.p + 32;
+  }
+  CU_TRY(c->in.reserve(in_size + 16));
+  CU_TRY(c->out.reserve(out_cap + 16));
+  CU_TRY(c->in_off.reserve(64));
+  CU_TRY(c->out_len.reserve(64));
+  // meta block in one device buffer: in_off[2] | out_off[2] | out_len | in_used | code
+  uint64_t meta[8] = {0, (uint64_t)in_size, 0, (uint64_t)out_cap, 0, 0, 0, 0};
+  uint64_t* d_meta = (uint64_t*)c->in_off.p;
+  CU_TRY(cudaMemcpyAsync(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->s_compute));
+  if (in_size) CU_TRY(cudaMemcpyAsync(c->in.p, in, in_size, cudaMemcpyHostToDevice, c->s_compute));
+  int rc = decode_device(c, 1, (const uint8_t*)c->in.p, d_meta, (uint8_t*)c->out.p, d_meta + 2, d_meta + 4, (int32_t*)(d_meta + 6), d_meta + 5,
+                         large_window, c->s_compute, d_dict, dict_size);
+  if (rc != 0) return rc;
+  CU_TRY(cudaMemcpyAsync(meta, d_meta, sizeof(meta), cudaMemcpyDeviceToHost, c->s_compute));
+  CU_TRY(cudaStreamSynchronize(c->s_compute));
+  *out_len = meta[4]; *used = meta[5]; *code = (int32_t)(uint32_t)meta[6];
+  if (*out_len > out_cap) *out_len = out_cap;
+  if (*out_len) {
+    CU_TRY(cudaMemcpyAsync(out, c->out.p, (size_t)*out_len, cudaMemcpyDeviceToHost, c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+  }
+  if (*code == BROTLI_DECODER_NEEDS_MORE_OUTPUT) {
+    const uint64_t in_off[2] = {0, (uint64_t)in_size}, out_off[2] = {0, (uint64_t)out_cap};
+    rc = redo_needs_more_output(c, 1, in, in_off, out_off, (const uint8_t*)c->in.p, out_len, code, d_dict, dict_size);
+  }
+  return rc;
+}
+
 // brotli_decode (src/lib.rs:446-468) on the GPU: a batch of one.
 BrotliDecoderReturnInfo one_shot(const uint8_t* in, size_t in_size, uint8_t* out, size_t out_cap, uint32_t large_window,
                                  uint64_t* in_used, const uint8_t* dict = nullptr, size_t dict_size = 0) {
   DeviceCtx* c = acquire_ctx();
   if (!c) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
   if (in_size >= ((uint64_t)1 << 32)) return invalid_arguments_info();  // src/decode.rs:2799-2812
-  uint64_t in_off[2] = {0, in_size}, out_off[2] = {0, out_cap}, out_len = 0, used = 0;
+  uint64_t out_len = 0, used = 0;
   int32_t code = 0;
   static const uint8_t kNothing[1] = {0};
   uint8_t dummy_out[1];
-  int rc = decode_host_packed(c, 1, in ? in : kNothing, in_off, out ? out : dummy_out, out_off, &out_len, &code, &used, large_window, dict, dict_size);
+  int rc = decode_one(c, in ? in : kNothing, in_size, out ? out : dummy_out, out_cap, &out_len, &code, &used, large_window, dict, dict_size);
   if (rc != 0) return make_info(BROTLI_DECODER_RESULT_ERROR, BROTLI_DECODER_ERROR_UNREACHABLE, 0, tl_error.c_str());
   if (in_used) *in_used = used;
   int result = code == 1 ? 1 : (code == 2 ? 2 : (code == 3 ? 3 : 0));  // BrotliResult
@@ -856,6 +915,24 @@ int BrotliB200KernelTimes(double* lane_ms, double* exact_ms, uint32_t* launches,
   return 0;
 }
 const char* BrotliB200LastError(void) { return tl_error.c_str(); }
+
+// Tuning knobs of the current device's context (tests and benchmarks force a path with them).
+int BrotliB200SetTuning(const char* name, uint64_t value) {
+  DeviceCtx* c = acquire_ctx();
+  if (!c || !name) return 0;
+  std::lock_guard<std::mutex> lock(c->launch_mu);
+  if (strcmp(name, "lane_min_streams") == 0) { c->lane_min_streams = (size_t)value; return 1; }
+  if (strcmp(name, "small_geometry") == 0) {
+    if (value == 0) { c->small_warps = 0; return 1; }
+    c->small_warps = 8;
+    c->small_ctas = brotli_b200::query_lane_resident_ctas(c->device, 8);
+    c->small_slot_bytes = brotli_b200::lane_slot_bytes(8);
+    if (c->small_ctas <= 0) { c->small_warps = 0; return 0; }
+    return 1;
+  }
+  if (strcmp(name, "sort_streams") == 0) { c->sort_streams = value != 0; return 1; }
+  return 0;
+}
 
 int BrotliB200ResidentWarps(void) {
   DeviceCtx* c = acquire_ctx();

@@ -70,6 +70,7 @@ struct Session {
 template <class Dev>
 struct SessionRunner {
   Dev& dev;
+  std::vector<SessionCopy> pre_moves;  // buffer growth of this batch: executed as one device-to-device pass before the decode
   explicit SessionRunner(Dev& d) : dev(d) {}
 
   // hand pending bytes to the caller (positions below `limit` only)
@@ -102,7 +103,7 @@ struct SessionRunner {
     if (need <= cap[sel]) return true;
     const int o = sel ^ 1;
     if (!reserve(p[o], cap[o], need + need / 2)) return false;
-    if (keep) { SessionCopy m{p[sel], p[o], keep}; if (dev.move(&m, 1) != 0) return false; }
+    if (keep) pre_moves.push_back(SessionCopy{p[sel], p[o], keep});  // (the old half stays allocated: it is the source)
     sel = o;
     return true;
   }
@@ -186,7 +187,12 @@ struct SessionRunner {
         r.allow_large_window = s.large_window ? 1u : 0u;
         arr[k] = r;
       }
-      if (live.empty()) break;
+      if (live.empty()) { pre_moves.clear(); break; }
+      if (!pre_moves.empty()) {
+        const int mrc = dev.move(pre_moves.data(), (uint32_t)pre_moves.size());
+        pre_moves.clear();
+        if (mrc != 0) { for (uint32_t i : live) fail(*ss[i], cs[i], device_error_code); return mrc; }
+      }
       const int rc = dev.run(arr.data(), (uint32_t)arr.size(), first ? blob.data() : nullptr, first ? blob.size() : 0,
                              first ? scatter.data() : nullptr, first ? (uint32_t)scatter.size() : 0u);
       first = false;
@@ -240,6 +246,10 @@ struct SessionRunner {
       const uint64_t before = s.consumed;            // == in_base + in_len - fresh[i]
       uint64_t used_abs = s.in_base + r.used;
       if (r.code == 2) used_abs = s.in_base + s.in_len;  // NeedsMoreInput swallows the whole input, src/decode.rs:2887-2899
+      // An error out of the forced flush of NeedsMoreInput leaves the caller's counters where they were (the reference
+      // breaks out before it writes them back, :2843-2846; bytes it had taken into its 8-byte carry-over -- at most 7 -- are
+      // the one thing this does not reproduce).
+      if (r.code < 0 && r.forced_flush_error) used_abs = before;
       if (used_abs < before) used_abs = before;
       if (used_abs > s.in_base + s.in_len) used_abs = s.in_base + s.in_len;
       const size_t adv = (size_t)(used_abs - before);

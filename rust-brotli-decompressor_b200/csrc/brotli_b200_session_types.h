@@ -30,6 +30,8 @@ struct ResumeState {
   uint64_t flushed_now;     // output the reference has handed out at ring flush points (what a fatal error leaves)
   uint32_t at_flush;        // NeedsMoreOutput at a ring flush point: `budget` is too small for position `decoded`
   uint32_t hit_cap;         // the decoder ran into out_cap: the outcome is not the reference's, repeat with a larger window
+  uint32_t forced_flush_error;  // the error came out of the forced flush of NeedsMoreInput (src/decode.rs:2838-2850): the reference
+                                // leaves *available_in / *next_in as they were at the start of the call
   // ---- checkpoint ----
   uint32_t kind;            // 0 start of stream, 1 metablock boundary, 2 inside a compressed metablock, 3 inside an uncompressed one
   uint64_t bitpos;

@@ -1754,7 +1754,8 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   hw::syncwarp();
   // On NeedsMoreInput the reference flushes its ring buffer (src/decode.rs:2834-2846); that
   // flush fails with BLOCK_LENGTH_1 when the command in flight has overshot MLEN (:1709-1711).
-  if (result == kNeedsMoreInput && d.rb_allocated && d.mlen < 0) result = kErrBlockLength1;
+  uint32_t forced_flush_error = 0;
+  if (result == kNeedsMoreInput && d.rb_allocated && d.mlen < 0) { result = kErrBlockLength1; forced_flush_error = 1; }
   if (d.at_flush) *decoded_size = d.next_flush;
   else if (result == kSuccess || result == kNeedsMoreInput || result == kNeedsMoreOutput) *decoded_size = d.pos;
   else *decoded_size = d.flushed;
@@ -1764,6 +1765,7 @@ BD_DEV int decode_stream(Decoder& d, const uint8_t* in, uint64_t in_size, uint8_
   if (resume && hw::lane() == 0) {
     resume->code = result; resume->decoded = *decoded_size; resume->used = *in_used; resume->flushed_now = d.flushed; resume->at_flush = d.at_flush;
     resume->hit_cap = (d.pos >= d.cap || d.discarded != 0) ? 1u : 0u;
+    resume->forced_flush_error = forced_flush_error;
   }
   return result;
 }

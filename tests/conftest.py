@@ -47,4 +47,9 @@ def gpu_lib(pkg):
     torch.zeros(1, device="cuda")
     L = pkg.lib()
     assert L.BrotliB200ResidentWarps() > 0, L.BrotliB200LastError()
+    # The library routes batches below ~6000 streams straight to the warp-per-stream kernel (they are faster there).  The
+    # parity tests use small batches and must exercise the lane-per-stream kernel too: switch the threshold off (the
+    # default routing has its own test, test_gpu_parity.py::test_batch_size_routing, and "exact_only" runs everything
+    # through the other kernel).
+    assert pkg.set_tuning("lane_min_streams", 0)
     return L

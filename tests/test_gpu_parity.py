@@ -277,6 +277,38 @@ def test_other_kernel_configurations(gpu_lib, mode):
     assert r.returncode == 0, r.stdout[-3000:]
 
 
+def test_batch_size_routing(gpu_lib, pkg, corpus):
+    """Default routing by batch size (DESIGN.md latency table): a small batch never touches the lane kernel, a large
+    one does, and both give the originals."""
+    import torch
+    comp, orig, _ = corpus.make_config("C2", 96, size=65536)
+    try:
+        assert pkg.set_tuning("lane_min_streams", 6000)
+        for n in (96, 6144):
+            idx = np.arange(n) % 96
+            blobs = [comp[i] for i in idx]
+            in_bytes, in_off = corpus.pack(blobs)
+            out_off = np.arange(n + 1, dtype=np.uint64) * 65536
+            d_in = torch.from_numpy(in_bytes).cuda(); d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
+            d_out_off = torch.from_numpy(out_off.view(np.int64)).cuda()
+            d_out = torch.zeros(n * 65536, dtype=torch.uint8, device="cuda")
+            d_len = torch.zeros(n, dtype=torch.int64, device="cuda"); d_codes = torch.zeros(n, dtype=torch.int32, device="cuda")
+            pkg.kernel_times(reset=True)
+            pkg.decompress_batch_device(n, d_in, d_in_off, d_out, d_out_off, d_len, d_codes)
+            torch.cuda.synchronize()
+            kt = pkg.kernel_times()
+            assert bool((d_codes == 1).all())
+            out = d_out.cpu().numpy().reshape(n, 65536)
+            for j in range(0, n, 97):
+                assert out[j].tobytes() == orig[idx[j]]
+            if n < 6000:
+                assert kt["lane_ms"] < 0.05 and kt["exact_ms"] > 1.0, kt   # exact kernel only
+            else:
+                assert kt["lane_ms"] > 5.0 and kt["exact_ms"] < 1.0, kt    # lane kernel, empty bail list
+    finally:
+        pkg.set_tuning("lane_min_streams", 0)
+
+
 def test_differential_fuzz_error_codes(gpu_lib, pkg, oracle, corpus):
     """every BrotliDecoderErrorCode and decoded_size the GPU path reports for malformed input
     equals the oracle's, over a few thousand seeded mutations (truncations, bit flips, byte smashes, multi-byte
@@ -380,8 +412,13 @@ def test_c_main_acceptance(gpu_lib, pkg, tmp_path):
     r = subprocess.run(["gcc", "-O1", "-I", str(tmp_path), src, "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(pkg.LIB_PATH),
                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    # after its three self-checks (asserts) main() is a stdin -> stdout decompressor over BrotliDecoderDecompressStream
+    comp = helpers.golden_fixture("alice29.txt.compressed")
+    r = subprocess.run([str(exe)], input=comp, capture_output=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert hashlib.sha256(r.stdout).hexdigest() == MAN["alice29.txt.compressed"]["original_sha256"]
+    r = subprocess.run([str(exe)], input=comp[:20000], capture_output=True, timeout=300)  # truncated: "Unexpected EOF", exit 1
+    assert r.returncode == 1 and b"Unexpected EOF" in r.stderr
 
 
 def test_c4_real_shape(gpu_lib, pkg, oracle, corpus):
