@@ -28,6 +28,8 @@ ncu -i $OUT/prof_lane.ncu-rep --page source --csv > $OUT/source.csv 2>/dev/null
 python profiles/ncu_l2_by_inst.py $OUT/source.csv 16 > $OUT/ncu_l2_by_inst.txt 2>&1
 python profiles/ncu_hot.py $OUT/prof_lane.ncu-rep > $OUT/ncu_lane_kernel.txt 2>&1
 ncu -i $OUT/prof_lane.ncu-rep --page raw --csv > $OUT/ncu_lane_kernel_raw.csv 2>/dev/null
+# DRAM traffic of that capture + kernel source fingerprint -> what bench.py quotes as roofline.traffic
+python profiles/ncu_traffic.py $OUT/ncu_lane_kernel_raw.csv 131072 brotli_decode_lane_kernel $OUT/current_traffic.json
 rm -f $OUT/source.csv
 if [ -n "$WITH_CONFIGS" ]; then timeout 900 python profiles/gpu_configs.py > $OUT/configs.jsonl 2> $OUT/configs.err; cat $OUT/configs.jsonl | cut -c1-250; fi
 ls -la $OUT

@@ -127,8 +127,10 @@ struct DeviceCtx {
   DevBuf cdict;            // custom LZ77 dictionary of the batch in flight
   DevBuf sess_states, sess_pieces, sess_blob;  // staging of a session launch: ResumeState[], SessionCopy[], bytes
   DevBuf redo_out;         // output windows of the exact re-decode of NeedsMoreOutput one-shots
-  void* pinned = nullptr;  // small pinned staging area for one-shot calls
-  size_t pinned_cap = 0;
+  // pinned host staging of the scattered-batch entry (BrotliB200DecompressBatch): grow-only
+  void* pin_in = nullptr; size_t pin_in_cap = 0;
+  void* pin_out = nullptr; size_t pin_out_cap = 0;
+  std::mutex pin_mu;
 };
 
 DeviceCtx g_ctx[kMaxDevices];
@@ -826,12 +828,27 @@ int BrotliB200DecompressBatch(size_t n, const uint8_t* const* in, const size_t* 
       in_off[i] = ia; out_off[i] = oa; ia += in_size[i]; oa += out_size[i];
     }
     in_off[n] = ia; out_off[n] = oa;
-    std::vector<uint8_t> in_blob(ia + 1), out_blob(oa + 1);
-    for (size_t i = 0; i < n; i++) if (in_size[i]) memcpy(in_blob.data() + in_off[i], in[i], in_size[i]);
-    int rc = decode_host_packed(c, n, in_blob.data(), in_off.data(), out_blob.data(), out_off.data(), out_len.data(), cds.data(), nullptr, 1u);
+    // packed staging in PINNED host memory (grow-only, owned by the context): the pipeline's copies then run as true
+    // asynchronous DMA instead of the driver's staged pageable path
+    std::lock_guard<std::mutex> pin_lock(c->pin_mu);
+    auto pin_reserve = [](void** p, size_t* cap, size_t need) -> bool {
+      if (need <= *cap) return true;
+      if (*p) cudaFreeHost(*p);
+      *p = nullptr; *cap = 0;
+      const size_t want = need + need / 4 + 4096;
+      if (cudaHostAlloc(p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+      *cap = want;
+      return true;
+    };
+    if (!pin_reserve(&c->pin_in, &c->pin_in_cap, ia + 1) || !pin_reserve(&c->pin_out, &c->pin_out_cap, oa + 1)) {
+      set_error("brotli_b200: pinned staging allocation failed"); return BROTLI_DECODER_ERROR_UNREACHABLE;
+    }
+    uint8_t* in_blob = (uint8_t*)c->pin_in; uint8_t* out_blob = (uint8_t*)c->pin_out;
+    for (size_t i = 0; i < n; i++) if (in_size[i]) memcpy(in_blob + in_off[i], in[i], in_size[i]);
+    int rc = decode_host_packed(c, n, in_blob, in_off.data(), out_blob, out_off.data(), out_len.data(), cds.data(), nullptr, 1u);
     if (rc != 0) return rc;
     for (size_t i = 0; i < n; i++) {
-      if (out_len[i]) memcpy(out[i], out_blob.data() + out_off[i], out_len[i]);
+      if (out_len[i]) memcpy(out[i], out_blob + out_off[i], out_len[i]);
       out_size[i] = (size_t)out_len[i];
       results[i] = cds[i] == 1 ? BROTLI_DECODER_RESULT_SUCCESS : BROTLI_DECODER_RESULT_ERROR;
       if (codes) codes[i] = (BrotliDecoderErrorCode)cds[i];
@@ -952,6 +969,9 @@ void BrotliB200Shutdown(void) {  // (open decoder states keep their own device b
     c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release(); c->order.release();
     c->sess_states.release(); c->sess_pieces.release(); c->sess_blob.release(); c->redo_out.release(); c->cdict.release();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
+    if (c->pin_in) cudaFreeHost(c->pin_in);
+    if (c->pin_out) cudaFreeHost(c->pin_out);
+    c->pin_in = c->pin_out = nullptr; c->pin_in_cap = c->pin_out_cap = 0;
     cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
     for (auto& t : c->ev_t) for (auto& e : t) if (e) { cudaEventDestroy(e); e = nullptr; }
     c->timed_count = 0;

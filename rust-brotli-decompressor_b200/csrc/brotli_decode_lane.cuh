@@ -66,6 +66,17 @@ constexpr uint32_t kMaxExtraLiterals = BD_LANE_EXTRA_LITERALS;  // literals a la
 #define BD_LANE_CMD_LITERALS 0
 #endif
 constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may decode in the round of their command
+// Literal bursts: while at least kBurstLanes lanes of the warp are inside a literal run, up to kBurst extra literal-only
+// iterations follow phase A (table look-ups synchronous, nothing else of the round issued).  A round costs ~650
+// instructions whatever its lanes do; a burst iteration ~60, so literal-heavy streams (binary data, 4 KiB responses)
+// need far fewer rounds.
+#ifndef BD_LANE_BURST
+#define BD_LANE_BURST 0
+#endif
+#ifndef BD_LANE_BURST_LANES
+#define BD_LANE_BURST_LANES 12
+#endif
+constexpr uint32_t kBurst = BD_LANE_BURST, kBurstLanes = BD_LANE_BURST_LANES;
 struct ArenaLayout {
   static constexpr size_t kTab = 0;                                   // u16[kGlobalTab]
   static constexpr size_t kCtxLit = kTab + 2 * (size_t)kGlobalTab;    // u8[64 * kMaxBlockTypes]
@@ -74,7 +85,8 @@ struct ArenaLayout {
   static constexpr size_t kBytes = (kCtxModes + kMaxBlockTypes + 255) & ~size_t(255);
 };
 
-enum : int { kLaneOk = 0, kLaneDone = 1, kLaneBail = 2 };
+enum : int { kLaneOk = 0, kLaneDone = 1, kLaneBail = 2, kLaneNext = 3 };  // kLaneNext: the metablock had no commands (raw bytes / metadata) and is done
+constexpr uint32_t kMaxLaneRaw = 1u << 18;  // uncompressed metablocks up to this size are copied by the lane itself (one active lane): larger ones go to the exact kernel
 
 #if defined(BROTLI_B200_HOSTSIM)
 static inline void sts16(hw::sref_t a, uint32_t v) { *(uint16_t*)a = (uint16_t)v; }
@@ -96,6 +108,7 @@ static inline void st32_if(bool cond, uint8_t* p, uint32_t v) { if (cond) memcpy
 static inline void sts32_if(bool cond, hw::sref_t a, uint32_t v) { if (cond) *(uint32_t*)a = v; }
 static inline void warp_sync() {}
 static inline bool warp_any(bool p) { return p; }
+static inline uint32_t warp_count(bool p) { return p ? 32u : 0u; }  /* the one simulated lane stands for a full warp */
 #define BD_PIN32(x) ((void)0)
 #define BD_PIN64(x) ((void)0)
 static inline void ld32_if(bool cond, const uint8_t* p, uint32_t& dst) { if (cond) memcpy(&dst, p, 4); }
@@ -182,6 +195,7 @@ BD_DEV void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) {
 #define BD_PIN32(x) asm volatile("" : "+r"(x))
 #define BD_PIN64(x) asm volatile("" : "+l"(x))
 BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 lanes take part
+BD_DEV uint32_t warp_count(bool p) { return __popc(__ballot_sync(0xffffffffu, p)); }
 #endif
 
 BD_DEV uint32_t mask_bits(uint32_t n) { return (1u << n) - 1u; }  // n <= 31
@@ -665,6 +679,68 @@ BD_COLD int block_switch(const LaneCtx& c, Lane& L, uint32_t cat, const BlockTre
 }
 
 
+// Bit window at byte `byte_off` of the (aligned) input: what stream_begin does for the first byte.
+BD_DEV void seek_byte(Lane& L, uint64_t byte_off) {
+  L.k = (uint32_t)(byte_off >> 2);
+  L.bp = 8 * (uint32_t)(byte_off & 3u);
+  cp_async_wait_all();  // nothing older may still be landing in the ring
+  const uint32_t b0 = L.k >> 2;
+  cp_async16(L.ring + (b0 & 1u) * L.ring_stride, L.gin + 16 * (size_t)(b0 < L.last_blk ? b0 : L.last_blk));
+  cp_async16(L.ring + ((b0 + 1) & 1u) * L.ring_stride, L.gin + 16 * (size_t)(b0 + 1 < L.last_blk ? b0 + 1 : L.last_blk));
+  cp_async_commit();
+  cp_async_wait_all();
+  L.lo = vlds32(L.ring + ((L.k >> 2) & 1u) * L.ring_stride + (L.k & 3u) * 4u);
+  L.hi = vlds32(L.ring + (((L.k + 1) >> 2) & 1u) * L.ring_stride + ((L.k + 1) & 3u) * 4u);
+  L.nx = vlds32(L.ring + (((L.k + 2) >> 2) & 1u) * L.ring_stride + ((L.k + 2) & 3u) * 4u);
+  if (((L.k + 2) >> 2) != b0) {  // the window already reaches into block b0 + 1: block b0 + 2 must be on its way (ring_next's invariant)
+    const uint32_t b2 = b0 + 2;
+    cp_async16(L.ring + (b2 & 1u) * L.ring_stride, L.gin + 16 * (size_t)(b2 < L.last_blk ? b2 : L.last_blk));
+    cp_async_commit();
+    cp_async_wait_all();
+  }
+}
+
+// Byte-align the bit window (JumpToByteBoundary, src/bit_reader/mod.rs:378-385); false if the padding bits are not zero.
+BD_DEV bool jump_to_byte_boundary(Lane& L) {
+  const uint32_t pad = (8u - (L.bp & 7u)) & 7u;
+  return pad == 0 || L.read(pad) == 0;
+}
+
+// ISUNCOMPRESSED metablock (CopyUncompressedBlockToOutput, src/decode.rs:1754-1806) for a well-formed stream: `n` raw bytes
+// from the byte-aligned bit position to the output, through the write combiner (so that later copies and literal contexts
+// see them in the history ring), then the bit window continues behind them.
+BD_COLD int copy_raw(const LaneCtx& c, Lane& L, uint32_t n) {
+  const uint64_t bo = ((uint64_t)L.k * 32 + L.bp) >> 3;  // byte offset from the aligned base
+  if (bo + n > (L.end_bit >> 3)) return kLaneBail;       // truncated input: the exact kernel's business
+  if (n > L.capb - L.posb || n > kMaxLaneRaw) return kLaneBail;
+  uint32_t posb = L.posb, acc = L.acc;
+  const uint32_t posb0 = posb;
+  const uint8_t* src = L.gin + bo;
+  uint32_t i = 0;
+  // up to an aligned output word (and past the region's first word, whose bytes below the region are not ours)
+  while (i < n && ((posb & 3u) != 0 || posb < 4)) {
+    append(L.out_al, L.bias, c.hist, posb, acc, src[i], 1);
+    i++;
+#if BD_LANE_HEAD_PER_ROUND
+    if (L.bias != 0 && posb0 < 4 && posb == 4) store_head_bytes(L.out_al, L.bias, 0, vlds32(c.hist));
+#endif
+  }
+  // whole words: aligned input words re-aligned with a funnel shift (never past the word holding the last stream byte)
+  const uint32_t* w = (const uint32_t*)L.gin;
+  while (i + 4 <= n) {
+    const uint64_t a = bo + i;
+    const uint32_t j = (uint32_t)(a >> 2), sh = 8 * (uint32_t)(a & 3u);
+    const uint32_t w0 = w[j], w1 = sh ? w[j + 1 <= L.k_max ? j + 1 : L.k_max] : 0u;
+    append(L.out_al, L.bias, c.hist, posb, acc, hw::funnelshift_r(w0, w1, sh), 4);
+    i += 4;
+  }
+  while (i < n) { append(L.out_al, L.bias, c.hist, posb, acc, src[i], 1); i++; }
+  (void)posb0;
+  L.posb = posb; L.acc = acc;
+  seek_byte(L, bo + n);
+  return kLaneNext;
+}
+
 // Metablock header up to the first command: src/decode.rs:2980-3288.
 BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   const uint32_t is_last = L.read(1);
@@ -672,7 +748,22 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   L.mlen = 0;
   if (is_last && L.read(1)) return kLaneDone;  // ISLASTEMPTY
   const uint32_t nib = L.read(2);
-  if (nib == 3) return kLaneBail;  // metadata block
+  if (nib == 3) {  // metadata metablock: reserved bit, MSKIPBYTES, MSKIPLEN - 1, padding, then the bytes to skip (:3031-3045)
+    if (L.read(1) != 0) return kLaneBail;
+    const uint32_t nbytes = L.read(2);
+    uint32_t skip = 0;
+    for (uint32_t i = 0; i < nbytes; i++) {
+      const uint32_t b = L.read(8);
+      if (i + 1 == nbytes && nbytes > 1 && b == 0) return kLaneBail;
+      skip |= b << (i * 8);
+    }
+    if (nbytes != 0) skip += 1;
+    if (!jump_to_byte_boundary(L) || L.overrun()) return kLaneBail;
+    const uint64_t bo = ((uint64_t)L.k * 32 + L.bp) >> 3;
+    if (bo + skip > (L.end_bit >> 3)) return kLaneBail;
+    if (skip != 0) seek_byte(L, bo + skip);
+    return kLaneNext;
+  }
   const uint32_t nn = nib + 4;
   uint32_t v = 0;
   for (uint32_t i = 0; i < nn; i++) {
@@ -680,7 +771,10 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     if (i + 1 == nn && nn > 4 && b == 0) return kLaneBail;
     v |= b << (i * 4);
   }
-  if (!is_last && L.read(1)) return kLaneBail;  // uncompressed metablock
+  if (!is_last && L.read(1)) {  // uncompressed metablock
+    if (!jump_to_byte_boundary(L) || L.overrun()) return kLaneBail;
+    return copy_raw(c, L, v + 1);
+  }
   L.mlen = (int32_t)v + 1;
   L.cold_next = c.E;
   // block types and lengths per category (HUFFMAN_CODE_0..3, :3046-3140)
@@ -1108,6 +1202,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
     bool blk_seen = false;       // this lane has requested an input block in this round (see LN_SKIP)
+    bool lit_fresh = false;      // this lane's literal run was announced by a command read in this round
 #if BD_LANE_HEAD_PER_ROUND
     const uint32_t posb0 = posb;
 #endif
@@ -1208,7 +1303,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
                 nskip += e2 & 15u;
               }
             }
-            if (ins != 0) ph = kPhLit;
+            if (ins != 0) { ph = kPhLit; lit_fresh = true; }
             else if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
           }
         }
@@ -1217,6 +1312,35 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         if (ph == kPhDist && ev == kStCommands && !(cmd_bits & (1u << 26)) && bl_d != 0) {
           const uint32_t tvd = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
           LN_LOOKAHEAD(tvd, r_dist, 48u, pc_valid, pc_e, pc_sel);
+        }
+      }
+    }
+    // ---- literal burst (see kBurst): more literals for the lanes inside a run while enough of the warp is ----
+    if (kBurst != 0) {
+      for (uint32_t b = 0; b < kBurst; b++) {
+        // (a lane whose run was only just announced by its command waits for phase P's bounds check of this round)
+        const bool lit = run && ev == kStCommands && ph == kPhLit && ins != 0 && bl_l != 0 && !lit_fresh;
+        if (warp_count(lit) < kBurstLanes) break;
+        if (lit) {
+          uint32_t tv = lit_tv;
+          if (!trivial) {
+            if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; if (kDict && posb - bias < 2) { p1 = 0; p2 = 0; } }
+            const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
+            tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
+          }
+          uint32_t bits, len, sym;
+          LN_DECODE(tv, r_lit, bits, len, sym);
+          (void)bits;
+          bl_l--;
+          append(out_al, bias, hist, posb, acc, sym, 1);
+          p2 = p1; p1 = sym;
+          --ins;
+          LN_SKIP(len);
+          pa_valid = false;
+          if (ins == 0) {
+            if (mlen <= 0) ev = kStHeader;  // a trailing insert without a copy ends the metablock (:2552-2556)
+            else ph = kPhDist;
+          }
         }
       }
     }
@@ -1507,8 +1631,9 @@ BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in,
   uint32_t st = kStIdle;
   if (active) st = stream_begin(c, L, in, in_size, out, out_cap);
   for (;;) {
-    if (st == kStHeader) {
+    while (st == kStHeader) {  // (metablocks without commands -- raw bytes, metadata -- are done on the spot)
       const int r = metablock_begin(c, L, bt);
+      if (r == kLaneNext) { st = L.is_last ? kStFinish : (L.overrun() ? kStBail : kStHeader); continue; }
       st = r == kLaneOk ? kStCommands : (r == kLaneDone ? kStFinish : kStBail);
     }
     warp_sync();

@@ -245,16 +245,36 @@ def test_lane_kernel_takes_the_headline_streams(gpu_lib, pkg, corpus):
 
 
 def test_bails_reach_the_exact_kernel(gpu_lib, pkg, oracle, corpus):
-    """Streams the optimistic kernel gives up (uncompressed metablocks, too small a region, corruption) come back
-    with the exact kernel's codes and sizes; the bail count says they took that path."""
+    """Streams the optimistic kernel gives up (too small a region, truncation, corruption, a large-window header) come
+    back with the exact kernel's codes and sizes; the bail count says they took that path.  Uncompressed and metadata
+    metablocks do NOT bail any more: the lane kernel copies / skips them itself."""
     comp, orig, _ = corpus.make_config("C2", 40)
     rnd = np.random.default_rng(5).integers(0, 256, size=3000, dtype=np.uint8).tobytes()
-    streams = list(comp) + [corpus.compress(rnd, 5), comp[0][: len(comp[0]) // 2], helpers.golden_fixture("x.compressed")]
-    caps = [len(o) for o in orig] + [3000, 65536, 1]
+    bad = bytearray(comp[1]); bad[len(bad) // 3] ^= 0x41
+    lw = helpers.golden_fixture("rnd_chunk.br")
+    streams = list(comp) + [corpus.compress(rnd, 5), comp[0][: len(comp[0]) // 2], helpers.golden_fixture("x.compressed"), bytes(bad), lw]
+    caps = [len(o) for o in orig] + [3000, 65536, 1, 65536, len(oracle.decode(lw, 1 << 24)[2])]
     caps[3] -= 1  # a valid stream with too little room
     pkg.kernel_times(reset=True)
     check_batch(pkg, oracle, streams, caps)
-    assert pkg.kernel_times()["bailed"] >= 3
+    bailed = pkg.kernel_times()["bailed"]
+    assert 4 <= bailed <= 6, bailed   # too small, truncated, corrupt, large window (+ x.compressed into 1 byte); not the raw-bytes stream
+
+
+def test_raw_and_metadata_metablocks_stay_on_the_lane_kernel(gpu_lib, pkg, oracle, corpus):
+    """ISUNCOMPRESSED and metadata metablocks (src/decode.rs:1754-1806, :3031-3045) decoded by the lane kernel: random data at
+    every quality (the encoder stores it raw), fixtures with raw / empty / metadata metablocks, unaligned regions."""
+    rng = np.random.default_rng(6)
+    streams, caps = [], []
+    for size in (1, 17, 3000, 65536, 200000):
+        for q in (0, 1, 5, 9, 11):
+            data = rng.integers(0, 256, size=size, dtype=np.uint8).tobytes()
+            streams.append(corpus.compress(data, q)); caps.append(size)
+    for name in SMALL:
+        streams.append(helpers.golden_fixture(name)); caps.append(MAN[name]["original_size"])
+    pkg.kernel_times(reset=True)
+    n_ok = check_batch(pkg, oracle, streams, caps)
+    assert n_ok == len(streams) and pkg.kernel_times()["bailed"] <= 1  # (rnd_chunk.br is in SMALL only if it has an original)
 
 
 @pytest.mark.parametrize("mode", ["exact_only", "lane_warps_8", "lane_warps_16"])
