@@ -54,8 +54,9 @@ def kernel_source_hash():
 def measured_traffic(kernel, streams_per_launch):
     """DRAM bytes per launch of the dominant kernel from profiles/current_traffic.json (written by profiles/gpu_round.sh from
     one `ncu --set full` capture: dram__bytes_read.sum + dram__bytes_write.sum, kernel source hash, launch shape).  None when
-    the capture is stale (other kernel sources) or was taken at another launch shape (bytes per stream depend on how many
-    windows compete for L2, so they are only scaled within +-25 % of the captured stream count)."""
+    the capture is stale (other kernel sources) or was taken at another launch shape: bytes per stream depend on how many
+    windows compete for L2 -- the resident lanes (66 304) for every launch of at least one wave, so whole-wave launches are
+    scaled by their stream count; a launch below one wave only within +-25 % of the captured count."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "current_traffic.json")))
     except (OSError, ValueError):
@@ -65,7 +66,8 @@ def measured_traffic(kernel, streams_per_launch):
     if t.get("kernel") not in kernel:
         return None, "capture is of another kernel"
     k = float(streams_per_launch) / float(t["streams_per_launch"])
-    if not 0.75 <= k <= 1.25:
+    one_wave = 148 * 14 * 32
+    if not (0.75 <= k <= 1.25 or (streams_per_launch >= one_wave and t["streams_per_launch"] >= one_wave)):
         return None, "capture has %d streams per launch" % t["streams_per_launch"]
     return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * k), "profiles/current_traffic.json (%s, %d streams per launch)" % (
         t.get("captured", "?"), t["streams_per_launch"])
