@@ -48,6 +48,7 @@ states = [pkg.DecoderState() for _ in range(n)]
 pos = [0] * n; pend = [b""] * n; res_code = [2] * n; total = 0
 launch0 = pkg.kernel_launch_count()
 rounds = 0
+round_ms = []
 t0 = time.perf_counter()
 t_oracle = 0.0
 while any(r in (2, 3) for r in res_code):
@@ -56,7 +57,9 @@ while any(r in (2, 3) for r in res_code):
         if res_code[i] == 2:
             c = comps[i % U]
             pend[i] = c[pos[i]:pos[i] + piece]; pos[i] += len(pend[i])
+    tr = time.perf_counter()
     got = pkg.decompress_stream_batch([states[i] for i in idx], [pend[i] for i in idx], [1 << 17] * len(idx))
+    round_ms.append(round((time.perf_counter() - tr) * 1e3, 1))
     for i, g in zip(idx, got):
         if i in ostreams:
             t1 = time.perf_counter()
@@ -69,6 +72,6 @@ dt = time.perf_counter() - t0 - t_oracle
 assert all(r == 1 for r in res_code) and total == sum(len(datas[i % U]) for i in range(n))
 print(json.dumps({"experiment": "multiplexed sessions", "sessions": n, "piece_bytes": piece, "rounds": rounds, "decompressed_GB": round(total / 1e9, 3),
                   "wall_s": round(dt, 3), "GBps": round(total / dt / 1e9, 3), "kernel_launches": pkg.kernel_launch_count() - launch0,
-                  "oracle_checked_sessions": len(check), "call_by_call_equal": True}), flush=True)
+                  "oracle_checked_sessions": len(check), "call_by_call_equal": True, "call_ms_per_round": round_ms}), flush=True)
 for s in states:
     s.close()

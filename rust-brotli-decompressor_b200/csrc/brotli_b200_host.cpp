@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/brotli_b200/decode.h"
@@ -126,6 +127,13 @@ struct DeviceCtx {
   DevBuf in, out, in_off, out_off, out_len, codes, in_used;
   DevBuf cdict;            // custom LZ77 dictionary of the batch in flight
   DevBuf sess_states, sess_pieces, sess_blob;  // staging of a session launch: ResumeState[], SessionCopy[], bytes
+  void* sess_pin_up = nullptr; size_t sess_pin_up_cap = 0;      // pinned host staging of the sessions' fresh input ...
+  void* sess_pin_down = nullptr; size_t sess_pin_down_cap = 0;  // ... and of their new output
+  // session buffers are recycled through power-of-two size classes (a state opens with three device buffers; thousands of
+  // states must not mean thousands of cudaMalloc calls per second): free lists per class, small classes cut from slabs
+  std::vector<uint8_t*> sess_free[48];
+  std::vector<void*> sess_slabs;
+  std::unordered_map<uint8_t*, int> sess_class;  // live block -> size class
   DevBuf redo_out;         // output windows of the exact re-decode of NeedsMoreOutput one-shots
   // pinned host staging of the scattered-batch entry (BrotliB200DecompressBatch): grow-only
   void* pin_in = nullptr; size_t pin_in_cap = 0;
@@ -398,12 +406,48 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
 // All of it runs on s_compute under c->mu (the staging buffers are the context's).
 struct CudaDev {
   DeviceCtx* c;
+  // Size-class allocator over cudaMalloc: every live block has its class in a host-side map (address -> class).
+  std::unordered_map<uint8_t*, int>& classes() { return c->sess_class; }
   uint8_t* alloc(size_t n) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return (uint8_t*)p;
+    int k = 12;  // 4 KiB minimum
+    while (((size_t)1 << k) < n) k++;
+    if (k >= 48) return nullptr;
+    auto& fl = c->sess_free[k];
+    if (fl.empty()) {
+      const size_t sz = (size_t)1 << k;
+      const size_t per_slab = sz <= ((size_t)4 << 20) ? (((size_t)32 << 20) / sz > 64 ? 64 : ((size_t)32 << 20) / sz) : 1;  // up to 32 MB / 64 blocks per cudaMalloc
+      void* p = nullptr;
+      if (cudaMalloc(&p, sz * per_slab) != cudaSuccess) {
+        cudaGetLastError();
+        if (per_slab == 1 || cudaMalloc(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        c->sess_slabs.push_back(p);
+        fl.push_back((uint8_t*)p);
+      } else {
+        c->sess_slabs.push_back(p);
+        for (size_t j = 0; j < per_slab; j++) fl.push_back((uint8_t*)p + j * sz);
+      }
+    }
+    uint8_t* r = fl.back(); fl.pop_back();
+    classes()[r] = k;
+    return r;
   }
-  void release(uint8_t* p) { if (p) cudaFree(p); }
+  void release(uint8_t* p) {
+    if (!p) return;
+    auto it = classes().find(p);
+    if (it == classes().end()) return;
+    c->sess_free[it->second].push_back(p);
+    classes().erase(it);
+  }
+  uint8_t* host_up(size_t bytes) {
+    if (bytes > c->sess_pin_up_cap) {
+      if (c->sess_pin_up) cudaFreeHost(c->sess_pin_up);
+      c->sess_pin_up = nullptr; c->sess_pin_up_cap = 0;
+      const size_t want = bytes + bytes / 2 + 65536;
+      if (cudaHostAlloc(&c->sess_pin_up, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      c->sess_pin_up_cap = want;
+    }
+    return (uint8_t*)c->sess_pin_up;
+  }
   size_t arena_bytes() const { return brotli_b200::arena_bytes_per_warp(); }
   int upload(uint8_t* d, const uint8_t* h, size_t n) {
     return cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : BROTLI_DECODER_ERROR_UNREACHABLE;
@@ -435,15 +479,21 @@ struct CudaDev {
     CU_TRY(cudaStreamSynchronize(c->s_compute));
     return 0;
   }
-  int gather(const brotli_b200::SessionCopy* pieces, uint32_t n, uint8_t* host, size_t bytes) {
-    CU_TRY(c->sess_blob.reserve(bytes + 16));
+  const uint8_t* gather(const brotli_b200::SessionCopy* pieces, uint32_t n, size_t bytes) {
+    if (bytes + 16 > c->sess_pin_down_cap) {
+      if (c->sess_pin_down) cudaFreeHost(c->sess_pin_down);
+      c->sess_pin_down = nullptr; c->sess_pin_down_cap = 0;
+      const size_t want = bytes + bytes / 2 + 65536;
+      if (cudaHostAlloc(&c->sess_pin_down, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      c->sess_pin_down_cap = want;
+    }
+    if (c->sess_blob.reserve(bytes + 16) != cudaSuccess) return nullptr;
     std::vector<brotli_b200::SessionCopy> v(pieces, pieces + n);
     for (auto& k : v) k.dst = (uint8_t*)c->sess_blob.p + (uintptr_t)k.dst;
-    int rc = copy_pieces(v);
-    if (rc != 0) return rc;
-    CU_TRY(cudaMemcpyAsync(host, c->sess_blob.p, bytes, cudaMemcpyDeviceToHost, c->s_compute));
-    CU_TRY(cudaStreamSynchronize(c->s_compute));
-    return 0;
+    if (copy_pieces(v) != 0) return nullptr;
+    if (cudaMemcpyAsync(c->sess_pin_down, c->sess_blob.p, bytes, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
+        cudaStreamSynchronize(c->s_compute) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (const uint8_t*)c->sess_pin_down;
   }
   int move(const brotli_b200::SessionCopy* pieces, uint32_t n) {
     std::vector<brotli_b200::SessionCopy> v(pieces, pieces + n);
@@ -968,6 +1018,13 @@ void BrotliB200Shutdown(void) {  // (open decoder states keep their own device b
     c->xdict = nullptr;
     c->lane_arena = nullptr; c->lane_ctas = 0; c->bail_list.release(); c->order.release();
     c->sess_states.release(); c->sess_pieces.release(); c->sess_blob.release(); c->redo_out.release(); c->cdict.release();
+    if (c->sess_pin_up) cudaFreeHost(c->sess_pin_up);
+    if (c->sess_pin_down) cudaFreeHost(c->sess_pin_down);
+    c->sess_pin_up = c->sess_pin_down = nullptr; c->sess_pin_up_cap = c->sess_pin_down_cap = 0;
+    for (void* p : c->sess_slabs) cudaFree(p);
+    c->sess_slabs.clear();
+    for (auto& fl : c->sess_free) fl.clear();
+    c->sess_class.clear();
     c->in.release(); c->out.release(); c->in_off.release(); c->out_off.release(); c->out_len.release(); c->codes.release(); c->in_used.release();
     if (c->pin_in) cudaFreeHost(c->pin_in);
     if (c->pin_out) cudaFreeHost(c->pin_out);

@@ -121,9 +121,10 @@ int query_resident_ctas(int device) {
 cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
-  // a small batch whose size the host knows does not need every resident CTA (launch and drain cost)
+  // a small batch whose size the host knows does not need every resident CTA (launch and drain cost) -- but its streams
+  // should still spread over the SMs: at most four per CTA
   if (!a.n_ptr) {
-    const int need = (int)((a.n + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int need = (int)((a.n + 3) / 4);
     if (need < ctas) ctas = need < 1 ? 1 : need;
   }
   brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, kDynamicSharedBytes, stream>>>(a);

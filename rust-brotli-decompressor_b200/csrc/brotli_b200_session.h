@@ -63,8 +63,9 @@ struct Session {
 };
 
 // Dev: uint8_t* alloc(size_t) / void release(uint8_t*) / int upload(dst, src, n) /
-//      int run(ResumeState* sessions, n, const uint8_t* blob, blob_bytes, SessionCopy* scatter, n_scatter)   (scatter[i].src = offset into blob)
-//      int gather(SessionCopy* pieces, n, uint8_t* host_blob, bytes)                                          (pieces[i].dst = offset into blob)
+//      uint8_t* host_up(bytes)     staging memory on the host for the batch's fresh input (pinned on a GPU)
+//      int run(ResumeState* sessions, n, const uint8_t* blob, blob_bytes, SessionCopy* scatter, n_scatter)   (blob = host_up(); scatter[i].src = offset into blob)
+//      const uint8_t* gather(SessionCopy* pieces, n, bytes)   new output -> one host blob (pieces[i].dst = offset into it), nullptr on error
 //      int move(SessionCopy* pieces, n)                                                                       device -> device
 //      size_t arena_bytes()
 template <class Dev>
@@ -134,7 +135,11 @@ struct SessionRunner {
     }
     if (todo.empty()) return 0;
     // ---- fresh input: one blob for the whole batch ----
-    std::vector<uint8_t> blob;
+    size_t blob_need = 0;
+    for (uint32_t i : todo) blob_need += *cs[i].available_in;
+    uint8_t* const blob = dev.host_up(blob_need + 16);
+    size_t blob_size = 0;
+    if (!blob) { for (uint32_t i : todo) fail(*ss[i], cs[i], device_error_code); return device_error_code; }
     std::vector<SessionCopy> scatter;
     std::vector<size_t> fresh(n, 0);
     for (uint32_t i : todo) {
@@ -149,8 +154,9 @@ struct SessionRunner {
         if (!s.d_dict || dev.upload(s.d_dict + 32, s.dict.data(), s.dict.size()) != 0) { fail(s, c, -26); continue; }
       }
       if (k) {
-        scatter.push_back(SessionCopy{(const uint8_t*)(uintptr_t)blob.size(), s.d_in[s.in_sel] + s.in_len, k});
-        blob.insert(blob.end(), *c.next_in, *c.next_in + k);
+        scatter.push_back(SessionCopy{(const uint8_t*)(uintptr_t)blob_size, s.d_in[s.in_sel] + s.in_len, k});
+        memcpy(blob + blob_size, *c.next_in, k);
+        blob_size += k;
         s.in_len += k;
       }
     }
@@ -193,7 +199,7 @@ struct SessionRunner {
         pre_moves.clear();
         if (mrc != 0) { for (uint32_t i : live) fail(*ss[i], cs[i], device_error_code); return mrc; }
       }
-      const int rc = dev.run(arr.data(), (uint32_t)arr.size(), first ? blob.data() : nullptr, first ? blob.size() : 0,
+      const int rc = dev.run(arr.data(), (uint32_t)arr.size(), first ? blob : nullptr, first ? blob_size : 0,
                              first ? scatter.data() : nullptr, first ? (uint32_t)scatter.size() : 0u);
       first = false;
       if (rc != 0) { for (uint32_t i : live) fail(*ss[i], cs[i], device_error_code); return rc; }
@@ -226,12 +232,11 @@ struct SessionRunner {
       }
     }
     if (!gather.empty()) {
-      std::vector<uint8_t> down(out_bytes);
-      const int rc = dev.gather(gather.data(), (uint32_t)gather.size(), down.data(), out_bytes);
-      if (rc != 0) { for (uint32_t i : todo) if (cs[i].result == -1) fail(*ss[i], cs[i], device_error_code); return rc; }
+      const uint8_t* down = dev.gather(gather.data(), (uint32_t)gather.size(), out_bytes);
+      if (!down) { for (uint32_t i : todo) if (cs[i].result == -1) fail(*ss[i], cs[i], device_error_code); return device_error_code; }
       for (size_t k = 0; k < got.size(); k++) {
         Session& s = *ss[got[k]];
-        const uint8_t* p = down.data() + (uintptr_t)gather[k].dst;
+        const uint8_t* p = down + (uintptr_t)gather[k].dst;
         s.pending.insert(s.pending.end(), p, p + gather[k].n);
         s.fetched += gather[k].n;
       }

@@ -96,9 +96,12 @@ struct HostDev {
     }
     return 0;
   }
-  int gather(const SessionCopy* p, uint32_t n, uint8_t* host, size_t) {
-    for (uint32_t i = 0; i < n; i++) memcpy(host + (uintptr_t)p[i].dst, p[i].src, p[i].n);
-    return 0;
+  std::vector<uint8_t> up, down;
+  uint8_t* host_up(size_t bytes) { if (up.size() < bytes) up.resize(bytes); return up.data(); }
+  const uint8_t* gather(const SessionCopy* p, uint32_t n, size_t bytes) {
+    if (down.size() < bytes + 1) down.resize(bytes + 1);
+    for (uint32_t i = 0; i < n; i++) memcpy(down.data() + (uintptr_t)p[i].dst, p[i].src, p[i].n);
+    return down.data();
   }
   int move(const SessionCopy* p, uint32_t n) { for (uint32_t i = 0; i < n; i++) memmove(p[i].dst, p[i].src, p[i].n); return 0; }
 };
