@@ -201,6 +201,10 @@ DeviceCtx* acquire_ctx() {
     c->lane_ctas = brotli_b200::query_lane_resident_ctas(dev, c->lane_warps);
     if (c->lane_ctas <= 0) { set_error("brotli_b200: occupancy query of the lane kernel failed"); return nullptr; }
     c->lane_slot_bytes = brotli_b200::lane_slot_bytes(c->lane_warps);
+    if (const char* slot_env = getenv("BROTLI_B200_LANE_SLOT_BYTES")) {  // experiments: a smaller table slot than the geometry allows
+      const uint32_t v = ((uint32_t)atoi(slot_env) / 4u) | 1u;            // (an odd number of words, see lane_slot_bytes)
+      if (v * 4u >= 80u && v * 4u <= c->lane_slot_bytes) c->lane_slot_bytes = v * 4u;
+    }
     const size_t lane_bytes = (size_t)c->lane_ctas * c->lane_warps * 32 * brotli_b200::lane_arena_bytes_per_lane();
     if (cudaMalloc((void**)&c->lane_arena, lane_bytes) != cudaSuccess) {
       set_error(std::string("brotli_b200: lane arena allocation failed: ") + cudaGetErrorString(cudaGetLastError()));

@@ -173,6 +173,8 @@ int query_lane_resident_ctas(int device, int warps) {
     case 16: per_sm = lane_occupancy<16>(dyn); break;
     case 20: per_sm = lane_occupancy<20>(dyn); break;
     case 24: per_sm = lane_occupancy<24>(dyn); break;
+    case 28: per_sm = lane_occupancy<28>(dyn); break;
+    case 32: per_sm = lane_occupancy<32>(dyn); break;
     default: return -1;
   }
   if (per_sm < 1) return -1;
@@ -180,7 +182,7 @@ int query_lane_resident_ctas(int device, int warps) {
 }
 
 // the dictionary instance exists for the default geometry only
-bool lane_kernel_takes_dictionary(int warps) { return warps == 14; }
+bool lane_kernel_takes_dictionary(int warps) { return warps == kLaneWarpsPerCta; }
 
 cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream) {
   if (la.cdict_len != 0 && !lane_kernel_takes_dictionary(warps)) return cudaErrorInvalidValue;
@@ -189,21 +191,21 @@ cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas,
   e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   const uint32_t dyn = (la.slot_bytes + 128u) * (uint32_t)(warps * 32);
+  if (la.cdict_len != 0) {  // (the default geometry: checked above)
+    if (cudaFuncSetAttribute(brotli_decode_lane_kernel<kLaneWarpsPerCta, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return cudaGetLastError();
+    brotli_decode_lane_kernel<kLaneWarpsPerCta, true><<<ctas, kLaneWarpsPerCta * 32, dyn, stream>>>(a, la);
+    return cudaGetLastError();
+  }
   switch (warps) {
     case 4: brotli_decode_lane_kernel<4><<<ctas, 128, dyn, stream>>>(a, la); break;
     case 8: brotli_decode_lane_kernel<8><<<ctas, 256, dyn, stream>>>(a, la); break;
     case 12: brotli_decode_lane_kernel<12><<<ctas, 384, dyn, stream>>>(a, la); break;
-    case 14:
-      if (la.cdict_len != 0) {
-        if (cudaFuncSetAttribute(brotli_decode_lane_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return cudaGetLastError();
-        brotli_decode_lane_kernel<14, true><<<ctas, 448, dyn, stream>>>(a, la);
-      } else {
-        brotli_decode_lane_kernel<14><<<ctas, 448, dyn, stream>>>(a, la);
-      }
-      break;
+    case 14: brotli_decode_lane_kernel<14><<<ctas, 448, dyn, stream>>>(a, la); break;
     case 16: brotli_decode_lane_kernel<16><<<ctas, 512, dyn, stream>>>(a, la); break;
     case 20: brotli_decode_lane_kernel<20><<<ctas, 640, dyn, stream>>>(a, la); break;
     case 24: brotli_decode_lane_kernel<24><<<ctas, 768, dyn, stream>>>(a, la); break;
+    case 28: brotli_decode_lane_kernel<28><<<ctas, 896, dyn, stream>>>(a, la); break;
+    case 32: brotli_decode_lane_kernel<32><<<ctas, 1024, dyn, stream>>>(a, la); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -26,7 +26,7 @@ constexpr uint32_t kDynamicSharedBytes = kWarpsPerCta * kWarpSharedBytes;
 // Lane kernel (brotli_b200_lane_kernel.cu): one stream per lane, one persistent CTA per SM; the SM's
 // shared memory is split into one private table slot per lane, so fewer warps mean wider root tables.
 #ifndef BROTLI_B200_LANE_WARPS_PER_CTA
-#define BROTLI_B200_LANE_WARPS_PER_CTA 14
+#define BROTLI_B200_LANE_WARPS_PER_CTA 20
 #endif
 constexpr int kLaneWarpsPerCta = BROTLI_B200_LANE_WARPS_PER_CTA;
 

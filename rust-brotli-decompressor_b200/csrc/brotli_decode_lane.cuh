@@ -73,6 +73,27 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #ifndef BD_LANE_BURST
 #define BD_LANE_BURST 0
 #endif
+// narrowest root a group may get in the shared slot, and the weights of the three symbol kinds in the root-width allocation
+// per-metablock table construction without the sort arrays (temporaries in the shared staging area)
+#ifndef BD_LANE_HEADER_V2
+#define BD_LANE_HEADER_V2 0
+#endif
+// one input-block request per round instead of one test per bit skip
+#ifndef BD_LANE_SKIP_LITE
+#define BD_LANE_SKIP_LITE 0
+#endif
+#ifndef BD_LANE_NARROW_ROOTS
+#define BD_LANE_NARROW_ROOTS 0
+#endif
+#ifndef BD_LANE_W_LIT
+#define BD_LANE_W_LIT 1
+#endif
+#ifndef BD_LANE_W_CMD
+#define BD_LANE_W_CMD 1
+#endif
+#ifndef BD_LANE_W_DIST
+#define BD_LANE_W_DIST 1
+#endif
 #ifndef BD_LANE_BURST_LANES
 #define BD_LANE_BURST_LANES 12
 #endif
@@ -89,6 +110,7 @@ enum : int { kLaneOk = 0, kLaneDone = 1, kLaneBail = 2, kLaneNext = 3 };  // kLa
 constexpr uint32_t kMaxLaneRaw = 1u << 18;  // uncompressed metablocks up to this size are copied by the lane itself (one active lane): larger ones go to the exact kernel
 
 #if defined(BROTLI_B200_HOSTSIM)
+static inline void sts8(hw::sref_t a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
 static inline void sts16(hw::sref_t a, uint32_t v) { *(uint16_t*)a = (uint16_t)v; }
 static inline void sts32(hw::sref_t a, uint32_t v) { *(uint32_t*)a = v; }
 static inline uint32_t vlds16(hw::sref_t a) { return *(const uint16_t*)a; }
@@ -126,6 +148,7 @@ static inline void cp_async_wait_all_but_latest() {}
 static inline void cp_async_wait_all() {}
 #else
 // volatile: these loads follow stores to the same slot (table fill) made through asm as well
+BD_DEV void sts8(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 BD_DEV void sts16(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 BD_DEV void sts32(hw::sref_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 BD_DEV uint32_t vlds16(hw::sref_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -253,6 +276,31 @@ BD_DEV uint32_t ring_next(const uint8_t* gin, hw::sref_t ring, uint32_t ring_str
   return vlds32(ring + ((j >> 2) & 1u) * ring_stride + (j & 3u) * 4u);
 }
 
+// Register copy of a lane's bit window for the loops of the per-metablock code.  The Lane record itself lives in
+// local memory (its address is passed around), so every store through a byte pointer or an asm statement with a
+// memory clobber would force its fields back to memory and in again -- an L2 round trip each.
+struct BitWin {
+  const uint8_t* gin;
+  hw::sref_t ring;
+  uint32_t ring_stride, lo, hi, nx, k, bp, last_blk;
+  uint64_t end_bit;
+  BD_DEV uint32_t peek() const { return hw::funnelshift_r(lo, hi, bp); }
+  BD_DEV void skip(uint32_t n) {
+    bp += n;
+    if (bp >= 32) {
+      lo = hi; hi = nx; k++;
+      nx = ring_next(gin, ring, ring_stride, last_blk, k + 2);
+      bp -= 32;
+    }
+  }
+  BD_DEV uint32_t read(uint32_t n) {  // n <= 25
+    const uint32_t v = peek() & mask_bits(n);
+    skip(n);
+    return v;
+  }
+  BD_DEV bool overrun() const { return (uint64_t)k * 32 + bp > end_bit; }
+};
+
 // Decoder state of one lane's stream.  Lives in local memory for the per-metablock (cold) code; the
 // command loop works on register copies.
 struct Lane {
@@ -302,6 +350,13 @@ struct Lane {
   }
   BD_DEV bool overrun() const { return (uint64_t)k * 32 + bp > end_bit; }
   BD_DEV uint32_t pos() const { return posb - bias; }
+  BD_DEV BitWin win() const {
+    BitWin b;
+    b.gin = gin; b.ring = ring; b.ring_stride = ring_stride; b.lo = lo; b.hi = hi; b.nx = nx; b.k = k; b.bp = bp;
+    b.last_blk = last_blk; b.end_bit = end_bit;
+    return b;
+  }
+  BD_DEV void put(const BitWin& b) { lo = b.lo; hi = b.hi; nx = b.nx; k = b.k; bp = b.bp; }
 };
 
 // ---- virtual table space ----
@@ -315,7 +370,8 @@ BD_DEV void tab_store(const LaneCtx& c, uint32_t v, uint32_t e) {
 // One symbol of the tree whose root (2^rbits entries) starts at virtual index root_v.
 // Entry = symbol << 4 | code length; length > rbits marks a pointer: its second-level table starts at
 // virtual index E + 4 * value and is indexed by the next (length - rbits) bits.
-BD_DEV uint32_t decode_generic(const LaneCtx& c, Lane& L, uint32_t root_v, uint32_t rbits) {
+template <class Reader>
+BD_DEV uint32_t decode_generic(const LaneCtx& c, Reader& L, uint32_t root_v, uint32_t rbits) {
   const uint32_t bits = L.peek();
   uint32_t e = tab_load(c, root_v + (bits & mask_bits(rbits)));
   uint32_t len = e & 15u;
@@ -415,6 +471,212 @@ BD_DEV uint32_t read_varlen8(Lane& L) {
 
 BD_DEV uint32_t bit_width(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++; } return r; }  // Log2Floor of src/decode.rs:502-509
 
+#if BD_LANE_HEADER_V2
+// ---- prefix-code tables from code lengths ----
+// Temporaries live in the lane's 64-byte cp.async landing zone (c.stage), which is idle outside the command loop:
+// [0..31] count[16] (u16: symbols per code length), [32..63] first the 5-bit lookup of the code-length code (u8[32]),
+// then next_code[16] (u16: the next canonical code of each length).  Local memory only holds the code lengths
+// themselves (one byte per symbol, read back four at a time): every access there is an L2 round trip.
+BD_DEV hw::sref_t tmp_count(const LaneCtx& c, uint32_t l) { return c.stage + 2u * l; }
+BD_DEV hw::sref_t tmp_next(const LaneCtx& c, uint32_t l) { return c.stage + 32u + 2u * l; }
+
+// Roots and second-level tables of one prefix code, canonical codes in bit-reversed order: the shape of
+// BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386) with our root width.  count[] (shared) holds the symbols per
+// length; the code is complete (checked by the caller).  Root of 2^rbits entries at virtual index root_v; codes
+// longer than the root go to second-level tables allocated from L.cold_next (always in the arena), one per root
+// prefix, as wide as the longest code under that prefix.  Prepares next_code[]; the entries themselves are written
+// by place_symbol for every symbol in increasing order (which is canonical order within a length).
+BD_DEV int begin_table(const LaneCtx& c, uint32_t& cold_next, uint32_t root_v, uint32_t rbits) {
+  // ascending lengths: first code of each length; provisional root entries (sub-table width) of the long prefixes
+  uint32_t f = 0, p0 = 0;
+  for (uint32_t l = 1; l <= 15; l++) {
+    const uint32_t n = vlds16(tmp_count(c, l));
+    sts16(tmp_next(c, l), f);
+    if (l > rbits && n != 0) {
+      const uint32_t sh = l - rbits;
+      const uint32_t plo = f >> sh, phi = (f + n - 1) >> sh;
+      for (uint32_t pfx = plo; pfx <= phi; pfx++) tab_store(c, root_v + (rbits ? hw::brev(pfx) >> (32 - rbits) : 0u), sh);
+    }
+    f += n;
+    if (l == rbits) p0 = f;  // prefixes below p0 are codes no longer than the root
+    f <<= 1;
+  }
+  // sub-tables in prefix order
+  for (uint32_t pfx = p0; pfx < (1u << rbits); pfx++) {
+    const uint32_t v = root_v + (rbits ? hw::brev(pfx) >> (32 - rbits) : 0u);
+    const uint32_t sub_w = tab_load(c, v);
+    const uint32_t sub_v = cold_next - c.E;  // index into the arena part
+    const uint32_t sub_size = sub_w < 2 ? 4u : 1u << sub_w;  // every arena allocation is a multiple of four entries
+    if (sub_v + sub_size > kGlobalTab) return kLaneBail;
+    cold_next += sub_size;
+    tab_store(c, v, ((sub_v >> 2) << 4) | (rbits + sub_w));
+  }
+  return kLaneOk;
+}
+BD_DEV void place_symbol(const LaneCtx& c, uint32_t root_v, uint32_t rbits, uint32_t sym, uint32_t l) {
+  const hw::sref_t nc = tmp_next(c, l);
+  const uint32_t code = vlds16(nc);
+  sts16(nc, code + 1);
+  const uint32_t rev = hw::brev(code) >> (32 - l);
+  const uint32_t e = (sym << 4) | l;
+  if (l <= rbits) {
+    for (uint32_t t = rev; t < (1u << rbits); t += 1u << l) tab_store(c, root_v + t, e);
+  } else {
+    const uint32_t ptr = tab_load(c, root_v + (rev & mask_bits(rbits)));
+    const uint32_t sub_v = (ptr >> 4) << 2, sub_w = (ptr & 15u) - rbits;
+    for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) c.gtab[sub_v + t] = (uint16_t)e;
+  }
+}
+
+// ReadHuffmanCode, src/decode.rs:868-1013: one prefix-code description -> lookup structure.
+BD_DEV int read_huffman_code_impl(const LaneCtx& c, BitWin& L, uint32_t& cold_next, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits) {
+  for (uint32_t l = 0; l < 16; l += 2) sts32(c.stage + 2u * l, 0u);  // count[]
+  const uint32_t hskip = L.read(2);
+  if (hskip == 1) {  // simple code: NSYM 1..4 explicit symbols (ReadSimpleHuffmanSymbols, :516-556)
+    const uint32_t nsym = L.read(2) + 1;
+    const uint32_t max_bits = bit_width(alphabet_size - 1);
+    uint32_t s[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < nsym; i++) {
+      s[i] = L.read(max_bits);
+      if (s[i] >= max_symbol) return kLaneBail;
+    }
+    for (uint32_t i = 0; i + 1 < nsym; i++)
+      for (uint32_t k = i + 1; k < nsym; k++) if (s[i] == s[k]) return kLaneBail;
+    if (nsym == 1) {
+      for (uint32_t t = 0; t < (1u << rbits); t++) tab_store(c, root_v + t, s[0] << 4);
+      return kLaneOk;
+    }
+    // canonical codes sorted by (length, value) reproduce BrotliBuildSimpleHuffmanTable (src/huffman/mod.rs:390-471)
+    uint32_t len[4] = {1, 1, 0, 0};
+    if (nsym == 3) { len[1] = 2; len[2] = 2; }
+    if (nsym == 4) {
+      if (L.read(1)) { len[0] = 1; len[1] = 2; len[2] = 3; len[3] = 3; } else { len[0] = len[1] = len[2] = len[3] = 2; }
+    }
+    for (uint32_t i = 0; i < nsym; i++) { const hw::sref_t cn = tmp_count(c, len[i]); sts16(cn, vlds16(cn) + 1); }
+    if (begin_table(c, cold_next, root_v, rbits) != kLaneOk) return kLaneBail;
+    // symbols in increasing order (four at most: selection by value)
+    uint32_t done = 0;
+    for (uint32_t n = 0; n < nsym; n++) {
+      uint32_t best = 4;
+      for (uint32_t i = 0; i < nsym; i++) if (!((done >> i) & 1u) && (best == 4 || s[i] < s[best])) best = i;
+      done |= 1u << best;
+      place_symbol(c, root_v, rbits, s[best], len[best]);
+    }
+    return kLaneOk;
+  }
+  // complex code: code-length code lengths (ReadCodeLengthCodeLengths, :801-853), four bits each in cl_lo (symbols
+  // 0..7), cl_mid (8..15), cl_hi (16, 17)
+  uint32_t cl_lo = 0, cl_mid = 0, cl_hi = 0;
+  uint32_t space = 32, num_codes = 0;
+  for (uint32_t i = hskip; i < 18; i++) {
+    const uint32_t ix = L.peek() & 15u;
+    // kCodeLengthPrefixLength / kCodeLengthPrefixValue (src/decode.rs:59-61) packed four bits per entry
+    const uint32_t plen = (uint32_t)(0x4222322242223222ull >> (ix * 4)) & 15u;
+    const uint32_t v = (uint32_t)(0x5340234013402340ull >> (ix * 4)) & 15u;
+    L.skip(plen);
+    const uint32_t sy = tbl::kCodeLengthCodeOrder[i];
+    const uint32_t vv = v << ((sy & 7u) * 4u);
+    if (sy < 8) cl_lo |= vv; else if (sy < 16) cl_mid |= vv; else cl_hi |= vv;
+    if (v != 0) {
+      space -= 32u >> v;
+      num_codes++;
+      if (space - 1u >= 32u) break;  // space is 0 or wrapped
+    }
+  }
+  if (!(num_codes == 1 || space == 0)) return kLaneBail;
+  // 5-bit lookup of the code-length code (BrotliBuildCodeLengthsHuffmanTable, src/huffman/mod.rs:196-271): symbol << 3 | length
+  const hw::sref_t cl_tab = c.stage + 32u;
+#define BD_CL_CL(sy) ((((sy) < 8 ? cl_lo : ((sy) < 16 ? cl_mid : cl_hi)) >> (((sy) & 7u) * 4u)) & 15u)
+  if (num_codes == 1) {
+    uint32_t only = 0;
+    for (uint32_t i = 0; i < 18; i++) if (BD_CL_CL(i)) only = i;
+    for (uint32_t t = 0; t < 32; t += 4) sts32(cl_tab + t, (only << 3) * 0x01010101u);
+  } else {
+    // symbols per length (five bits each), then canonical codes in symbol order
+    uint32_t cnt = 0;
+    for (uint32_t sy = 0; sy < 18; sy++) { const uint32_t l = BD_CL_CL(sy); if (l) cnt += 1u << (5u * (l - 1u)); }
+    uint32_t next = 0, f = 0;  // next code of each length (six bits each)
+    for (uint32_t l = 1; l <= 5; l++) {
+      next |= f << (6u * (l - 1u));
+      f = (f + ((cnt >> (5u * (l - 1u))) & 31u)) << 1;
+    }
+    for (uint32_t sy = 0; sy < 18; sy++) {
+      const uint32_t l = BD_CL_CL(sy);
+      if (!l) continue;
+      const uint32_t code = (next >> (6u * (l - 1u))) & 63u;
+      next += 1u << (6u * (l - 1u));
+      const uint32_t rev = hw::brev(code) >> (32 - l);
+      for (uint32_t t = rev; t < 32; t += 1u << l) sts8(cl_tab + t, (sy << 3) | l);
+    }
+  }
+#undef BD_CL_CL
+  // symbol code lengths with repeat codes (ReadSymbolCodeLengths, :661-731; Process*CodeLength :565-658)
+  uint32_t cl_words[176];  // one byte per symbol, read back four at a time
+  uint8_t* const cl = (uint8_t*)cl_words;
+  uint32_t symbol = 0, prev_len = 8, repeat = 0, repeat_len = 0;
+  space = 32768;
+  if (max_symbol > 704) return kLaneBail;
+  while (symbol < max_symbol && space > 0) {
+    const uint32_t p = vlds8(cl_tab + (L.peek() & 31u));
+    L.skip(p & 7u);
+    const uint32_t code_len = p >> 3;
+    if (code_len < 16) {
+      repeat = 0;
+      cl[symbol] = (uint8_t)code_len;
+      if (code_len != 0) {
+        prev_len = code_len;
+        space -= 32768u >> code_len;
+        const hw::sref_t cn = tmp_count(c, code_len);
+        sts16(cn, vlds16(cn) + 1);
+      }
+      symbol++;
+    } else {
+      const uint32_t extra_bits = code_len - 14;
+      uint32_t delta = L.read(extra_bits);
+      const uint32_t new_len = code_len == 16 ? prev_len : 0;
+      if (repeat_len != new_len) { repeat = 0; repeat_len = new_len; }
+      const uint32_t old_repeat = repeat;
+      if (repeat > 0) { repeat -= 2; repeat <<= extra_bits; }
+      repeat += delta + 3;
+      delta = repeat - old_repeat;
+      if (symbol + delta > max_symbol) { space = 0xFFFFF; break; }
+      for (uint32_t j = 0; j < delta; j++) cl[symbol + j] = (uint8_t)repeat_len;
+      symbol += delta;
+      if (repeat_len != 0) {
+        space -= delta << (15 - repeat_len);
+        const hw::sref_t cn = tmp_count(c, repeat_len);
+        sts16(cn, vlds16(cn) + delta);
+      }
+    }
+  }
+  if (space != 0) return kLaneBail;
+  if (begin_table(c, cold_next, root_v, rbits) != kLaneOk) return kLaneBail;  // (overwrites the code-length lookup)
+  // symbols in increasing order; the words holding their lengths are loaded two iterations ahead
+  const uint32_t nw = (symbol + 3) >> 2;
+  uint32_t w0 = cl_words[0], w1 = nw > 1 ? cl_words[1] : 0u;
+  for (uint32_t i = 0; i < nw; i++) {
+    const uint32_t w2 = i + 2 < nw ? cl_words[i + 2] : 0u;
+    uint32_t w = w0;
+    if (i + 1 == nw && (symbol & 3u) != 0) w &= mask_bits(8u * (symbol & 3u));  // bytes past the last symbol were never written
+    for (uint32_t j = 0; w != 0; j++, w >>= 8) {
+      const uint32_t l = w & 0xFFu;
+      if (l) place_symbol(c, root_v, rbits, 4 * i + j, l);
+    }
+    w0 = w1; w1 = w2;
+  }
+  return kLaneOk;
+}
+
+BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits) {
+  BitWin b = L.win();
+  uint32_t cold_next = L.cold_next;
+  const int r = read_huffman_code_impl(c, b, cold_next, alphabet_size, max_symbol, root_v, rbits);
+  L.put(b);
+  L.cold_next = cold_next;
+  return r;
+}
+
+#else
 // Fill the lookup structure of one prefix code from its symbols sorted by (length, value).
 // count[l] = symbols of length l.  Root of 2^rbits entries at root_v; longer codes go to second-level
 // tables allocated from L.cold_next (always in the arena).  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
@@ -578,6 +840,8 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
   return fill_table(c, L, sorted, count, root_v, rbits);
 }
 
+#endif
+
 // A tree that lives wholly in the arena part of the table space (block-switch and context-map codes).
 BD_DEV int read_arena_tree(const LaneCtx& c, Lane& L, uint32_t alphabet, uint32_t& root_v) {
   root_v = L.cold_next;
@@ -606,15 +870,19 @@ BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_
   const uint32_t saved_cold = L.cold_next;
   uint32_t root_v;
   if (read_arena_tree(c, L, ntrees + rle_max, root_v) != kLaneOk) return kLaneBail;
-  uint32_t i = 0;
-  while (i < size) {
-    const uint32_t code = decode_generic(c, L, root_v, kBlockRootBits);
-    if (code == 0) { map[i++] = 0; continue; }
-    if (code > rle_max) { map[i++] = (uint8_t)(code - rle_max); continue; }
-    uint32_t reps = (1u << code) + L.read(code);
-    if (i + reps > size) return kLaneBail;
-    do { map[i++] = 0; } while (--reps);
-    if (L.overrun()) return kLaneBail;
+  {
+    BitWin b = L.win();  // (the byte stores to the map would otherwise send the bit window through local memory)
+    uint32_t i = 0;
+    while (i < size) {
+      const uint32_t code = decode_generic(c, b, root_v, kBlockRootBits);
+      if (code == 0) { map[i++] = 0; continue; }
+      if (code > rle_max) { map[i++] = (uint8_t)(code - rle_max); continue; }
+      uint32_t reps = (1u << code) + b.read(code);
+      if (i + reps > size) return kLaneBail;
+      do { map[i++] = 0; } while (--reps);
+      if (b.overrun()) return kLaneBail;
+    }
+    L.put(b);
   }
   L.cold_next = saved_cold;  // the map's own code is not needed any more
   if (L.read(1)) {
@@ -698,6 +966,12 @@ BD_DEV void seek_byte(Lane& L, uint64_t byte_off) {
     cp_async_commit();
     cp_async_wait_all();
   }
+}
+
+// Bit window back at word `k`, bit `bp` of the (aligned) input (a position this lane has been at before).
+BD_DEV void seek_bit(Lane& L, uint32_t k, uint32_t bp) {
+  seek_byte(L, (uint64_t)k * 4);
+  L.bp = bp;
 }
 
 // Byte-align the bit window (JumpToByteBoundary, src/bit_reader/mod.rs:378-385); false if the padding bits are not zero.
@@ -814,69 +1088,102 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
     if (!all_trivial && c.E < 2 * kCtxMapEntries) return kLaneBail;
     L.e_tab = all_trivial ? c.E : c.E - kCtxMapEntries;
   }
-  // Root widths.  Groups (0 literal, 1 command, 2 distance) whose narrowest roots do not all fit the shared
-  // slot are moved to the arena, largest first; the rest share the slot and are widened, cheapest step first.
+  // Root widths.  Groups (0 literal, 1 command, 2 distance) share the slot.  Their comfortable minimum is 4 / 4 / 3
+  // bits; when that does not fit, the largest group is narrowed bit by bit -- down to 0 bits: one entry per tree, a
+  // pointer to a second-level table that covers the whole code, which the command loop's look-ahead fetches
+  // asynchronously like any other second-level entry -- so a group only leaves the slot (synchronous look-ups in the
+  // arena) when it has more trees than the slot has entries.  Narrow roots make the second-level tables larger; if
+  // they overflow the arena, the tree groups are read again with the roots in the arena (second attempt).
+  // The groups that stay are then widened where it pays most: widening group g from R to R' costs
+  // ntrees * (2^R' - 2^R) entries and saves the second-level look-ups of the symbols whose codes are R+1..R' bits
+  // long.  Typical shares of symbols with codes longer than R (per cent; text and binary corpora)
+  // stand in for the streams' own statistics.  Jumps over several widths are considered at once (the saving per
+  // entry is not monotonic: the first bits of a root save nothing).
   const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
   const uint32_t rmin[3] = {4, 4, 3}, rmax[3] = {8, 8, 7};
-  uint32_t rb[3] = {rmin[0], rmin[1], rmin[2]};
-  bool shared[3] = {true, true, true};
-  for (;;) {
-    uint32_t total = 0, g = 3, best = 0;
-    for (uint32_t i = 0; i < 3; i++) if (shared[i]) {
-      const uint32_t sz = ntrees[i] << rb[i];
-      total += sz;
-      if (sz >= best) { best = sz; g = i; }
-    }
-    if (total <= L.e_tab || g == 3) break;
-    shared[g] = false;
-#ifdef BD_LANE_SPILL_NARROW
-    rb[g] = rmin[g];
-#else
-    rb[g] = (ntrees[g] << rmax[g]) <= kGlobalTab / 2 ? rmax[g] : rmin[g];  // the arena has room for wide roots
-#endif
-  }
-  // Widen where it pays most: a step R -> R+1 of group g costs ntrees << R entries and saves the second-level
-  // look-ups of the symbols whose codes are R+1 bits long.  Typical shares of symbols with codes longer than R
-  // (per cent; text and binary corpora) stand in for the streams' own statistics, weighted by
-  // how many symbols of each kind a command brings (literals count double in literal-heavy data; here 1:1:1).
-  static const uint8_t kLongShare[3][6] = {{97, 66, 36, 18, 9, 3},   // literal:  R = 3..8
-                                           {51, 37, 25, 16, 10, 6},  // command
-                                           {78, 32, 12, 5, 3, 1}};   // distance
-  for (;;) {
-    uint32_t total = 0, g = 3;
-    uint32_t best_num = 0, best_den = 1;  // benefit / cost of the best step, compared as fractions
-    for (uint32_t i = 0; i < 3; i++) if (shared[i]) total += ntrees[i] << rb[i];
-    for (uint32_t i = 0; i < 3; i++) if (shared[i] && rb[i] < rmax[i]) {
-      const uint32_t extra = ntrees[i] << rb[i];
-      if (total + extra > L.e_tab) continue;
-      const uint32_t num = (uint32_t)kLongShare[i][rb[i] - 3] - (rb[i] + 1 <= 8 ? (uint32_t)kLongShare[i][rb[i] - 2] : 0u);
-      if (g == 3 || num * best_den > best_num * extra) { best_num = num; best_den = extra; g = i; }
-    }
-    if (g == 3) break;
-    rb[g]++;
-  }
-  uint32_t next_shared = 0;
-  const uint32_t order[3] = {1, 0, 2};
-  for (uint32_t oi = 0; oi < 3; oi++) {
-    const uint32_t g = order[oi];
-    const uint32_t sz = ntrees[g] << rb[g];
-    if (shared[g]) {
-      L.root[g] = next_shared;
-      next_shared += sz;
-    } else {
-      if (L.cold_next + sz > c.E + kGlobalTab) return kLaneBail;
-      L.root[g] = L.cold_next;
-      L.cold_next += sz;
-    }
-    L.rbits[g] = rb[g];
-  }
-  // HuffmanTreeGroupDecode x3, :1130-1219
   const uint32_t alpha[3] = {256, 704, L.dist_alphabet};
-  for (uint32_t g = 0; g < 3; g++) {
-    for (uint32_t i = 0; i < ntrees[g]; i++) {
-      if (read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g]) != kLaneOk) return kLaneBail;
-      if (L.overrun()) return kLaneBail;
+  const uint32_t save_lo = L.lo, save_hi = L.hi, save_nx = L.nx, save_k = L.k, save_bp = L.bp, save_cold = L.cold_next;
+  for (uint32_t attempt = 0;; attempt++) {
+    uint32_t rb[3] = {rmin[0], rmin[1], rmin[2]};
+    bool shared[3] = {true, true, true};
+    bool narrowed = false;
+    if (attempt == 0 && BD_LANE_NARROW_ROOTS) {
+      for (;;) {
+        uint32_t total = 0, g = 3, best = 0;
+        for (uint32_t i = 0; i < 3; i++) {
+          const uint32_t sz = ntrees[i] << rb[i];
+          total += sz;
+          if (rb[i] != 0 && sz >= best) { best = sz; g = i; }
+        }
+        if (total <= L.e_tab || g == 3) break;
+        rb[g]--;
+        narrowed = true;
+      }
     }
+    for (;;) {
+      uint32_t total = 0, g = 3, best = 0;
+      for (uint32_t i = 0; i < 3; i++) if (shared[i]) {
+        const uint32_t sz = ntrees[i] << rb[i];
+        total += sz;
+        if (sz >= best) { best = sz; g = i; }
+      }
+      if (total <= L.e_tab || g == 3) break;
+      shared[g] = false;
+#ifdef BD_LANE_SPILL_NARROW
+      rb[g] = rmin[g];
+#else
+      rb[g] = (ntrees[g] << rmax[g]) <= kGlobalTab / 2 ? rmax[g] : rmin[g];  // the arena has room for wide roots
+#endif
+    }
+    static const uint8_t kLongShare[3][9] = {{100, 100, 99, 97, 66, 36, 18, 9, 3},   // literal:  R = 0..8
+                                             {100, 96, 78, 51, 37, 25, 16, 10, 6},   // command
+                                             {100, 98, 92, 78, 32, 12, 5, 3, 1}};    // distance
+    static const uint8_t kGroupWeight[3] = {BD_LANE_W_LIT, BD_LANE_W_CMD, BD_LANE_W_DIST};
+    for (;;) {
+      uint32_t total = 0, g = 3, to = 0;
+      uint32_t best_num = 0, best_den = 1;  // benefit / cost of the best step, compared as fractions
+      for (uint32_t i = 0; i < 3; i++) if (shared[i]) total += ntrees[i] << rb[i];
+      for (uint32_t i = 0; i < 3; i++) if (shared[i]) {
+        for (uint32_t r2 = rb[i] + 1; r2 <= rmax[i]; r2++) {
+          const uint32_t extra = (ntrees[i] << r2) - (ntrees[i] << rb[i]);
+          if (total + extra > L.e_tab) break;
+          const uint32_t num = ((uint32_t)kLongShare[i][rb[i]] - (uint32_t)kLongShare[i][r2]) * kGroupWeight[i];
+          if (num * best_den > best_num * extra) { best_num = num; best_den = extra; g = i; to = r2; }
+        }
+      }
+      if (g == 3) break;
+      rb[g] = to;
+    }
+    uint32_t next_shared = 0;
+    const uint32_t order[3] = {1, 0, 2};
+    bool fits = true;
+    for (uint32_t oi = 0; oi < 3; oi++) {
+      const uint32_t g = order[oi];
+      const uint32_t sz = ntrees[g] << rb[g];
+      if (shared[g]) {
+        L.root[g] = next_shared;
+        next_shared += sz;
+      } else {
+        if (L.cold_next + sz > c.E + kGlobalTab) { fits = false; break; }
+        L.root[g] = L.cold_next;
+        L.cold_next += sz;
+      }
+      L.rbits[g] = rb[g];
+    }
+    // HuffmanTreeGroupDecode x3, :1130-1219
+    int r = fits ? kLaneOk : kLaneBail;
+    for (uint32_t g = 0; g < 3 && r == kLaneOk; g++) {
+      for (uint32_t i = 0; i < ntrees[g] && r == kLaneOk; i++) {
+        r = read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g]);
+        if (r == kLaneOk && L.overrun()) r = kLaneBail;
+      }
+    }
+    if (r == kLaneOk) break;
+    if (!narrowed) return kLaneBail;
+    // narrow roots did not work out (most likely: second-level tables beyond the arena): once more, the classic way
+    L.cold_next = save_cold;
+    seek_bit(L, save_k, save_bp);
+    if (L.lo != save_lo || L.hi != save_hi || L.nx != save_nx) return kLaneBail;  // (cannot happen: the input does not change)
   }
 #ifdef BD_LANE_MB_STATS
   BD_LANE_MB_STATS(c, L);
@@ -982,6 +1289,9 @@ BD_DEV uint32_t build_xdict_entry(uint8_t* dst, const uint8_t* word, uint32_t le
 #ifndef BD_LANE_COUNT
 #define BD_LANE_COUNT(i) ((void)0)  /* path statistics hook of the host build (tests/hostsim) */
 #endif
+#ifndef BD_LANE_LA_STATS
+#define BD_LANE_LA_STATS(slot, in, two) ((void)0)  /* look-ahead statistics hook of the host build (profiles/hostsim_tables.py) */
+#endif
 enum : uint32_t { kStIdle = 0, kStHeader = 1, kStCommands = 2, kStFinish = 3, kStDone = 4, kStBail = 5 };
 enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a lane's stream needs next
 
@@ -1048,6 +1358,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   BD_PIN64(gin); BD_PIN32(k_max); BD_PIN32(last_blk); BD_PIN64(out_al); BD_PIN32(bias); BD_PIN32(capb);
   BD_PIN32(max_backward); BD_PIN32(npostfix); BD_PIN32(ndirect); BD_PIN32(r_lit); BD_PIN32(r_cmd); BD_PIN32(r_dist); BD_PIN32(root_lit);
   const bool ran = run;
+  uint32_t klim = (((k + 2) >> 2) + 1) << 2;  // 4 x the highest input block requested so far (see LN_SKIP, LN_KLIM)
   uint32_t ph = kPhCmd;
   uint32_t ins = 0, copy_len = 0, cmd_bits = 0;
   uint32_t p1 = 0, p2 = 0;
@@ -1081,6 +1392,46 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #else
 #define LN_HEAD_CHECK(P0) ((void)0)
 #endif
+#if BD_LANE_SKIP_LITE
+// Bits consumed; on a word boundary the window takes word k + 3 from the ring (speculatively loaded: the load is
+// unconditional, only its use depends on the boundary).  Input blocks are requested ONCE per round (LN_INPUT_BLOCK,
+// after phase C1, where the round's bit position is final): the block after the one nx is in, so two blocks -- at
+// least 97 bits -- are ahead of every round.  klim = 4 x the highest block requested: a lane that eats through all
+// of it within one round (k > klim on a word boundary) fetches the next block on the spot.
+#define LN_SKIP(n)                                                                               \
+  do {                                                                                           \
+    bp += (n);                                                                                   \
+    const bool adv_ = bp >= 32;  /* branch-free word shift: nearly every round some lane needs it */ \
+    if (BD_UNLIKELY(adv_ && k > klim)) {                                                         \
+      const uint32_t b_ = (k + 3) >> 2;                                                          \
+      cp_async16(ring + (b_ & 1u) * ring_stride, gin + 16 * (size_t)(b_ < last_blk ? b_ : last_blk)); \
+      cp_async_commit(); cp_async_wait_all();                                                    \
+      klim += 4;                                                                                 \
+    }                                                                                            \
+    const uint32_t j_ = k + 3;                                                                   \
+    const uint32_t nw_ = vlds32(ring + ((j_ >> 2) & 1u) * ring_stride + (j_ & 3u) * 4u);         \
+    k += adv_ ? 1u : 0u;                                                                         \
+    lo = adv_ ? hi : lo; hi = adv_ ? nx : hi; nx = adv_ ? nw_ : nx;                              \
+    bp &= 31u;                                                                                   \
+  } while (0)
+#define LN_KLIM() ((((k + 2) >> 2) + 1) << 2)
+#define LN_INPUT_BLOCK(RUN)                                                                      \
+  do {                                                                                           \
+    const uint32_t nb_ = ((k + 2) >> 2) + 1;                                                     \
+    const bool need_ = (RUN) && (nb_ << 2) > klim;                                               \
+    LN_CP16_IF_STREAM(need_, ring + (nb_ & 1u) * ring_stride, gin + 16 * (size_t)(nb_ < last_blk ? nb_ : last_blk)); \
+    klim = need_ ? nb_ << 2 : klim;                                                              \
+  } while (0)
+/* the per-metablock bit reader expects the block after nx's to be there */
+#define LN_BLOCK_SWITCH_RING()                                                        \
+  do {                                                                                \
+    const uint32_t nb_ = ((k + 2) >> 2) + 1;                                          \
+    if ((nb_ << 2) > klim) {                                                          \
+      cp_async16(ring + (nb_ & 1u) * ring_stride, gin + 16 * (size_t)(nb_ < last_blk ? nb_ : last_blk)); \
+      cp_async_commit(); cp_async_wait_all();                                         \
+    }                                                                                 \
+  } while (0)
+#else
 // Bits consumed; on a word boundary the window takes word k + 2 from the ring.  When that word starts a new
 // 16-byte block, the block after it is requested with cp.async -- not committed here: the round's convergent
 // commit covers it, and the convergent wait at the start of the next round completes it long before its words
@@ -1100,6 +1451,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     lo = adv_ ? hi : lo; hi = adv_ ? nx : hi; nx = adv_ ? nw_ : nx;                              \
     bp &= 31u;                                                                                   \
   } while (0)
+#define LN_KLIM() 0u
+#define LN_INPUT_BLOCK(RUN) ((void)0)
+#define LN_BLOCK_SWITCH_RING() ((void)0)
+#endif
 #define LN_SAVE()                                                                                   \
   do {                                                                                              \
     L.lo = lo; L.hi = hi; L.nx = nx; L.k = k; L.bp = bp; L.posb = posb; L.acc = acc; L.mlen = mlen;  \
@@ -1109,9 +1464,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 // through local memory (:2367-2372, :2413-2424, :2567-2571)
 #define LN_BLOCK_SWITCH(CAT)                                                          \
   do {                                                                                \
+    LN_BLOCK_SWITCH_RING();                                                           \
     LN_SAVE();                                                                        \
     const int r_ = block_switch(c, L, CAT, bt);                                       \
     lo = L.lo; hi = L.hi; nx = L.nx; k = L.k; bp = L.bp;                                       \
+    klim = LN_KLIM();  /* (the per-metablock bit reader keeps the block after nx's requested) */ \
     bl_l = L.bl[0]; bl_c = L.bl[1]; bl_d = L.bl[2];                                   \
     LN_TREES();                                                                       \
     ctx_fresh = false;                                                                \
@@ -1182,6 +1539,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
     const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
     const uint32_t i2_ = ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);                 \
+    BD_LANE_LA_STATS(SLOT, in_, two_);                                                           \
     LN_CP16_IF_KEEP(two_, stage + (SLOT), gtab + (i2_ & ~7u));                                   \
     PV = in_; PE = two_ ? 0x80000000u : e_; PSEL = two_ ? (i2_ & 7u) << 1 : PSEL;                \
   } while (0)
@@ -1201,7 +1559,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
+#if !BD_LANE_SKIP_LITE
     bool blk_seen = false;       // this lane has requested an input block in this round (see LN_SKIP)
+#endif
     bool lit_fresh = false;      // this lane's literal run was announced by a command read in this round
 #if BD_LANE_HEAD_PER_ROUND
     const uint32_t posb0 = posb;
@@ -1345,7 +1705,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       }
     }
     warp_sync();
-    cp_async_commit();  // group: what phase A requested (distance look-ahead, input blocks)
+    cp_async_commit();  // group: what phase A requested (distance look-ahead)
 
     // ---- phase P: retire the copy chunk requested at the end of the previous round ----
     cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
@@ -1426,8 +1786,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         LN_LOOKAHEAD(tv, next_cmd ? r_cmd : r_lit, 32u, pa_valid, pa_e, pa_sel);
       }
     }
+    LN_INPUT_BLOCK(run);
     warp_sync();
-    cp_async_commit();  // group: next-A look-ahead (and phase C1's input blocks)
+    cp_async_commit();  // group: next-A look-ahead and the round's input block
 
     // ---- phase C2: the copy or static dictionary word (:2583-2689); its source bytes are requested below ----
     if (go && ev == kStCommands) {
@@ -1544,6 +1905,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #undef LN_CP16_IF_STREAM
 #undef LN_CP16_IF_SRC
 #undef LN_SKIP
+#undef LN_KLIM
+#undef LN_INPUT_BLOCK
+#undef LN_BLOCK_SWITCH_RING
 #undef LN_SAVE
 #undef LN_TREES
 #undef LN_BLOCK_SWITCH

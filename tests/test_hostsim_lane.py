@@ -21,7 +21,7 @@ MUST_DECODE = ["alice29.txt.compressed", "asyoulik.txt.compressed", "lcet10.txt.
 def test_fixture(hostsim, name):
     e = MAN[name]
     data = helpers.golden_fixture(name)
-    for entries in (430, 178, 146, 100000):
+    for entries in (430, 178, 146, 103, 73, 53, 34, 100000):
         for mis in (0, 1, 2, 3, 13, 16, 28, 31):
             code, out, used = hostsim.lane_decode(data, e["original_size"], entries, mis)
             if code == 1:
@@ -39,7 +39,7 @@ def test_generated_configs_and_capacity(hostsim, oracle, corpus):
         comp, orig, _ = corpus.make_config(cfg, n, size=size)
         ok = 0
         for c, o in zip(comp, orig):
-            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([178, 146])), int(rng.integers(0, 32)))
+            code, out, used = hostsim.lane_decode(c, len(o), int(rng.choice([178, 146, 103, 73, 34])), int(rng.integers(0, 32)))
             if code == 1:
                 assert out == o and used == len(c)
                 ok += 1
