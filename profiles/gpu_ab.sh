@@ -8,7 +8,7 @@ for rep in 1 2; do
 for v in $VARS; do
   LIB=""
   if [ "$v" != "default" ]; then LIB=$PWD/rust-brotli-decompressor_b200/variants/libbrotli_b200_$v.so; fi
-  BROTLI_B200_LIB=$LIB timeout 600 python bench.py --streams 131072 --unique 2048 --steps 3 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${v}_$rep.json 2> $OUT/bench_${v}_$rep.err
+  BROTLI_B200_LIB=$LIB timeout 600 python bench.py --streams ${STREAMS:-189440} --unique 2048 --steps 3 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${v}_$rep.json 2> $OUT/bench_${v}_$rep.err
   python -c "import json; j=json.load(open('$OUT/bench_${v}_$rep.json')); print('$v rep $rep headline probe', j['value'], 'GB/s ms', j['ms_per_step'], 'bit_exact', j.get('bit_exact'))"
   if [ $rep = 1 ]; then
     BROTLI_B200_LIB=$LIB timeout 900 python profiles/gpu_configs.py > $OUT/configs_$v.jsonl 2> $OUT/configs_$v.err

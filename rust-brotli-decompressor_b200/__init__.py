@@ -235,7 +235,7 @@ class DecoderState:
 
 
 def set_tuning(name, value):
-    """BrotliB200SetTuning: "lane_min_streams", "small_geometry", "sort_streams"."""
+    """BrotliB200SetTuning: "lane_min_streams", "small_geometry", "sort_streams", "lane_slot_bytes"."""
     return bool(lib().BrotliB200SetTuning(name.encode(), int(value)))
 
 

@@ -170,7 +170,7 @@ DeviceCtx* acquire_ctx() {
   c->device = dev;
   c->ctas = brotli_b200::query_resident_ctas(dev);
   if (c->ctas <= 0) { set_error("brotli_b200: occupancy query failed (kernel image not loadable on this device?)"); return nullptr; }
-  const size_t arena_bytes = (size_t)c->ctas * brotli_b200::kWarpsPerCta * brotli_b200::arena_bytes_per_warp();
+  const size_t arena_bytes = (size_t)c->ctas * brotli_b200::kMaxWarpsPerCta * brotli_b200::arena_bytes_per_warp();
   bool ok = cudaMalloc((void**)&c->arena, arena_bytes) == cudaSuccess &&
             cudaMalloc((void**)&c->dictionary, kDictionaryBytes + 64) == cudaSuccess &&
             cudaMalloc((void**)&c->ticket, 256) == cudaSuccess &&
@@ -472,7 +472,8 @@ struct CudaDev {
       for (auto& k : v) k.src = (const uint8_t*)c->sess_blob.p + (uintptr_t)k.src;
       int rc = copy_pieces(v);
       if (rc != 0) return rc;
-      CU_TRY(cudaStreamSynchronize(c->s_compute));  // `v` and the caller's blob are pageable
+      // (no synchronisation: the blob is the pinned staging buffer of host_up(), reused only after this call's final
+      // synchronisation, and a copy from the pageable `v` is staged before cudaMemcpyAsync returns)
     }
     CU_TRY(c->sess_states.reserve((size_t)n * sizeof(brotli_b200::ResumeState)));
     CU_TRY(cudaMemcpyAsync(c->sess_states.p, arr, (size_t)n * sizeof(brotli_b200::ResumeState), cudaMemcpyHostToDevice, c->s_compute));
@@ -501,10 +502,8 @@ struct CudaDev {
   }
   int move(const brotli_b200::SessionCopy* pieces, uint32_t n) {
     std::vector<brotli_b200::SessionCopy> v(pieces, pieces + n);
-    int rc = copy_pieces(v);
-    if (rc != 0) return rc;
-    CU_TRY(cudaStreamSynchronize(c->s_compute));
-    return 0;
+    // (stream order is all the later launches need; the host never reads these buffers)
+    return copy_pieces(v);
   }
 };
 
@@ -1002,6 +1001,14 @@ int BrotliB200SetTuning(const char* name, uint64_t value) {
     return 1;
   }
   if (strcmp(name, "sort_streams") == 0) { c->sort_streams = value != 0; return 1; }
+  if (strcmp(name, "lane_slot_bytes") == 0) {  // table slot of the default geometry: 0 = all the geometry allows; smaller slots for tests
+    const uint32_t full = brotli_b200::lane_slot_bytes(c->lane_warps);
+    const uint32_t v = (((uint32_t)value / 4u) | 1u) * 4u;  // an odd number of words (see lane_slot_bytes)
+    if (value == 0) { c->lane_slot_bytes = full; return 1; }
+    if (v < 80u || v > full) return 0;
+    c->lane_slot_bytes = v;
+    return 1;
+  }
   return 0;
 }
 

@@ -7,6 +7,7 @@
 // Host code reaches these only through the launch_* functions declared in brotli_b200_runtime.h.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "brotli_decode_core.cuh"
 #include "brotli_b200_runtime.h"
@@ -17,9 +18,14 @@ namespace brotli_b200 {
 // storage per warp (dynamic, kWarpSharedBytes each).
 static_assert(sizeof(WarpShared) % 8 == 0, "table storage must stay 8-byte aligned");
 static_assert(kWarpSharedBytes > sizeof(WarpShared) + 2 * 2048, "per-warp region too small for any table");
-constexpr uint32_t kSharedTableEntries = (kWarpSharedBytes - sizeof(WarpShared)) / 2;
+static_assert(kWarpSharedBytesWide > sizeof(WarpShared) + 2 * 2048, "per-warp region too small for any table");
 
-__global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_batch_kernel(BatchArgs a) {
+// Two geometries of the same kernel: WARPS warps per CTA with WSB bytes of shared memory each.  The default (24 x 9216)
+// has the faster warps; the wide one (28 x 8000: 4144 resident warps) takes batches whose streams then fit into fewer
+// waves -- config C4's 4096 streams of 16 MiB run in one wave instead of two (66 vs 47 GB/s).
+template <int WARPS, uint32_t WSB>
+__global__ void __launch_bounds__(WARPS * 32, kMinCtasPerSm) brotli_decode_batch_kernel(BatchArgs a) {
+  constexpr uint32_t kSharedTableEntries = (WSB - sizeof(WarpShared)) / 2;
   __shared__ uint2 s_cmd_lut[704];
   __shared__ __align__(16) uint8_t s_ctx_lut[2048];
   extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -29,12 +35,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtasPerSm) brotli_decode_b
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * WARPS + warp;
 
   Decoder d;
   d.arena = a.arena + gwarp * ArenaLayout::kBytes;
   d.tables = (uint16_t*)(d.arena + ArenaLayout::kTables);
-  d.sh = (WarpShared*)(s_dyn + (size_t)warp * kWarpSharedBytes);
+  d.sh = (WarpShared*)(s_dyn + (size_t)warp * WSB);
   d.ws = &d.sh->ws;
   d.stab = (uint16_t*)(d.sh + 1);
   d.stab_cap = kSharedTableEntries;
@@ -109,12 +115,24 @@ size_t resume_state_bytes() { return sizeof(ResumeState); }
 
 size_t arena_bytes_per_warp() { return ArenaLayout::kBytes; }
 
+namespace {
+constexpr uint32_t kDynamicSharedBytesWide = kWarpsPerCtaWide * kWarpSharedBytesWide;
+bool g_wide_ok = false;  // the wide geometry is resident with one CTA per SM as well (checked once per process)
+}
+
 int query_resident_ctas(int device) {
   int per_sm = 0, sms = 0;
-  if (cudaFuncSetAttribute(brotli_decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynamicSharedBytes) != cudaSuccess) return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brotli_decode_batch_kernel, kThreadsPerCta, kDynamicSharedBytes) != cudaSuccess) return -1;
+  auto* k = brotli_decode_batch_kernel<kWarpsPerCta, kWarpSharedBytes>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynamicSharedBytes) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreadsPerCta, kDynamicSharedBytes) != cudaSuccess) return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   if (per_sm < 1) per_sm = 1;
+  auto* kw = brotli_decode_batch_kernel<kWarpsPerCtaWide, kWarpSharedBytesWide>;
+  int per_sm_wide = 0;
+  g_wide_ok = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynamicSharedBytesWide) == cudaSuccess &&
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, kw, kWarpsPerCtaWide * 32, kDynamicSharedBytesWide) == cudaSuccess &&
+              per_sm_wide >= 1 && per_sm == 1;
+  if (!g_wide_ok) cudaGetLastError();
   return per_sm * sms;
 }
 
@@ -126,8 +144,17 @@ cudaError_t launch_decode_batch(const BatchArgs& a, int ctas, cudaStream_t strea
   if (!a.n_ptr) {
     const int need = (int)((a.n + 3) / 4);
     if (need < ctas) ctas = need < 1 ? 1 : need;
+    // Geometry by wave count: a wave of the wide geometry takes ~1.17x as long as one of the default (latency table,
+    // profiles/r02), so it is taken when it saves a wave (4144 instead of 3552 streams per wave on 148 SMs).
+    static const bool allow_wide = !(getenv("BROTLI_B200_EXACT_WIDE") && getenv("BROTLI_B200_EXACT_WIDE")[0] == '0');
+    const uint64_t per_wave = (uint64_t)ctas * kWarpsPerCta, per_wave_wide = (uint64_t)ctas * kWarpsPerCtaWide;
+    const uint64_t waves = (a.n + per_wave - 1) / per_wave, waves_wide = (a.n + per_wave_wide - 1) / per_wave_wide;
+    if (g_wide_ok && allow_wide && a.n > per_wave && waves_wide * 117 < waves * 100) {
+      brotli_decode_batch_kernel<kWarpsPerCtaWide, kWarpSharedBytesWide><<<ctas, kWarpsPerCtaWide * 32, kDynamicSharedBytesWide, stream>>>(a);
+      return cudaGetLastError();
+    }
   }
-  brotli_decode_batch_kernel<<<ctas, kThreadsPerCta, kDynamicSharedBytes, stream>>>(a);
+  brotli_decode_batch_kernel<kWarpsPerCta, kWarpSharedBytes><<<ctas, kThreadsPerCta, kDynamicSharedBytes, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,10 @@ constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMinCtasPerSm = 1;
 constexpr uint32_t kWarpSharedBytes = BROTLI_B200_WARP_SHARED_BYTES;
 constexpr uint32_t kDynamicSharedBytes = kWarpsPerCta * kWarpSharedBytes;
+// the wide geometry of the same kernel (see brotli_b200_kernels.cu): more, slightly slower warps
+constexpr int kWarpsPerCtaWide = 28;
+constexpr uint32_t kWarpSharedBytesWide = 8000;
+constexpr int kMaxWarpsPerCta = kWarpsPerCtaWide > kWarpsPerCta ? kWarpsPerCtaWide : kWarpsPerCta;
 
 // Lane kernel (brotli_b200_lane_kernel.cu): one stream per lane, one persistent CTA per SM; the SM's
 // shared memory is split into one private table slot per lane, so fewer warps mean wider root tables.

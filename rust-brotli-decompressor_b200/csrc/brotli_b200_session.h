@@ -90,6 +90,35 @@ struct SessionRunner {
     if (c.total_out) *c.total_out = (size_t)s.delivered;
   }
 
+  // Host copies of one batch (caller input -> staging blob, staging blob -> caller output): collected while the
+  // calls are walked in order, then made in parallel (they are independent and dominate a batch of many sessions).
+  struct HostCopy { uint8_t* dst; const uint8_t* src; size_t n; };
+  std::vector<HostCopy> jobs;
+  void run_jobs() {
+    const long nj = (long)jobs.size();
+#pragma omp parallel for schedule(dynamic, 16) if (nj >= 64)
+    for (long j = 0; j < nj; j++) memcpy(jobs[(size_t)j].dst, jobs[(size_t)j].src, jobs[(size_t)j].n);
+    jobs.clear();
+  }
+  // hand the caller what is pending, then this call's new bytes (src, n) straight from the staging blob: only what
+  // the caller's buffer cannot take is kept in `pending`
+  void deliver_new(Session& s, StreamCall& c, const uint8_t* src, size_t n, uint64_t limit = ~(uint64_t)0) {
+    if (n == 0 || s.pending_bytes() != 0) {
+      if (n) s.pending.insert(s.pending.end(), src, src + n);
+      deliver(s, c, limit);
+      return;
+    }
+    size_t m = n;
+    if (m > *c.available_out) m = *c.available_out;
+    if (limit < s.delivered + m) m = limit > s.delivered ? (size_t)(limit - s.delivered) : 0;
+    if (m) {
+      jobs.push_back(HostCopy{*c.next_out, src, m});
+      *c.next_out += m; *c.available_out -= m; s.delivered += m;
+    }
+    if (m < n) s.pending.insert(s.pending.end(), src + m, src + n);
+    if (c.total_out) *c.total_out = (size_t)s.delivered;
+  }
+
   bool reserve(uint8_t*& p, size_t& cap, size_t need) {
     if (need <= cap) return true;
     const size_t want = (need + 4095) & ~(size_t)4095;  // (callers add the slack they want: the two halves of a pair must not leapfrog)
@@ -120,6 +149,7 @@ struct SessionRunner {
   int stream_calls(Session** ss, StreamCall* cs, size_t n, int device_error_code) {
     std::vector<uint32_t> todo;       // calls that need the decoder
     std::vector<uint64_t> budget(n, 0);
+    jobs.clear();
     for (size_t i = 0; i < n; i++) {
       Session& s = *ss[i]; StreamCall& c = cs[i];
       c.result = -1;
@@ -155,11 +185,12 @@ struct SessionRunner {
       }
       if (k) {
         scatter.push_back(SessionCopy{(const uint8_t*)(uintptr_t)blob_size, s.d_in[s.in_sel] + s.in_len, k});
-        memcpy(blob + blob_size, *c.next_in, k);
+        jobs.push_back(HostCopy{blob + blob_size, *c.next_in, k});
         blob_size += k;
         s.in_len += k;
       }
     }
+    run_jobs();
     // ---- decode; a launch that ran into the end of its output window is repeated with a larger one ----
     std::vector<uint32_t> round;
     for (uint32_t i : todo) if (cs[i].result == -1) round.push_back(i);
@@ -218,6 +249,8 @@ struct SessionRunner {
     // ---- new output comes down: one blob for the whole batch ----
     std::vector<SessionCopy> gather;
     std::vector<uint32_t> got;
+    std::vector<const uint8_t*> new_ptr(n, nullptr);
+    std::vector<size_t> new_n(n, 0);
     size_t out_bytes = 0;
     for (uint32_t i : todo) {
       Session& s = *ss[i];
@@ -236,8 +269,8 @@ struct SessionRunner {
       if (!down) { for (uint32_t i : todo) if (cs[i].result == -1) fail(*ss[i], cs[i], device_error_code); return device_error_code; }
       for (size_t k = 0; k < got.size(); k++) {
         Session& s = *ss[got[k]];
-        const uint8_t* p = down + (uintptr_t)gather[k].dst;
-        s.pending.insert(s.pending.end(), p, p + gather[k].n);
+        new_ptr[got[k]] = down + (uintptr_t)gather[k].dst;
+        new_n[got[k]] = gather[k].n;
         s.fetched += gather[k].n;
       }
     }
@@ -261,10 +294,10 @@ struct SessionRunner {
       *c.next_in += adv; *c.available_in -= adv;
       s.consumed = used_abs;
       s.in_len = (size_t)(used_abs - s.in_base);     // what the caller keeps will come again
-      if (r.code == 2) { s.stop = Session::kNeedIn; deliver(s, c); c.result = kResNeedsMoreInput; }
-      else if (r.code == 3) { s.stop = Session::kAtFlush; s.flush_at = s.out_base + r.decoded; deliver(s, c); c.result = kResNeedsMoreOutput; }
-      else if (r.code == 1) { s.stop = Session::kDone; deliver(s, c); c.result = s.pending_bytes() ? kResNeedsMoreOutput : kResSuccess; }
-      else { deliver(s, c, s.out_base + r.flushed_now); fail(s, c, r.code); }  // only what passed a flush point: nothing is flushed at the error
+      if (r.code == 2) { s.stop = Session::kNeedIn; deliver_new(s, c, new_ptr[i], new_n[i]); c.result = kResNeedsMoreInput; }
+      else if (r.code == 3) { s.stop = Session::kAtFlush; s.flush_at = s.out_base + r.decoded; deliver_new(s, c, new_ptr[i], new_n[i]); c.result = kResNeedsMoreOutput; }
+      else if (r.code == 1) { s.stop = Session::kDone; deliver_new(s, c, new_ptr[i], new_n[i]); c.result = s.pending_bytes() ? kResNeedsMoreOutput : kResSuccess; }
+      else { deliver_new(s, c, new_ptr[i], new_n[i], s.out_base + r.flushed_now); fail(s, c, r.code); }  // only what passed a flush point: nothing is flushed at the error
       if (s.stop == Session::kFailed || s.stop == Session::kDone) continue;
       // slide the input window: bytes behind the checkpoint are never read again
       const uint64_t cut = s.rs.bitpos >> 3;
@@ -295,6 +328,7 @@ struct SessionRunner {
         }
       }
     }
+    run_jobs();  // (the staging blob is the device backend's: it stays valid until the next batch)
     if (!moves.empty()) {
       const int rc = dev.move(moves.data(), (uint32_t)moves.size());
       if (rc != 0) return rc;

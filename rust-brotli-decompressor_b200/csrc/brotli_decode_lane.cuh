@@ -74,6 +74,13 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #define BD_LANE_BURST 0
 #endif
 // narrowest root a group may get in the shared slot, and the weights of the three symbol kinds in the root-width allocation
+// roots that live in the arena are looked up asynchronously as well (their root entry is requested a phase ahead)
+#ifndef BD_LANE_ASYNC_ARENA_ROOTS
+#define BD_LANE_ASYNC_ARENA_ROOTS 1
+#endif
+#ifndef BD_LANE_ARENA_LANES
+#define BD_LANE_ARENA_LANES 2  /* lanes of a warp with a tree group in the arena from which the warp takes that loop instance */
+#endif
 // per-metablock table construction without the sort arrays (temporaries in the shared staging area)
 #ifndef BD_LANE_HEADER_V2
 #define BD_LANE_HEADER_V2 0
@@ -159,9 +166,11 @@ BD_DEV uint32_t funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __
 BD_DEV uint32_t funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 #ifndef BD_LANE_L2_HINTS
-#define BD_LANE_L2_HINTS 1
+#define BD_LANE_L2_HINTS 4
 #endif
-#if BD_LANE_L2_HINTS == 1
+// modes: 0 no hints; 1 (default) input / output / copy sources evict-first, table arena evict-last; 2 as 1, copy sources
+// without a hint; 3 as 1, output stores without a hint; 4 as 1, table arena without a hint
+#if BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
 BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }  // streaming: evict first
 #else
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
@@ -171,7 +180,7 @@ BD_DEV void sts32_if(bool cond, hw::sref_t a, uint32_t v) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "r"(a), "r"(v) : "memory");
 }
 BD_DEV void st32_if(bool cond, uint8_t* p, uint32_t v) {
-#if BD_LANE_L2_HINTS == 1
+#if BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
 #else
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
@@ -1289,6 +1298,9 @@ BD_DEV uint32_t build_xdict_entry(uint8_t* dst, const uint8_t* word, uint32_t le
 #ifndef BD_LANE_COUNT
 #define BD_LANE_COUNT(i) ((void)0)  /* path statistics hook of the host build (tests/hostsim) */
 #endif
+#ifndef BD_LANE_DIST_STATS
+#define BD_LANE_DIST_STATS(ud, len, dictword) ((void)0)  /* copy distance statistics hook of the host build */
+#endif
 #ifndef BD_LANE_LA_STATS
 #define BD_LANE_LA_STATS(slot, in, two) ((void)0)  /* look-ahead statistics hook of the host build (profiles/hostsim_tables.py) */
 #endif
@@ -1301,7 +1313,7 @@ enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a
 // kStride: distance between the two 16-byte blocks of a lane's block-interleaved input ring (16 x the CTA's
 // threads), a compile-time constant of the kernel instance.
 // kDict: the batch has a custom LZ77 dictionary (a separate kernel instance, so that streams without one pay nothing).
-template <uint32_t kStride, bool kDict>
+template <uint32_t kStride, bool kDict, bool kArena>
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
   // register copies of the hot state
   const uint8_t* gin = nullptr;
@@ -1373,7 +1385,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
   BD_PIN64(pol_stream); BD_PIN64(pol_keep);
+#if BD_LANE_L2_HINTS == 4
+#define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
+#else
 #define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_keep)
+#endif
 #define LN_CP16_IF_STREAM(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_stream)
 #if BD_LANE_L2_HINTS == 2
 #define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
@@ -1528,8 +1544,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   // Look-ahead for a symbol that will be decoded a phase later: the root look-up is done now and, when the code
   // is longer than the root, its second-level entry (the aligned 16-byte block holding it) is requested with
   // cp.async into stage[SLOT..SLOT+15].  PV/PE/PSEL: valid flag, entry (bit 31: take it from the stage), byte
-  // offset in the block.  Only for trees whose roots are in the shared slot (otherwise the later decode does
-  // the look-ups itself).
+  // offset in the block.  In the kArena instance of the loop -- taken by a warp when one of its lanes has a tree
+  // group in the arena (it did not fit the shared slot) -- a root in the arena has its ROOT entry requested the same
+  // way (bits 31 and 30 of PE); the few codes longer than such a (wide) root then cost one synchronous load in
+  // LN_TAKE instead of two dependent ones for every symbol.  Warps without such a lane run the instance without
+  // these instructions (they are on the round's critical path: -1.8 % on the headline batch when always there).
 #define LN_LOOKAHEAD(TV, TR, SLOT, PV, PE, PSEL)                                                 \
   do {                                                                                           \
     const uint32_t bits_ = LN_PEEK();                                                            \
@@ -1538,17 +1557,22 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const uint32_t e_ = vlds16(stab + ((in_ ? v_ : 0u) << 1));                                   \
     const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
     const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
-    const uint32_t i2_ = ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);                 \
+    const bool ar_ = kArena && !in_;  /* root in the arena: request the root entry */            \
+    const uint32_t i2_ = ar_ ? v_ - E : ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);  \
     BD_LANE_LA_STATS(SLOT, in_, two_);                                                           \
-    LN_CP16_IF_KEEP(two_, stage + (SLOT), gtab + (i2_ & ~7u));                                   \
-    PV = in_; PE = two_ ? 0x80000000u : e_; PSEL = two_ ? (i2_ & 7u) << 1 : PSEL;                \
+    LN_CP16_IF_KEEP(two_ || ar_, stage + (SLOT), gtab + (i2_ & ~7u));                            \
+    PV = kArena || in_; PE = ar_ ? 0xC0000000u : (two_ ? 0x80000000u : e_); PSEL = (two_ || ar_) ? (i2_ & 7u) << 1 : PSEL; \
   } while (0)
 // entry of a looked-ahead symbol (its group has been waited for)
-#define LN_TAKE(SLOT, PV, PE, PSEL, BITS, LEN, SYM)                                              \
+#define LN_TAKE(SLOT, PV, PE, PSEL, TR, BITS, LEN, SYM)                                          \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
     const uint32_t es_ = vlds16(stage + (SLOT) + PSEL);  /* unconditional: no branch */          \
-    const uint32_t e_ = (PE & 0x80000000u) ? es_ : PE;                                           \
+    uint32_t e_ = (PE & 0x80000000u) ? es_ : PE;                                                 \
+    if (kArena && BD_UNLIKELY((PE & 0x40000000u) != 0 && (e_ & 15u) > (TR))) {  /* arena root, long code */ \
+      BD_LANE_COUNT(9);                                                                          \
+      e_ = gtab[((e_ >> 4) << 2) + low_bits(BITS >> (TR), (e_ & 15u) - (TR))];                   \
+    }                                                                                            \
     PV = false;                                                                                  \
     LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
   } while (0)
@@ -1582,7 +1606,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (ev == kStCommands) {
         uint32_t bits, len, sym;
         if (BD_LIKELY(pa_valid)) {
-          LN_TAKE(32u, pa_valid, pa_e, pa_sel, bits, len, sym);
+          LN_TAKE(32u, pa_valid, pa_e, pa_sel, (is_lit ? r_lit : r_cmd), bits, len, sym);
         } else {
           uint32_t tv = is_lit ? lit_tv : cmd_tv;
           const uint32_t tr = is_lit ? r_lit : r_cmd;
@@ -1730,7 +1754,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (ev == kStCommands) {
         uint32_t bits, len, sym;
         if (BD_LIKELY(pc_valid)) {
-          LN_TAKE(48u, pc_valid, pc_e, pc_sel, bits, len, sym);
+          LN_TAKE(48u, pc_valid, pc_e, pc_sel, r_dist, bits, len, sym);
         } else {
           const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
           BD_LANE_COUNT(7);
@@ -1800,6 +1824,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (BD_UNLIKELY((uint32_t)dist > max_distance)) {
         // static dictionary: the transformed word is an entry of the expanded table
         BD_LANE_COUNT(2);
+        BD_LANE_DIST_STATS(0u, copy_len, true);
         if (dist <= 0 || dist > 0x7FFFFFFC || copy_len < 4 || copy_len > 24 || k > k_max + 2) {
           ev = kStBail;
         } else {
@@ -1830,6 +1855,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           mlen -= (int32_t)copy_len;
           crem = copy_len;
           uint32_t ud = (uint32_t)dist;
+          BD_LANE_DIST_STATS(ud, copy_len, false);
           if (kDict && ud > pos) {
             // the source starts in the custom dictionary, which logically precedes the output: a plain copy from the
             // dictionary's tail when it also ends there; a copy that runs on into the output is the exact kernel's
@@ -2002,7 +2028,12 @@ BD_DEV uint32_t decode_streams(const LaneCtx& c, bool active, const uint8_t* in,
     }
     warp_sync();
     if (!warp_any(st == kStCommands)) break;
-    run_commands<kStride, kDict>(c, L, bt, st == kStCommands, st);
+    // (two instances of the loop: see LN_LOOKAHEAD)
+    const bool in_arena = st == kStCommands && (L.root[0] >= c.E || L.root[1] >= c.E || L.root[2] >= c.E);
+    // (a few such lanes do not pay for the longer look-ahead code of the other lanes: measured on the headline batch,
+    // where 3 % of the streams have their distance trees in the arena)
+    if (BD_LANE_ASYNC_ARENA_ROOTS && warp_count(in_arena) >= BD_LANE_ARENA_LANES) run_commands<kStride, kDict, true>(c, L, bt, st == kStCommands, st);
+    else run_commands<kStride, kDict, false>(c, L, bt, st == kStCommands, st);
     // METABLOCK_DONE, src/decode.rs:3345-3381: BLOCK_LENGTH_2 (:3356-3359) / truncated input
     if (st == kStHeader && (L.mlen < 0 || L.overrun())) st = kStBail;
     if (st == kStHeader && L.is_last) st = kStFinish;

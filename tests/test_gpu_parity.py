@@ -277,7 +277,7 @@ def test_raw_and_metadata_metablocks_stay_on_the_lane_kernel(gpu_lib, pkg, oracl
     assert n_ok == len(streams) and pkg.kernel_times()["bailed"] <= 1  # (rnd_chunk.br is in SMALL only if it has an original)
 
 
-@pytest.mark.parametrize("mode", ["exact_only", "lane_warps_8", "lane_warps_16"])
+@pytest.mark.parametrize("mode", ["exact_only", "lane_warps_8", "lane_warps_14", "lane_warps_24", "lane_warps_32", "small_slots"])
 def test_other_kernel_configurations(gpu_lib, mode):
     """The same parity run with the lane kernel switched off (every stream through the exact warp-per-stream
     kernel) and with other lane-kernel geometries (smaller / larger shared-memory table slots per lane)."""
@@ -287,10 +287,10 @@ def test_other_kernel_configurations(gpu_lib, mode):
     env = dict(os.environ)
     if mode == "exact_only":
         env["BROTLI_B200_LANE"] = "0"
-    elif mode == "lane_warps_8":
-        env["BROTLI_B200_LANE_WARPS"] = "8"
+    elif mode == "small_slots":  # 34 table entries per lane: most tree groups live in the arena (asynchronous root look-ups)
+        env["BROTLI_B200_LANE_SLOT_BYTES"] = "84"
     else:
-        env["BROTLI_B200_LANE_WARPS"] = "16"
+        env["BROTLI_B200_LANE_WARPS"] = mode.rsplit("_", 1)[1]
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(helpers.ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
                         "-k", "config_samples or corrupt_truncated or fixtures_one_shot or empty_and_ragged"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
