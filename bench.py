@@ -73,6 +73,33 @@ def measured_traffic(kernel, streams_per_launch):
         t.get("captured", "?"), t["streams_per_launch"])
 
 
+def memory_system_ceiling(dominant, n_streams, kernel_ms, warps=20):
+    """What the memory system gives the lane kernel's access pattern with no decode work (profiles/probes/gather_probe.cu,
+    run live on this GPU: per-lane 16-byte gathers from 64 KiB windows + 4-byte stores), next to the DRAM reads of the
+    kernel itself (committed ncu capture / its duration in this run).  The lane kernel is bound by this, not by the
+    copy roofline: DESIGN.md section 6."""
+    exe = os.path.join(ROOT, "profiles", "probes", "gather_probe")
+    if "lane" not in dominant or not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, str(warps)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120)
+        probe = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+    out = {"probe": "profiles/probes/gather_probe.cu (live)", "pattern": "2 gathers of 16 B in flight per lane + one 4-byte store per iteration, %d lanes, 64 KiB window per lane" % probe["lanes"],
+           "probe_Ggathers_per_s": probe["Ggathers_per_s"], "probe_dram_GBps_at_64B_per_gather": probe["dram_GBps_at_64B_per_gather"]}
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "current_traffic.json")))
+        if t.get("kernel_source_hash") == kernel_source_hash():
+            reads = float(t["dram_bytes_read"]) / float(t["streams_per_launch"]) * n_streams / 64.0
+            out["kernel_dram_reads_per_stream"] = int(float(t["dram_bytes_read"]) / float(t["streams_per_launch"]) / 64.0)
+            out["kernel_Gdram_reads_per_s"] = round(reads / (kernel_ms * 1e-3) / 1e9, 2)
+            out["frac_of_probe"] = round(out["kernel_Gdram_reads_per_s"] / probe["Ggathers_per_s"], 3)
+    except (OSError, ValueError, KeyError):
+        pass
+    return out
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,6 +531,10 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
         }
+        if world == 1:
+            ms_ceiling = memory_system_ceiling(dominant, n, max(lane_ms, exact_ms))
+            if ms_ceiling is not None:
+                line["roofline"]["memory_system"] = ms_ceiling
         if other is not None:
             line["other_configs"] = other
         k = min(n_unique_head, 2048)

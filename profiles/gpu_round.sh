@@ -19,7 +19,7 @@ if [ -n "$WITH_REFERENCE" ]; then
   cat $OUT/bench_reference.json
 fi
 # launch list (cold-cache, serialised: compare shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
   python bench.py --streams 131072 --unique 2048 --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/launches_bench.log 2>&1
 # full capture of the dominant decode kernel (4th launch = first timed step)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:brotli_decode_lane -s 3 -c 1 -o $OUT/prof_lane \

@@ -68,12 +68,18 @@ void run(int warps, uint8_t* d_win, uint32_t window, uint32_t iters, uint32_t* d
          warps, 148 * threads, G, STORES, ms, gathers / ms / 1e6, gathers * 64 / ms / 1e6, ms * 1e6 / iters);
 }
 
-int main() {
+int main(int argc, char** argv) {
   const uint32_t window = 65536, iters = 4000;
   const size_t bytes = (size_t)148 * 32 * 32 * window;  // up to 32 warps per SM
   uint8_t* d_win; uint32_t* d_out;
   CK(cudaMalloc(&d_win, bytes)); CK(cudaMemset(d_win, 1, bytes));
   CK(cudaMalloc(&d_out, (size_t)148 * 1024 * 4));
+  if (argc >= 2) {  // one line: the lane kernel's pattern (two gathers in flight, 4-byte stores) at `warps` per SM -- bench.py
+    const int warps = atoi(argv[1]);
+    if (warps < 1 || warps > 32) return 2;
+    run<2, 1>(warps, d_win, window, iters, d_out);
+    return 0;
+  }
   for (int warps : {8, 14, 20, 24, 32}) {
     run<1, 0>(warps, d_win, window, iters, d_out);
     run<1, 1>(warps, d_win, window, iters, d_out);

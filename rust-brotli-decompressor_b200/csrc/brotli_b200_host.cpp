@@ -105,6 +105,10 @@ struct DeviceCtx {
   // second geometry for batches below one wave: fewer, fuller warps with wider table slots (profiles/r02/lat_*.jsonl)
   int small_warps = 0, small_ctas = 0;
   uint32_t small_slot_bytes = 0;
+  // further geometries with fewer resident lanes than the default, taken when a batch falls into waves better with them
+  // (profiles/r02/waves.txt): {warps, ctas, slot bytes}; ctas == 0: not available
+  struct LaneGeom { int warps = 0, ctas = 0; uint32_t slot_bytes = 0; };
+  LaneGeom alt[2];
   size_t lane_min_streams = 0; // batches smaller than this go straight to the warp-per-stream kernel
   uint8_t* lane_arena = nullptr;
   uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
@@ -227,6 +231,15 @@ DeviceCtx* acquire_ctx() {
       c->small_ctas = brotli_b200::query_lane_resident_ctas(dev, c->small_warps);
       c->small_slot_bytes = brotli_b200::lane_slot_bytes(c->small_warps);
       if (c->small_ctas <= 0) c->small_warps = 0;
+      if (!(getenv("BROTLI_B200_LANE_FIT") && getenv("BROTLI_B200_LANE_FIT")[0] == '0') && c->lane_warps == 20) {
+        const int alt_warps[2] = {14, 16};
+        for (int k = 0; k < 2; k++) {
+          c->alt[k].warps = alt_warps[k];
+          c->alt[k].ctas = brotli_b200::query_lane_resident_ctas(dev, alt_warps[k]);
+          c->alt[k].slot_bytes = brotli_b200::lane_slot_bytes(alt_warps[k]);
+          if (c->alt[k].ctas <= 0) c->alt[k].ctas = 0;
+        }
+      }
     }
     c->bail_count = c->ticket + 16;  // same 256-byte allocation as the tickets
     const char* sort_env = getenv("BROTLI_B200_SORT");
@@ -265,6 +278,24 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
     la.slot_bytes = c->lane_slot_bytes;
     if (c->small_warps && a.custom_dict_size == 0 && n <= (size_t)c->small_ctas * c->small_warps * 32) {
       lane_warps = c->small_warps; lane_ctas = c->small_ctas; la.slot_bytes = c->small_slot_bytes;
+    } else if (a.custom_dict_size == 0 && c->lane_slot_bytes == brotli_b200::lane_slot_bytes(c->lane_warps)) {
+      // Geometry by wave fit.  Full waves cost the same per stream at 14..24 warps per SM (the kernel is bound by the
+      // memory system), a partial last wave costs at least a stream's latency -- about half a wave of the default
+      // geometry -- however few streams it holds.  Cost in lane-slots: full waves + max(that floor, 0.8 x the rest).
+      // The default keeps a 7 % bonus (the model is good to a few per cent: profiles/r02/waves.txt).
+      auto cost = [](size_t streams, size_t lanes) {
+        const size_t full = streams / lanes, rest = streams - full * lanes;
+        const size_t floor_slots = 51000;
+        const size_t tail = rest == 0 ? 0 : (rest * 4 / 5 > floor_slots ? rest * 4 / 5 : floor_slots);
+        return full * lanes + tail;
+      };
+      size_t best = cost(n, (size_t)lane_ctas * lane_warps * 32) * 93 / 100;
+      for (int k = 0; k < 2; k++) {
+        if (c->alt[k].ctas <= 0) continue;
+        const size_t lanes = (size_t)c->alt[k].ctas * c->alt[k].warps * 32;
+        const size_t ck = n <= lanes ? 0 : cost(n, lanes);  // (a batch that fits one wave of fewer, fuller-slotted lanes takes it)
+        if (ck < best) { best = ck; lane_warps = c->alt[k].warps; lane_ctas = c->alt[k].ctas; la.slot_bytes = c->alt[k].slot_bytes; }
+      }
     }
     la.arena = c->lane_arena; la.bail_count = c->bail_count; la.bail_list = (uint32_t*)c->bail_list.p;
     la.xdict = c->xdict;

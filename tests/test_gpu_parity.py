@@ -329,6 +329,39 @@ def test_batch_size_routing(gpu_lib, pkg, corpus):
         pkg.set_tuning("lane_min_streams", 0)
 
 
+def test_exact_kernel_wide_geometry(gpu_lib, pkg, oracle, corpus):
+    """The warp-per-stream kernel has two geometries (24 and 28 warps per SM, csrc/brotli_b200_kernels.cu); a batch that
+    needs fewer waves with the second one takes it (config C4's 4096 streams do).  4096 streams of every kind -- valid,
+    truncated, corrupt, too little room -- through the exact kernel alone: codes, sizes and bytes equal to the oracle's."""
+    rng = np.random.default_rng(21)
+    comp, orig, _ = corpus.make_config("C5", 64, size=6000)
+    streams, caps = [], []
+    for i in range(4096):
+        c, o = comp[i % 64], orig[i % 64]
+        if i % 16 == 3:
+            m = helpers.mutations(c, rng, 1)[0] or c
+            streams.append(m); caps.append(len(o) + 16)
+        elif i % 16 == 7:
+            streams.append(c); caps.append(max(len(o) - 1 - i % 5, 0))
+        else:
+            streams.append(c); caps.append(len(o))
+    try:
+        assert pkg.set_tuning("lane_min_streams", 1 << 30)   # nothing goes to the lane kernel
+        pkg.kernel_times(reset=True)
+        got = pkg.decompress_batch(streams, caps)
+        kt = pkg.kernel_times()
+        assert kt["lane_ms"] < 0.05 and kt["exact_ms"] > 0.5, kt
+        memo = {}
+        for i, ((gres, gcode, gout), s_, c_) in enumerate(zip(got, streams, caps)):
+            key = (s_, c_)
+            if key not in memo:
+                memo[key] = oracle.decode(s_, c_)
+            ores, ocode, oout = memo[key]
+            assert gcode == ocode and gout == oout, (i, gcode, ocode)
+    finally:
+        pkg.set_tuning("lane_min_streams", 0)
+
+
 def test_differential_fuzz_error_codes(gpu_lib, pkg, oracle, corpus):
     """every BrotliDecoderErrorCode and decoded_size the GPU path reports for malformed input
     equals the oracle's, over a few thousand seeded mutations (truncations, bit flips, byte smashes, multi-byte
