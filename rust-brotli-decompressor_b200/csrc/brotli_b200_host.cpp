@@ -109,6 +109,7 @@ struct DeviceCtx {
   // (profiles/r02/waves.txt): {warps, ctas, slot bytes}; ctas == 0: not available
   struct LaneGeom { int warps = 0, ctas = 0; uint32_t slot_bytes = 0; };
   LaneGeom alt[2];
+  bool geom_lanes_uploaded = false;
   size_t lane_min_streams = 0; // batches smaller than this go straight to the warp-per-stream kernel
   uint8_t* lane_arena = nullptr;
   uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
@@ -278,25 +279,10 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
     la.slot_bytes = c->lane_slot_bytes;
     if (c->small_warps && a.custom_dict_size == 0 && n <= (size_t)c->small_ctas * c->small_warps * 32) {
       lane_warps = c->small_warps; lane_ctas = c->small_ctas; la.slot_bytes = c->small_slot_bytes;
-    } else if (a.custom_dict_size == 0 && c->lane_slot_bytes == brotli_b200::lane_slot_bytes(c->lane_warps)) {
-      // Geometry by wave fit.  Full waves cost the same per stream at 14..24 warps per SM (the kernel is bound by the
-      // memory system), a partial last wave costs at least a stream's latency -- about half a wave of the default
-      // geometry -- however few streams it holds.  Cost in lane-slots: full waves + max(that floor, 0.8 x the rest).
-      // The default keeps a 7 % bonus (the model is good to a few per cent: profiles/r02/waves.txt).
-      auto cost = [](size_t streams, size_t lanes) {
-        const size_t full = streams / lanes, rest = streams - full * lanes;
-        const size_t floor_slots = 51000;
-        const size_t tail = rest == 0 ? 0 : (rest * 4 / 5 > floor_slots ? rest * 4 / 5 : floor_slots);
-        return full * lanes + tail;
-      };
-      size_t best = cost(n, (size_t)lane_ctas * lane_warps * 32) * 93 / 100;
-      for (int k = 0; k < 2; k++) {
-        if (c->alt[k].ctas <= 0) continue;
-        const size_t lanes = (size_t)c->alt[k].ctas * c->alt[k].warps * 32;
-        const size_t ck = n <= lanes ? 0 : cost(n, lanes);  // (a batch that fits one wave of fewer, fuller-slotted lanes takes it)
-        if (ck < best) { best = ck; lane_warps = c->alt[k].warps; lane_ctas = c->alt[k].ctas; la.slot_bytes = c->alt[k].slot_bytes; }
-      }
     }
+    // geometry by wave fit, decided on the device after the sort (uniform batches only): see launch_choose_lane_geometry
+    const bool fit = lane_warps == c->lane_warps && a.custom_dict_size == 0 && c->sort_streams && n >= 64 &&
+                     c->lane_slot_bytes == brotli_b200::lane_slot_bytes(c->lane_warps) && (c->alt[0].ctas > 0 || c->alt[1].ctas > 0);
     la.arena = c->lane_arena; la.bail_count = c->bail_count; la.bail_list = (uint32_t*)c->bail_list.p;
     la.xdict = c->xdict;
     la.cdict = a.custom_dict; la.cdict_len = a.custom_dict_size;
@@ -311,8 +297,36 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
       g_launches.fetch_add(2);
       a.order = (const uint32_t*)c->order.p + 3 * n;
     }
-    CU_TRY(brotli_b200::launch_decode_lane(a, la, lane_ctas, lane_warps, stream));
-    g_launches.fetch_add(1);
+    if (fit) {
+      // one launch per candidate geometry; all but the chosen one exit at once (the choice is made on the device, so
+      // the call stays asynchronous)
+      uint32_t* const d_geom = c->ticket + 24;  // [0] choice, [1..3] resident lanes per candidate (same 256-byte allocation as the tickets)
+      uint32_t lanes[3] = {(uint32_t)(lane_ctas * lane_warps * 32), c->alt[0].ctas > 0 ? (uint32_t)(c->alt[0].ctas * c->alt[0].warps * 32) : 0u,
+                           c->alt[1].ctas > 0 ? (uint32_t)(c->alt[1].ctas * c->alt[1].warps * 32) : 0u};
+      if (!c->geom_lanes_uploaded) {
+        CU_TRY(cudaMemcpyAsync(d_geom + 1, lanes, sizeof(lanes), cudaMemcpyHostToDevice, stream));
+        c->geom_lanes_uploaded = true;
+      }
+      CU_TRY(brotli_b200::launch_choose_lane_geometry((uint32_t)n, (const uint32_t*)c->order.p + n, d_geom + 1, 3, d_geom, stream));
+      CU_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream));
+      CU_TRY(cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream));
+      la.geom_choice = d_geom;
+      for (uint32_t g = 0; g < 3; g++) {
+        if (lanes[g] == 0) continue;
+        brotli_b200::LaneArgs lg = la;
+        lg.geom_id = g;
+        const int gw = g == 0 ? lane_warps : c->alt[g - 1].warps, gc = g == 0 ? lane_ctas : c->alt[g - 1].ctas;
+        if (g != 0) lg.slot_bytes = c->alt[g - 1].slot_bytes;
+        const size_t gwarps = (size_t)gc * gw, gper = (n + gwarps - 1) / gwarps;
+        lg.chunk = gper >= 32 ? 32u : (uint32_t)gper;
+        CU_TRY(brotli_b200::launch_decode_lane(a, lg, gc, gw, stream, false));
+        g_launches.fetch_add(1);
+      }
+      g_launches.fetch_add(1);
+    } else {
+      CU_TRY(brotli_b200::launch_decode_lane(a, la, lane_ctas, lane_warps, stream));
+      g_launches.fetch_add(1);
+    }
     // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
     a.order = la.bail_list; a.n_ptr = la.bail_count; a.ticket = c->ticket + 8;
   }

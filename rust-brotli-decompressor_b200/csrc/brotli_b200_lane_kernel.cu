@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   uint32_t* const s_word_info = lane::g_word_info;
   uint32_t* const s_transform_info = lane::g_transform_info;
   extern __shared__ __align__(16) uint8_t s_dyn[];
+  if (la.geom_choice && *la.geom_choice != la.geom_id) return;  // another geometry's launch decodes this batch
   for (uint32_t i = threadIdx.x; i < 704; i += blockDim.x) s_cmd_lut[i] = pack_cmd_lut(i);
   for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_ctx_lut[i] = tbl::kBrotliContextLookup[i];
   {
@@ -137,6 +138,36 @@ cudaError_t launch_order_by_size(uint32_t n, const uint64_t* in_off, uint32_t* s
   return cub::DeviceRadixSort::SortPairsDescending((void*)(scratch + 4 * (size_t)n), temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 24, stream);
 }
 
+// Geometry by wave fit (see brotli_b200_runtime.h).  Full waves cost the same per stream at 14..24 warps per SM (the
+// kernel is bound by the memory system), a partial last wave costs at least a stream's latency -- about half a wave of
+// the default geometry -- however few streams it holds.  Cost in lane-slots: full waves + max(that floor, 0.8 x the
+// rest); a batch that fits one wave of an alternative takes the first such; the default keeps a 7 % bonus (the model
+// is good to a few per cent: profiles/r02/waves.txt, fit.txt).
+__global__ void brotli_lane_geometry_kernel(uint32_t n, const uint32_t* sorted_keys, const uint32_t* lanes, uint32_t n_geom, uint32_t* choice) {
+  uint32_t pick = 0;
+  const uint32_t kmax = sorted_keys[0], kmin = sorted_keys[n - 1];
+  if (2 * kmin >= kmax && kmin != 0) {
+    auto cost = [](uint64_t streams, uint64_t l) {
+      const uint64_t full = streams / l, rest = streams - full * l;
+      const uint64_t floor_slots = 51000;
+      const uint64_t tail = rest == 0 ? 0 : (rest * 4 / 5 > floor_slots ? rest * 4 / 5 : floor_slots);
+      return full * l + tail;
+    };
+    uint64_t best = cost(n, lanes[0]) * 93 / 100;
+    for (uint32_t k = 1; k < n_geom; k++) {
+      if (lanes[k] == 0) continue;
+      const uint64_t ck = n <= lanes[k] ? 0 : cost(n, lanes[k]);
+      if (ck < best) { best = ck; pick = k; }
+    }
+  }
+  *choice = pick;
+}
+
+cudaError_t launch_choose_lane_geometry(uint32_t n, const uint32_t* sorted_keys, const uint32_t* lanes, uint32_t n_geom, uint32_t* choice, cudaStream_t stream) {
+  brotli_lane_geometry_kernel<<<1, 1, 0, stream>>>(n, sorted_keys, lanes, n_geom, choice);
+  return cudaGetLastError();
+}
+
 namespace {
 template <int WARPS>
 int lane_occupancy(uint32_t dyn) {
@@ -184,12 +215,15 @@ int query_lane_resident_ctas(int device, int warps) {
 // the dictionary instance exists for the default geometry only
 bool lane_kernel_takes_dictionary(int warps) { return warps == kLaneWarpsPerCta; }
 
-cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream) {
+cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream, bool reset_counters) {
   if (la.cdict_len != 0 && !lane_kernel_takes_dictionary(warps)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (reset_counters) {
+    e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+  }
   const uint32_t dyn = (la.slot_bytes + 128u) * (uint32_t)(warps * 32);
   if (la.cdict_len != 0) {  // (the default geometry: checked above)
     if (cudaFuncSetAttribute(brotli_decode_lane_kernel<kLaneWarpsPerCta, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return cudaGetLastError();

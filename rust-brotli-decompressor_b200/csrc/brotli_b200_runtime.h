@@ -68,6 +68,9 @@ struct LaneArgs {
   uint32_t chunk;        // streams a warp takes per ticket (1..32)
   const uint8_t* cdict;  // custom LZ77 dictionary of the batch or nullptr; 16 readable bytes on either side
   uint64_t cdict_len;
+  // geometry chosen on the device (launch_choose_lane_geometry): a launch whose id is not the chosen one exits at once
+  const uint32_t* geom_choice = nullptr;
+  uint32_t geom_id = 0;
 };
 
 size_t arena_bytes_per_warp();
@@ -83,7 +86,12 @@ size_t xdict_bytes();
 cudaError_t launch_build_xdict(const uint8_t* dictionary, uint8_t* xdict, cudaStream_t stream);
 int query_lane_resident_ctas(int device, int warps);
 bool lane_kernel_takes_dictionary(int warps);
-cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream);
+cudaError_t launch_decode_lane(const BatchArgs& a, const LaneArgs& la, int ctas, int warps, cudaStream_t stream, bool reset_counters = true);
+// Geometry by wave fit, decided on the device after the longest-first sort (`sorted_keys`: compressed sizes in 256-byte
+// buckets, descending): lanes[0] is the default geometry, lanes[1..n_geom) the alternatives with fewer resident lanes
+// (0 = not available).  *choice = index of the geometry to run.  Only uniform batches (smallest stream at least half
+// the largest) are fitted: their waves run in lock-step, which is what makes the fit matter.
+cudaError_t launch_choose_lane_geometry(uint32_t n, const uint32_t* sorted_keys, const uint32_t* lanes, uint32_t n_geom, uint32_t* choice, cudaStream_t stream);
 cudaError_t launch_checksum_batch(uint32_t n, const uint8_t* bytes, const uint64_t* off, const uint64_t* len, uint64_t* sums,
                                   cudaStream_t stream);
 

@@ -74,6 +74,14 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #define BD_LANE_BURST 0
 #endif
 // narrowest root a group may get in the shared slot, and the weights of the three symbol kinds in the root-width allocation
+// root widths: all combinations instead of the greedy widening
+#ifndef BD_LANE_ROOTS_EXHAUSTIVE
+#define BD_LANE_ROOTS_EXHAUSTIVE 0
+#endif
+// only the current block type's distance trees in the shared slot (see refresh_cur_dist)
+#ifndef BD_LANE_DIST_CACHE
+#define BD_LANE_DIST_CACHE 1
+#endif
 // roots that live in the arena are looked up asynchronously as well (their root entry is requested a phase ahead)
 #ifndef BD_LANE_ASYNC_ARENA_ROOTS
 #define BD_LANE_ASYNC_ARENA_ROOTS 1
@@ -340,6 +348,7 @@ struct Lane {
   uint32_t rbits[3], root[3];  // per group (0 literal, 1 command, 2 distance): root width, root base (virtual index)
   uint32_t trivial_lo, trivial_hi;      // bit i: literal block type i uses one tree for all 64 contexts
   uint32_t trivial, lit_tree, ctx_mode_off, ctx_slice, cmd_tree, dist_slice;
+  uint32_t dist_home;    // 0, or (distance-tree cache) the virtual index in the arena where all distance trees' roots live
   uint32_t cold_next;    // next free virtual index of the arena part of the table space
   uint32_t e_tab;        // entries of the shared slot available to tables in this metablock (E, or E - kCtxMapEntries)
 
@@ -912,10 +921,28 @@ BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_
 BD_DEV uint32_t tree_root(const Lane& L, uint32_t g, uint32_t i) { return L.root[g] + (i << L.rbits[g]); }
 
 // Distance-context -> root of its tree for the current distance block type, kept in the shared slot.
+// With the distance-tree cache (L.dist_home != 0: more distance trees than a block type can use) only the trees of the
+// current block type's four distance contexts are in the shared slot: each context has a cache slot of one root, filled
+// here from the tree's home in the arena (second-level pointers are arena indices, so a root can be copied anywhere).
+// Contexts that share a tree share the slot of the first of them.
 BD_DEV void refresh_cur_dist(const LaneCtx& c, const Lane& L) {
+  uint32_t tr[4];
   for (uint32_t ctx = 0; ctx < 4; ctx++) {
     const uint32_t t = c.ctx_dist[L.dist_slice + ctx];
-    sts32(c.slot + ctx * 4, tree_root(L, 2, t));
+    tr[ctx] = t;
+    if (L.dist_home == 0) { sts32(c.slot + ctx * 4, tree_root(L, 2, t)); continue; }
+    uint32_t same = ctx;
+    for (uint32_t k = 0; k < ctx; k++) if (tr[k] == t && same == ctx) same = k;
+    const uint32_t dst_v = L.root[2] + (same << L.rbits[2]);
+    sts32(c.slot + ctx * 4, dst_v);
+    if (same != ctx) continue;
+    const uint16_t* src = c.gtab + (L.dist_home - c.E) + (t << L.rbits[2]);
+    const uint32_t n = 1u << L.rbits[2];
+    if (n >= 2) {
+      for (uint32_t j = 0; j < n; j += 2) sts32(c.stab + ((dst_v + j) << 1), *(const uint32_t*)(src + j));  // (both sides 4-byte aligned)
+    } else {
+      sts16(c.stab + (dst_v << 1), src[0]);
+    }
   }
 }
 
@@ -1108,7 +1135,12 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   // long.  Typical shares of symbols with codes longer than R (per cent; text and binary corpora)
   // stand in for the streams' own statistics.  Jumps over several widths are considered at once (the saving per
   // entry is not monotonic: the first bits of a root save nothing).
-  const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], L.n_dist};
+  // Distance-tree cache: a block type uses at most four distance trees (one per distance context), so when the
+  // metablock has more, the shared slot only holds four cache slots (see refresh_cur_dist) and the group is sized --
+  // and widened -- as four trees; all trees are built at their home in the arena.
+  const bool dist_cache = BD_LANE_DIST_CACHE && L.n_dist > 4;
+  const uint32_t ntrees_all[3] = {L.n_lit, L.nbt[1], L.n_dist};
+  const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], dist_cache ? 4u : L.n_dist};
   const uint32_t rmin[3] = {4, 4, 3}, rmax[3] = {8, 8, 7};
   const uint32_t alpha[3] = {256, 704, L.dist_alphabet};
   const uint32_t save_lo = L.lo, save_hi = L.hi, save_nx = L.nx, save_k = L.k, save_bp = L.bp, save_cold = L.cold_next;
@@ -1148,6 +1180,23 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
                                              {100, 96, 78, 51, 37, 25, 16, 10, 6},   // command
                                              {100, 98, 92, 78, 32, 12, 5, 3, 1}};    // distance
     static const uint8_t kGroupWeight[3] = {BD_LANE_W_LIT, BD_LANE_W_CMD, BD_LANE_W_DIST};
+#if BD_LANE_ROOTS_EXHAUSTIVE
+    // all combinations of widths of the groups in the slot (at most 5^3): fewest expected second-level look-ups, then
+    // fewest entries
+    {
+      uint32_t best_score = 0xFFFFFFFFu, best_size = 0, pick[3] = {rb[0], rb[1], rb[2]};
+      const uint32_t lo0 = rb[0], lo1 = rb[1], lo2 = rb[2];
+      const uint32_t hi0 = shared[0] ? rmax[0] : lo0, hi1 = shared[1] ? rmax[1] : lo1, hi2 = shared[2] ? rmax[2] : lo2;
+      for (uint32_t r0 = lo0; r0 <= hi0; r0++) for (uint32_t r1 = lo1; r1 <= hi1; r1++) for (uint32_t r2 = lo2; r2 <= hi2; r2++) {
+        const uint32_t size = (shared[0] ? ntrees[0] << r0 : 0u) + (shared[1] ? ntrees[1] << r1 : 0u) + (shared[2] ? ntrees[2] << r2 : 0u);
+        if (size > L.e_tab) continue;
+        const uint32_t score = (shared[0] ? kLongShare[0][r0] * kGroupWeight[0] : 0u) + (shared[1] ? kLongShare[1][r1] * kGroupWeight[1] : 0u) +
+                               (shared[2] ? kLongShare[2][r2] * kGroupWeight[2] : 0u);
+        if (score < best_score || (score == best_score && size < best_size)) { best_score = score; best_size = size; pick[0] = r0; pick[1] = r1; pick[2] = r2; }
+      }
+      rb[0] = pick[0]; rb[1] = pick[1]; rb[2] = pick[2];
+    }
+#else
     for (;;) {
       uint32_t total = 0, g = 3, to = 0;
       uint32_t best_num = 0, best_den = 1;  // benefit / cost of the best step, compared as fractions
@@ -1163,6 +1212,7 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
       if (g == 3) break;
       rb[g] = to;
     }
+#endif
     uint32_t next_shared = 0;
     const uint32_t order[3] = {1, 0, 2};
     bool fits = true;
@@ -1179,11 +1229,23 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
       }
       L.rbits[g] = rb[g];
     }
+    L.dist_home = 0;
+    if (fits && dist_cache && shared[2]) {  // (a distance group that went to the arena as a whole needs no cache)
+      const uint32_t sz = L.n_dist << rb[2];
+      if (L.cold_next + sz > c.E + kGlobalTab) fits = false;
+      else { L.dist_home = L.cold_next; L.cold_next += sz; }
+    } else if (fits && dist_cache) {
+      // the whole group is in the arena after all: it was placed as four trees, it has n_dist
+      const uint32_t extra = (L.n_dist - 4u) << rb[2];
+      if (L.root[2] + (4u << rb[2]) != L.cold_next || L.cold_next + extra > c.E + kGlobalTab) fits = false;
+      else L.cold_next += extra;
+    }
     // HuffmanTreeGroupDecode x3, :1130-1219
     int r = fits ? kLaneOk : kLaneBail;
     for (uint32_t g = 0; g < 3 && r == kLaneOk; g++) {
-      for (uint32_t i = 0; i < ntrees[g] && r == kLaneOk; i++) {
-        r = read_huffman_code(c, L, alpha[g], alpha[g], tree_root(L, g, i), L.rbits[g]);
+      for (uint32_t i = 0; i < ntrees_all[g] && r == kLaneOk; i++) {
+        const uint32_t rv = (g == 2 && L.dist_home != 0) ? L.dist_home + (i << L.rbits[2]) : tree_root(L, g, i);
+        r = read_huffman_code(c, L, alpha[g], alpha[g], rv, L.rbits[g]);
         if (r == kLaneOk && L.overrun()) r = kLaneBail;
       }
     }
