@@ -7,29 +7,34 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
 nproc >> $OUT/gpu.txt; free -g >> $OUT/gpu.txt
+if [ -n "$PROFILE_ONLY" ]; then SKIP_TESTS=1; fi
 if [ -z "$SKIP_TESTS" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> $OUT/pytest_gpu.log
   tail -5 $OUT/pytest_gpu.log
 fi
+if [ -z "$PROFILE_ONLY" ]; then
 timeout 900 python bench.py --steps 5 --warmup 3 ${BENCH_ARGS} > $OUT/bench.json 2> $OUT/bench.err
 echo "bench exit $?"; cat $OUT/bench.json; tail -5 $OUT/bench.err
+fi
 if [ -n "$WITH_REFERENCE" ]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
   cat $OUT/bench_reference.json
 fi
-# launch list (cold-cache, serialised: compare shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
-  python bench.py --streams 131072 --unique 2048 --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/launches_bench.log 2>&1
-# full capture of the dominant decode kernel (4th launch = first timed step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:brotli_decode_lane -s 3 -c 1 -o $OUT/prof_lane \
-  python bench.py --streams 131072 --unique 2048 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_bench.log 2>&1
+# launch list of the decode path (cold-cache, serialised: compare shares only): our kernels, the CUB sort and torch's fills
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:brotli|RadixSort|Fill' -c 300 --csv --log-file $OUT/launches.csv \
+  python bench.py --unique 2048 --steps 2 --warmup 3 --no-e2e --no-cpu --no-other-configs > $OUT/launches_bench.log 2>&1
+# full capture of the dominant decode kernel on the full headline batch (4th launch = first timed step).  The geometry fit is
+# off for the capture: it launches every candidate geometry and all but one exit at once (the default is the chosen one here)
+BROTLI_B200_LANE_FIT=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:brotli_decode_lane -s 3 -c 1 -o $OUT/prof_lane \
+  python bench.py --unique 2048 --steps 1 --warmup 3 --no-e2e --no-cpu --no-other-configs > $OUT/prof_bench.log 2>&1
 ncu -i $OUT/prof_lane.ncu-rep --page source --csv > $OUT/source.csv 2>/dev/null
 python profiles/ncu_l2_by_inst.py $OUT/source.csv 16 > $OUT/ncu_l2_by_inst.txt 2>&1
 python profiles/ncu_hot.py $OUT/prof_lane.ncu-rep > $OUT/ncu_lane_kernel.txt 2>&1
+python profiles/ncu_regions.py $OUT/prof_lane.ncu-rep 12 > $OUT/ncu_regions.txt 2>&1
 ncu -i $OUT/prof_lane.ncu-rep --page raw --csv > $OUT/ncu_lane_kernel_raw.csv 2>/dev/null
 # DRAM traffic of that capture + kernel source fingerprint -> what bench.py quotes as roofline.traffic
-python profiles/ncu_traffic.py $OUT/ncu_lane_kernel_raw.csv 131072 brotli_decode_lane_kernel $OUT/current_traffic.json
+python profiles/ncu_traffic.py $OUT/ncu_lane_kernel_raw.csv 262144 brotli_decode_lane_kernel $OUT/current_traffic.json
 rm -f $OUT/source.csv
 if [ -n "$WITH_CONFIGS" ]; then timeout 900 python profiles/gpu_configs.py > $OUT/configs.jsonl 2> $OUT/configs.err; cat $OUT/configs.jsonl | cut -c1-250; fi
 ls -la $OUT
