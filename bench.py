@@ -66,8 +66,7 @@ def measured_traffic(kernel, streams_per_launch):
     if t.get("kernel") not in kernel:
         return None, "capture is of another kernel"
     k = float(streams_per_launch) / float(t["streams_per_launch"])
-    one_wave = 148 * 20 * 32  # resident lanes of the default lane-kernel geometry
-    if not (0.75 <= k <= 1.25 or (streams_per_launch >= one_wave and t["streams_per_launch"] >= one_wave)):
+    if not 0.75 <= k <= 1.25:  # (other batch sizes run other geometries and fall into waves differently)
         return None, "capture has %d streams per launch" % t["streams_per_launch"]
     return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * k), "profiles/current_traffic.json (%s, %d streams per launch)" % (
         t.get("captured", "?"), t["streams_per_launch"])

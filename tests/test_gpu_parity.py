@@ -362,6 +362,41 @@ def test_exact_kernel_wide_geometry(gpu_lib, pkg, oracle, corpus):
         pkg.set_tuning("lane_min_streams", 0)
 
 
+def test_lane_geometry_by_wave_fit(gpu_lib, pkg, corpus):
+    """A uniform batch that fits one wave of the 14-warp geometry but not the 8-warp one is decoded by the geometry the
+    device picks after the sort (csrc/brotli_b200_lane_kernel.cu, brotli_lane_geometry_kernel): every candidate geometry
+    is launched, all but the chosen one exit at once.  Same bytes as the originals either way; a mixed batch of the same
+    size is not fitted (one lane-kernel launch)."""
+    import torch
+    comp, orig, _ = corpus.make_config("C2", 48, size=4096)          # uniform: 4 KiB text windows
+    compm, origm, _ = corpus.make_config("C5", 48, size=4096)        # mixed qualities and families
+    n = 40000
+    for blobs, originals, uniform in ((comp, orig, True), (compm, origm, False)):
+        idx = np.arange(n) % len(blobs)
+        in_bytes, in_off = corpus.pack([blobs[i] for i in idx])
+        osz = np.array([len(originals[i]) for i in idx], dtype=np.uint64)
+        out_off = np.zeros(n + 1, dtype=np.uint64); np.cumsum(osz, out=out_off[1:])
+        d_in = torch.from_numpy(in_bytes.copy()).cuda(); d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
+        d_out_off = torch.from_numpy(out_off.view(np.int64)).cuda()
+        d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(n, dtype=torch.int64, device="cuda"); d_codes = torch.zeros(n, dtype=torch.int32, device="cuda")
+        before = pkg.kernel_launch_count()
+        pkg.kernel_times(reset=True)
+        pkg.decompress_batch_device(n, d_in, d_in_off, d_out, d_out_off, d_len, d_codes)
+        torch.cuda.synchronize()
+        launches = pkg.kernel_launch_count() - before
+        kt = pkg.kernel_times()
+        assert bool((d_codes == 1).all()) and kt["lane_ms"] > 0.5
+        out = d_out.cpu().numpy()
+        for j in range(0, n, 331):
+            assert out[int(out_off[j]):int(out_off[j + 1])].tobytes() == originals[idx[j]]
+        # sort (2) + lane kernel + exact kernel = 4 launches; the fitted path adds the choice and two more lane launches
+        sizes = np.array([len(b) for b in blobs])
+        is_uniform = 2 * (sizes.min() >> 8) >= (sizes.max() >> 8) and (sizes.min() >> 8) != 0
+        assert is_uniform == uniform, (sizes.min(), sizes.max())
+        assert launches >= 6 if uniform else launches == 4, launches
+
+
 def test_differential_fuzz_error_codes(gpu_lib, pkg, oracle, corpus):
     """every BrotliDecoderErrorCode and decoded_size the GPU path reports for malformed input
     equals the oracle's, over a few thousand seeded mutations (truncations, bit flips, byte smashes, multi-byte
