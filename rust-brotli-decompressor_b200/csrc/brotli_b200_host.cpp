@@ -377,21 +377,23 @@ int decode_host_packed(DeviceCtx* c, size_t n, const uint8_t* in_bytes, const ui
   std::vector<Chunk> chunks;
   for (size_t b = 0; b < n;) {
     size_t e = b; uint64_t acc = 0;
-    // a chunk should fill every resident lane of the lane kernel: a launch takes about as long for a few streams
-    // as for one stream per lane
-    // (the first chunk is 0.4 of that: its H2D copy is not hidden behind anything, but its D2H copy should last as long
-    // as the decode of the second chunk -- BROTLI_B200_PIPE_TRACE timeline, profiles/r01/zz_pipe_trace.txt.  A longer geometric ramp --
-    // BROTLI_B200_PIPE_RAMP=k: 1/2^k, ..., 1/2, 1 -- was measured and loses: every extra launch costs a full wave,
-    // 374 / 380 / 396 ms per headline call for k = 2 / 3 / 4 against 373 ms for the single quarter chunk)
-    size_t min_streams = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
+    // A chunk should fill every resident lane of the lane kernel (a launch takes about as long for a few streams as for
+    // one stream per lane), but nothing can leave before the first chunk is up and decoded, and the D2H stream -- the
+    // bottleneck: 2.6x the bytes of the H2D stream -- should never wait for a decode.  So the chunks ramp up: 1/4 and
+    // 1/2 of the resident lanes, then full waves (BROTLI_B200_PIPE_RAMP=k: 1/2^k, ..., 1/2, 1; 0: the plan of round 1,
+    // a single 0.4 chunk first).  Measured on the headline call, profiles/r02/e2e_ramp.txt; a remainder below a quarter
+    // wave joins the chunk before it.
+    const size_t lanes = c->lane_ctas > 0 ? (size_t)c->lane_ctas * c->lane_warps * 32 : 1;
+    size_t min_streams = lanes;
     {
-      static const int ramp = getenv("BROTLI_B200_PIPE_RAMP") ? atoi(getenv("BROTLI_B200_PIPE_RAMP")) : 0;
+      static const int ramp = getenv("BROTLI_B200_PIPE_RAMP") && getenv("BROTLI_B200_PIPE_RAMP")[0] ? atoi(getenv("BROTLI_B200_PIPE_RAMP")) : 2;
       const int ci = (int)chunks.size();
       if (ramp > 0) { if (ci < ramp) min_streams >>= (ramp - ci); }
       else if (b == 0) min_streams = min_streams * 2 / 5;
       if (min_streams == 0) min_streams = 1;
     }
     while (e < n && (e == b || acc < kPipelineChunkBytes || e - b < min_streams)) { acc += (in_off[e + 1] - in_off[e]) + (out_off[e + 1] - out_off[e]); e++; }
+    if (n - e < lanes / 4) e = n;
     chunks.push_back(Chunk{b, e, nullptr, nullptr, nullptr});
     b = e;
   }
