@@ -175,7 +175,11 @@ BROTLI_B200_API void BrotliDecoderFreeUsize(BrotliDecoderState* state, size_t* d
 
 /* Device-resident batch: every pointer is a device pointer on the current CUDA device;
  * `cuda_stream` is a cudaStream_t (NULL = default stream).  Asynchronous: returns after the
- * launch; results are valid once the stream has been synchronised.  No host<->device copies. */
+ * launch; results are valid once the stream has been synchronised.  No host<->device copies.
+ * The library's scratch buffers (bail list, stream order) grow on the first call of a larger batch: that call may
+ * allocate device memory (an implicit synchronisation), so the entry is not meant for CUDA graph capture; launches of
+ * different host threads / streams are ordered one after the other (they share the decoders' table arenas).  A stream
+ * that is corrupt beyond a too small capacity keeps NeedsMoreOutput(3) here. */
 BROTLI_B200_API int BrotliB200DecompressBatchDevice(size_t n, const uint8_t* d_in_bytes, const uint64_t* d_in_off,
                                                     uint8_t* d_out_bytes, const uint64_t* d_out_off,
                                                     uint64_t* d_out_len, int32_t* d_codes, void* cuda_stream);
@@ -241,12 +245,16 @@ BROTLI_B200_API double BrotliB200LastKernelMs(void);
 BROTLI_B200_API int BrotliB200KernelTimes(double* lane_ms, double* exact_ms, uint32_t* launches, uint32_t* bailed, int reset);
 /* Tuning knobs of the current device (tests and benchmarks force a decode path with them): "lane_min_streams" -- batches
  * smaller than this skip the lane-per-stream kernel (default 6000, from the measured latency table); "small_geometry" --
- * 0/1, the 8-warp geometry for batches below one wave; "sort_streams" -- 0/1, longest-first order.  Returns 1 if set. */
+ * 0/1, the 8-warp geometry for batches below one wave; "sort_streams" -- 0/1, longest-first order; "lane_slot_bytes" -- a
+ * smaller table slot per lane than the geometry allows (0 = all of it).  Returns 1 if set. */
 BROTLI_B200_API int BrotliB200SetTuning(const char* name, uint64_t value);
 /* Last library-level error message of the calling thread ("" if none). */
 BROTLI_B200_API const char* BrotliB200LastError(void);
 /* Resident decoding warps per launch on the current device (148 SMs x warps per SM on a B200). */
 BROTLI_B200_API int BrotliB200ResidentWarps(void);
+/* Warps per SM of the lane-per-stream kernel that decoded the most recent batch on the current device (the geometry is
+ * chosen per batch, for uniform batches on the device itself); 0 if that batch did not use it.  Synchronises the device. */
+BROTLI_B200_API int BrotliB200LastLaneGeometry(void);
 /* Frees the per-device scratch arenas and staging buffers. */
 BROTLI_B200_API void BrotliB200Shutdown(void);
 

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "BrotliB200DecompressBatchPacked", "BrotliB200DecompressBatch", "BrotliB200ChecksumBatchDevice",
     "BrotliB200DecompressWithDictionary", "BrotliB200DecompressBatchPackedWithDictionary", "BrotliB200DecoderSetCustomDictionary",
     "BrotliB200DecoderDecompressStreamBatch", "BrotliB200SetTuning",
-    "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps",
+    "BrotliB200KernelLaunchCount", "BrotliB200LastKernelMs", "BrotliB200KernelTimes", "BrotliB200LastError", "BrotliB200ResidentWarps", "BrotliB200LastLaneGeometry",
     "BrotliB200Shutdown",
 ]
 
@@ -112,6 +112,7 @@ def lib():
     L.BrotliB200KernelTimes.argtypes = [vp, vp, vp, vp, ctypes.c_int]
     L.BrotliB200LastError.restype = u8p
     L.BrotliB200ResidentWarps.restype = ctypes.c_int
+    L.BrotliB200LastLaneGeometry.restype = ctypes.c_int
     L.BrotliB200Shutdown.restype = None
     _lib = L
     return L
@@ -232,6 +233,11 @@ class DecoderState:
 
     def error_string(self):
         return lib().BrotliDecoderGetErrorString(self._s).decode()
+
+
+def last_lane_geometry():
+    """BrotliB200LastLaneGeometry: warps per SM of the lane kernel that decoded the most recent batch (0: it was not used)."""
+    return int(lib().BrotliB200LastLaneGeometry())
 
 
 def set_tuning(name, value):

@@ -110,6 +110,7 @@ struct DeviceCtx {
   struct LaneGeom { int warps = 0, ctas = 0; uint32_t slot_bytes = 0; };
   LaneGeom alt[2];
   bool geom_lanes_uploaded = false;
+  int last_lane_warps = 0;       // geometry of the most recent lane launch; -1: chosen on the device (ticket + 24)
   size_t lane_min_streams = 0; // batches smaller than this go straight to the warp-per-stream kernel
   uint8_t* lane_arena = nullptr;
   uint8_t* xdict = nullptr;    // expanded static dictionary of the lane kernel
@@ -270,6 +271,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
   CU_TRY(cudaEventRecord(c->ev_t[slot][0], stream));
   // (a streaming session is one stream: exact kernel; a batch with a custom dictionary takes the lane kernel's dictionary
   // instance when the configured geometry has one)
+  c->last_lane_warps = 0;
   if (c->lane_ctas > 0 && a.sessions == nullptr && n >= c->lane_min_streams &&
       (a.custom_dict_size == 0 || brotli_b200::lane_kernel_takes_dictionary(c->lane_warps))) {
     // optimistic pass: one stream per lane; whatever it gives up lands on the bail list
@@ -311,6 +313,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
       CU_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream));
       CU_TRY(cudaMemsetAsync(la.bail_count, 0, sizeof(uint32_t), stream));
       la.geom_choice = d_geom;
+      c->last_lane_warps = -1;
       for (uint32_t g = 0; g < 3; g++) {
         if (lanes[g] == 0) continue;
         brotli_b200::LaneArgs lg = la;
@@ -326,6 +329,7 @@ int decode_device(DeviceCtx* c, size_t n, const uint8_t* d_in, const uint64_t* d
     } else {
       CU_TRY(brotli_b200::launch_decode_lane(a, la, lane_ctas, lane_warps, stream));
       g_launches.fetch_add(1);
+      c->last_lane_warps = lane_warps;
     }
     // exact pass over the bail list (usually empty): one warp per stream, full reference semantics
     a.order = la.bail_list; a.n_ptr = la.bail_count; a.ticket = c->ticket + 8;
@@ -1057,6 +1061,20 @@ int BrotliB200SetTuning(const char* name, uint64_t value) {
     return 1;
   }
   return 0;
+}
+
+int BrotliB200LastLaneGeometry(void) {
+  DeviceCtx* c = acquire_ctx();
+  if (!c) return -1;
+  std::lock_guard<std::mutex> lock(c->launch_mu);
+  if (c->last_lane_warps >= 0) return c->last_lane_warps;
+  uint32_t choice = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&choice, c->ticket + 24, sizeof(choice), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  if (choice == 0) return c->lane_warps;
+  return choice <= 2 ? c->alt[choice - 1].warps : -1;
 }
 
 int BrotliB200ResidentWarps(void) {
