@@ -9,7 +9,10 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module("rust-brotli-decompressor_b200")
 corpus = importlib.import_module("tools.corpus")
 pkg.lib()
+ONLY = [c for c in os.environ.get("CONFIGS", "").split(",") if c]  # e.g. CONFIGS=C3,C5
 for cfg, n_unique, n, size in (("C3", 4096, 1 << 20, 4096), ("C5", 2200, 131072, 65536), ("C4", 8, 2048, 4 << 20)):
+    if ONLY and cfg not in ONLY:
+        continue
     comp, orig, desc = corpus.make_config(cfg, n_unique, size=size)
     idx = np.random.default_rng(1).integers(0, n_unique, size=n)
     sizes = np.array([len(c) for c in comp], dtype=np.uint64)

@@ -82,6 +82,15 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #ifndef BD_LANE_DIST_CACHE
 #define BD_LANE_DIST_CACHE 1
 #endif
+// cache slots of the distance-tree cache: as many as a block type really uses (1), or always four (0: the first version)
+#ifndef BD_LANE_DIST_SLOTS_EXACT
+#define BD_LANE_DIST_SLOTS_EXACT 1
+#endif
+// MEASUREMENT ONLY (output is wrong): every backreference reads its source from the lane's most recent output lines, which
+// are still in L2 -- what the kernel would run at if copy sources cost no DRAM transaction
+#ifndef BD_LANE_PROBE_NEAR
+#define BD_LANE_PROBE_NEAR 0
+#endif
 // roots that live in the arena are looked up asynchronously as well (their root entry is requested a phase ahead)
 #ifndef BD_LANE_ASYNC_ARENA_ROOTS
 #define BD_LANE_ASYNC_ARENA_ROOTS 1
@@ -176,9 +185,14 @@ BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 #ifndef BD_LANE_L2_HINTS
 #define BD_LANE_L2_HINTS 4
 #endif
-// modes: 0 no hints; 1 (default) input / output / copy sources evict-first, table arena evict-last; 2 as 1, copy sources
-// without a hint; 3 as 1, output stores without a hint; 4 as 1, table arena without a hint
-#if BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
+// modes: 0 no hints; 1 input / output / copy sources evict-first, table arena evict-last; 2 as 1, copy sources
+// without a hint; 3 as 1, output stores without a hint; 4 (default) as 1, table arena without a hint; 5 as 4, output
+// stores evict-LAST (does a lane's recent output stay in L2 for its short-distance copies?)
+#if BD_LANE_L2_HINTS == 5
+// (not volatile, no inputs: the compiler keeps one copy of the policy per function)
+BD_DEV uint64_t l2_policy_keep_pure() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_keep_pure()) : "memory"); }
+#elif BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
 BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }  // streaming: evict first
 #else
 BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
@@ -188,7 +202,9 @@ BD_DEV void sts32_if(bool cond, hw::sref_t a, uint32_t v) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "r"(a), "r"(v) : "memory");
 }
 BD_DEV void st32_if(bool cond, uint8_t* p, uint32_t v) {
-#if BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
+#if BD_LANE_L2_HINTS == 5
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.L2::cache_hint.u32 [%1], %2, %3;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v), "l"(l2_policy_keep_pure()) : "memory");
+#elif BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
 #else
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
@@ -349,6 +365,7 @@ struct Lane {
   uint32_t trivial_lo, trivial_hi;      // bit i: literal block type i uses one tree for all 64 contexts
   uint32_t trivial, lit_tree, ctx_mode_off, ctx_slice, cmd_tree, dist_slice;
   uint32_t dist_home;    // 0, or (distance-tree cache) the virtual index in the arena where all distance trees' roots live
+  uint32_t dist_slots;   // cache slots: the largest number of distinct trees any distance block type uses (1..4)
   uint32_t cold_next;    // next free virtual index of the arena part of the table space
   uint32_t e_tab;        // entries of the shared slot available to tables in this metablock (E, or E - kCtxMapEntries)
 
@@ -921,19 +938,22 @@ BD_COLD int decode_context_map(const LaneCtx& c, Lane& L, uint32_t size, uint32_
 BD_DEV uint32_t tree_root(const Lane& L, uint32_t g, uint32_t i) { return L.root[g] + (i << L.rbits[g]); }
 
 // Distance-context -> root of its tree for the current distance block type, kept in the shared slot.
-// With the distance-tree cache (L.dist_home != 0: more distance trees than a block type can use) only the trees of the
-// current block type's four distance contexts are in the shared slot: each context has a cache slot of one root, filled
-// here from the tree's home in the arena (second-level pointers are arena indices, so a root can be copied anywhere).
-// Contexts that share a tree share the slot of the first of them.
+// With the distance-tree cache (L.dist_home != 0: more distance trees than any one block type uses) only the trees of the
+// current block type's four distance contexts are in the shared slot: L.dist_slots cache slots of one root each, filled
+// here from the trees' homes in the arena (second-level pointers are arena indices, so a root can be copied anywhere).
+// Contexts that share a tree share a slot -- the q5..q9 encoder gives every distance block type ONE tree for all four
+// contexts, so the whole distance group usually costs a single root.
 BD_DEV void refresh_cur_dist(const LaneCtx& c, const Lane& L) {
-  uint32_t tr[4];
+  uint32_t tr[4], slot_of[4];
+  uint32_t used = 0;  // cache slots taken by this block type (at most L.dist_slots: the maximum over all block types)
   for (uint32_t ctx = 0; ctx < 4; ctx++) {
     const uint32_t t = c.ctx_dist[L.dist_slice + ctx];
     tr[ctx] = t;
     if (L.dist_home == 0) { sts32(c.slot + ctx * 4, tree_root(L, 2, t)); continue; }
     uint32_t same = ctx;
     for (uint32_t k = 0; k < ctx; k++) if (tr[k] == t && same == ctx) same = k;
-    const uint32_t dst_v = L.root[2] + (same << L.rbits[2]);
+    slot_of[ctx] = same != ctx ? slot_of[same] : used++;
+    const uint32_t dst_v = L.root[2] + (slot_of[ctx] << L.rbits[2]);
     sts32(c.slot + ctx * 4, dst_v);
     if (same != ctx) continue;
     const uint16_t* src = c.gtab + (L.dist_home - c.E) + (t << L.rbits[2]);
@@ -1135,12 +1155,25 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
   // long.  Typical shares of symbols with codes longer than R (per cent; text and binary corpora)
   // stand in for the streams' own statistics.  Jumps over several widths are considered at once (the saving per
   // entry is not monotonic: the first bits of a root save nothing).
-  // Distance-tree cache: a block type uses at most four distance trees (one per distance context), so when the
-  // metablock has more, the shared slot only holds four cache slots (see refresh_cur_dist) and the group is sized --
-  // and widened -- as four trees; all trees are built at their home in the arena.
-  const bool dist_cache = BD_LANE_DIST_CACHE && L.n_dist > 4;
+  // Distance-tree cache: a block type uses at most four distance trees (one per distance context) -- in practice one:
+  // the encoder's distance context maps send all four contexts of a block type to the same tree.  When the metablock
+  // has more trees than any block type uses, the shared slot only holds that many cache slots (see refresh_cur_dist)
+  // and the group is sized -- and widened -- accordingly; all trees are built at their home in the arena.
+  uint32_t dist_slots = 1;
+  for (uint32_t b = 0; b < L.nbt[2]; b++) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < 4; i++) {
+      bool seen = false;
+      for (uint32_t j = 0; j < i; j++) seen = seen || c.ctx_dist[4 * b + j] == c.ctx_dist[4 * b + i];
+      k += seen ? 0u : 1u;
+    }
+    if (k > dist_slots) dist_slots = k;
+  }
+  if (!BD_LANE_DIST_SLOTS_EXACT) dist_slots = 4;
+  L.dist_slots = dist_slots;
+  const bool dist_cache = BD_LANE_DIST_CACHE && L.n_dist > dist_slots;
   const uint32_t ntrees_all[3] = {L.n_lit, L.nbt[1], L.n_dist};
-  const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], dist_cache ? 4u : L.n_dist};
+  const uint32_t ntrees[3] = {L.n_lit, L.nbt[1], dist_cache ? dist_slots : L.n_dist};
   const uint32_t rmin[3] = {4, 4, 3}, rmax[3] = {8, 8, 7};
   const uint32_t alpha[3] = {256, 704, L.dist_alphabet};
   const uint32_t save_lo = L.lo, save_hi = L.hi, save_nx = L.nx, save_k = L.k, save_bp = L.bp, save_cold = L.cold_next;
@@ -1235,9 +1268,9 @@ BD_COLD int metablock_begin(const LaneCtx& c, Lane& L, BlockTrees& bt) {
       if (L.cold_next + sz > c.E + kGlobalTab) fits = false;
       else { L.dist_home = L.cold_next; L.cold_next += sz; }
     } else if (fits && dist_cache) {
-      // the whole group is in the arena after all: it was placed as four trees, it has n_dist
-      const uint32_t extra = (L.n_dist - 4u) << rb[2];
-      if (L.root[2] + (4u << rb[2]) != L.cold_next || L.cold_next + extra > c.E + kGlobalTab) fits = false;
+      // the whole group is in the arena after all: it was placed as dist_slots trees, it has n_dist
+      const uint32_t extra = (L.n_dist - dist_slots) << rb[2];
+      if (L.root[2] + (dist_slots << rb[2]) != L.cold_next || L.cold_next + extra > c.E + kGlobalTab) fits = false;
       else L.cold_next += extra;
     }
     // HuffmanTreeGroupDecode x3, :1130-1219
@@ -1447,7 +1480,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #if BD_LANE_L2_HINTS && !defined(BROTLI_B200_HOSTSIM)
   uint64_t pol_stream = l2_policy_stream(), pol_keep = l2_policy_keep();
   BD_PIN64(pol_stream); BD_PIN64(pol_keep);
-#if BD_LANE_L2_HINTS == 4
+#if BD_LANE_L2_HINTS == 4 || BD_LANE_L2_HINTS == 5
 #define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #else
 #define LN_CP16_IF_KEEP(COND, DST, SRC) cp_async16_if_hint(COND, DST, SRC, pol_keep)
@@ -1918,6 +1951,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           crem = copy_len;
           uint32_t ud = (uint32_t)dist;
           BD_LANE_DIST_STATS(ud, copy_len, false);
+#if BD_LANE_PROBE_NEAR == 1
+          if (pos >= 64) ud = 20u + (ud & 15u);   // (may share a 32-byte sector with the word being written: a partial sector)
+#elif BD_LANE_PROBE_NEAR == 2
+          if (pos >= 256) ud = 64u + (ud & 63u);  // whole sectors written two to sixteen rounds ago
+#endif
           if (kDict && ud > pos) {
             // the source starts in the custom dictionary, which logically precedes the output: a plain copy from the
             // dictionary's tail when it also ends there; a copy that runs on into the output is the exact kernel's
