@@ -91,6 +91,21 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #ifndef BD_LANE_PROBE_NEAR
 #define BD_LANE_PROBE_NEAR 0
 #endif
+// Phase A's literal words leave for global memory in phase P, behind the wait for the copy chunk: a global store issued
+// while the chunk's cp.async is still in flight holds the warp's memory pipeline until the chunk has landed (measured:
+// dropping either the stores or the chunk requests takes 24 % off the kernel, dropping both 28 %, and where the chunk
+// reads from does not matter), so phase A ran behind the chunk's latency instead of beside it.
+#ifndef BD_LANE_DEFER_A_STORES
+#define BD_LANE_DEFER_A_STORES 1
+#endif
+#ifndef BD_LANE_WAIT_ALL_AT_P
+#define BD_LANE_WAIT_ALL_AT_P 0
+#endif
+// MEASUREMENT ONLY (output is wrong; control flow of streams without literal contexts is unchanged): bit 0 drops the global
+// output stores, bit 1 the copy-source requests, bit 2 the history-ring mirror stores -- what do these instructions cost?
+#ifndef BD_LANE_PROBE_ABLATE
+#define BD_LANE_PROBE_ABLATE 0
+#endif
 // roots that live in the arena are looked up asynchronously as well (their root entry is requested a phase ahead)
 #ifndef BD_LANE_ASYNC_ARENA_ROOTS
 #define BD_LANE_ASYNC_ARENA_ROOTS 1
@@ -158,6 +173,7 @@ static inline uint32_t warp_count(bool p) { return p ? 32u : 0u; }  /* the one s
 #define BD_PIN32(x) ((void)0)
 #define BD_PIN64(x) ((void)0)
 static inline void ld32_if(bool cond, const uint8_t* p, uint32_t& dst) { if (cond) memcpy(&dst, p, 4); }
+static inline void probe_ldg16_if(bool, const void*) {}
 static inline void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) { if (cond) dst = *p; }
 // asynchronous 16-byte copy global -> "shared": immediate on the host
 static inline void cp_async16(hw::sref_t dst, const uint8_t* src) { memcpy((void*)dst, src, 16); }
@@ -188,7 +204,9 @@ BD_DEV uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }
 // modes: 0 no hints; 1 input / output / copy sources evict-first, table arena evict-last; 2 as 1, copy sources
 // without a hint; 3 as 1, output stores without a hint; 4 (default) as 1, table arena without a hint; 5 as 4, output
 // stores evict-LAST (does a lane's recent output stay in L2 for its short-distance copies?)
-#if BD_LANE_L2_HINTS == 5
+#if BD_LANE_PROBE_ABLATE & 1
+BD_DEV void st32(uint8_t*, uint32_t) {}
+#elif BD_LANE_L2_HINTS == 5
 // (not volatile, no inputs: the compiler keeps one copy of the policy per function)
 BD_DEV uint64_t l2_policy_keep_pure() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 BD_DEV void st32(uint8_t* p, uint32_t v) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_keep_pure()) : "memory"); }
@@ -199,10 +217,15 @@ BD_DEV void st32(uint8_t* p, uint32_t v) { *(uint32_t*)p = v; }
 #endif
 // predicated stores that stay predicated (no branch around a one-instruction body)
 BD_DEV void sts32_if(bool cond, hw::sref_t a, uint32_t v) {
+#if BD_LANE_PROBE_ABLATE & 4
+  return;
+#endif
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "r"(a), "r"(v) : "memory");
 }
 BD_DEV void st32_if(bool cond, uint8_t* p, uint32_t v) {
-#if BD_LANE_L2_HINTS == 5
+#if BD_LANE_PROBE_ABLATE & 1
+  (void)cond; (void)p; (void)v;
+#elif BD_LANE_L2_HINTS == 5
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.L2::cache_hint.u32 [%1], %2, %3;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v), "l"(l2_policy_keep_pure()) : "memory");
 #elif BD_LANE_L2_HINTS == 1 || BD_LANE_L2_HINTS == 2 || BD_LANE_L2_HINTS == 4
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}" ::"r"((uint32_t)cond), "l"(p), "r"(v) : "memory");
@@ -250,6 +273,10 @@ BD_DEV void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) {
 }
 #define BD_PIN32(x) asm volatile("" : "+r"(x))
 #define BD_PIN64(x) asm volatile("" : "+l"(x))
+// MEASUREMENT ONLY: a predicated 16-byte global load whose result is dropped (BD_LANE_PROBE_ABLATE bit 3)
+BD_DEV void probe_ldg16_if(bool cond, const void* p) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 a<4>;\n\tsetp.ne.u32 p, %0, 0;\n\t@p ld.global.cg.v4.u32 {a0, a1, a2, a3}, [%1];\n\t}" ::"r"((uint32_t)cond), "l"(p) : "memory");
+}
 BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 lanes take part
 BD_DEV uint32_t warp_count(bool p) { return __popc(__ballot_sync(0xffffffffu, p)); }
 #endif
@@ -454,6 +481,20 @@ BD_DEV void append(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& po
   acc = full ? funnelshift_rc(v, 0u, 32u - sh) : word;
   posb += n;
 }
+// As append(), but a completed word only goes to the history ring; its global store is left to the caller
+// (dw_pos: the word's position, 0xFFFFFFFF = none pending; a second completed word sends the first one off).
+BD_DEV void append_defer(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& posb, uint32_t& acc, uint32_t v, uint32_t n,
+                         uint32_t& dw_pos, uint32_t& dw_word) {
+  const uint32_t a = posb & 3u, sh = a * 8u;
+  const uint32_t word = acc | (v << sh);
+  const bool full = a + n >= 4;
+  sts32_if(full, hist + (posb & 28u), word);
+  if (BD_UNLIKELY(full && dw_pos != 0xFFFFFFFFu)) st32_if(dw_pos >= bias, out_al + dw_pos, dw_word);
+  dw_pos = full ? posb & ~3u : dw_pos;
+  dw_word = full ? word : dw_word;
+  acc = full ? funnelshift_rc(v, 0u, 32u - sh) : word;
+  posb += n;
+}
 // v_hi:v_lo holds exactly n (1..8) valid low bytes, the rest is zero
 BD_DEV void append8(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& posb, uint32_t& acc, uint32_t v_lo, uint32_t v_hi, uint32_t n) {
   const uint32_t a = posb & 3u, sh = a * 8u, wpos = posb & ~3u;
@@ -461,9 +502,14 @@ BD_DEV void append8(uint8_t* out_al, uint32_t bias, hw::sref_t hist, uint32_t& p
   const uint32_t x1 = funnelshift_l(v_lo, v_hi, sh);
   const uint32_t t = a + n;
   const bool s0 = t >= 4, s1 = t >= 8;
+#if BD_LANE_PROBE_ABLATE & 16
+  sts32_if(s0, hist + (wpos & 28u), x0);
+  sts32_if(s1, hist + ((wpos + 4) & 28u), x1);
+#else
   store_word_if(s0, out_al, bias, hist, wpos, x0);
   sts32_if(s1, hist + ((wpos + 4) & 28u), x1);
   st32_if(s1, out_al + wpos + 4, x1);
+#endif
   acc = s1 ? funnelshift_rc(v_hi, 0u, 32u - sh) : (s0 ? x1 : x0);
   posb += n;
 }
@@ -1497,6 +1543,13 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #define LN_CP16_IF_SRC(COND, DST, SRC) cp_async16_if(COND, DST, SRC)
 #endif
 #define LN_PEEK() hw::funnelshift_r(lo, hi, bp)
+#if BD_LANE_DEFER_A_STORES
+#define LN_APPEND_A(V) append_defer(out_al, bias, hist, posb, acc, (V), 1, dw_pos, dw_word)
+#define LN_FLUSH_A() do { st32_if(!(BD_LANE_PROBE_ABLATE & 32) && dw_pos != 0xFFFFFFFFu && dw_pos >= bias, out_al + dw_pos, dw_word); dw_pos = 0xFFFFFFFFu; } while (0)
+#else
+#define LN_APPEND_A(V) append(out_al, bias, hist, posb, acc, (V), 1)
+#define LN_FLUSH_A() ((void)0)
+#endif
 #if BD_LANE_HEAD_PER_ROUND
 // the region's first word was completed since position P0 (fewer than 32 bytes ago: it is still in the history ring)
 #define LN_HEAD_CHECK(P0) do { if (BD_UNLIKELY(bias != 0 && (P0) < 4 && posb >= 4)) store_head_bytes(out_al, bias, 0, vlds32(hist)); } while (0)
@@ -1606,8 +1659,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool iss_ = (ISS);                                               \
     const uint32_t nn_ = crem < 16 ? crem : 16u;                           \
     const uint32_t off_ = (uint32_t)(uintptr_t)csrc & 15u;                 \
-    LN_CP16_IF_SRC(iss_, stage, csrc - off_);                              \
-    LN_CP16_IF_SRC(iss_ && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
+    LN_CP16_IF_SRC(iss_ && !(BD_LANE_PROBE_ABLATE & 2), stage, csrc - off_);                              \
+    LN_CP16_IF_SRC(iss_ && !(BD_LANE_PROBE_ABLATE & 2) && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
+    if (BD_LANE_PROBE_ABLATE & 8) { probe_ldg16_if(iss_, csrc - off_); probe_ldg16_if(iss_ && off_ + nn_ > 16, csrc - off_ + 16); } \
     if (iss_) { pend_n = nn_; pend_off = off_; crem -= nn_; csrc += 16; }  \
   } while (0)
 // append the chunk in flight to the output
@@ -1686,6 +1740,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const uint32_t posb0 = posb;
 #endif
     uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
+    uint32_t dw_pos = 0xFFFFFFFFu, dw_word = 0;  // output word completed by phase A's literals, stored in phase P (BD_LANE_DEFER_A_STORES)
     // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
     cp_async_wait_all_but_latest();
 #ifdef BD_LANE_ROUND_STATS
@@ -1719,7 +1774,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         uint32_t nskip = len;
         if (is_lit) {
           bl_l--;
-          append(out_al, bias, hist, posb, acc, sym, 1);
+          LN_APPEND_A(sym);
           p2 = p1; p1 = sym;
           --ins;
           // Further literals of the run in the same round while they cost no trip to the arena: one tree for all
@@ -1731,7 +1786,7 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
               const uint32_t e2 = vlds16(stab + ((v2 < E ? v2 : 0u) << 1));
               if (v2 >= E || (e2 & 15u) > r_lit) break;
               bl_l--;
-              append(out_al, bias, hist, posb, acc, e2 >> 4, 1);
+              LN_APPEND_A(e2 >> 4);
               --ins;
               nskip += e2 & 15u;
             }
@@ -1827,7 +1882,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     cp_async_commit();  // group: what phase A requested (distance look-ahead)
 
     // ---- phase P: retire the copy chunk requested at the end of the previous round ----
+#if BD_LANE_WAIT_ALL_AT_P
+    cp_async_wait_all();  // experiment: nothing in flight while phase P stores
+#else
     cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
+#endif
+    LN_FLUSH_A();  // (dw_pos is only ever set by a running lane)
     if (run && pend_n != 0) LN_RETIRE_CHUNK();
     if (kCmdLiterals != 0 && run) {  // literals decoded in their command's round (phase A); nothing happens for lit_n == 0
       append(out_al, bias, hist, posb, acc, lit_pack, lit_n);
@@ -1955,6 +2015,14 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
           if (pos >= 64) ud = 20u + (ud & 15u);   // (may share a 32-byte sector with the word being written: a partial sector)
 #elif BD_LANE_PROBE_NEAR == 2
           if (pos >= 256) ud = 64u + (ud & 63u);  // whole sectors written two to sixteen rounds ago
+#elif BD_LANE_PROBE_NEAR == 3
+          if (pos >= 1024) ud = 256u + (ud & 255u);
+#elif BD_LANE_PROBE_NEAR == 4
+          if (pos >= 4096) ud = 1024u + (ud & 1023u);
+#elif BD_LANE_PROBE_NEAR == 5
+          if (pos >= 16384) ud = 4096u + (ud & 4095u);
+#elif BD_LANE_PROBE_NEAR == 6
+          if (ud < 4096 && pos >= 8192) ud += 4096u;  // no copy reads anything written in the last 4 KiB
 #endif
           if (kDict && ud > pos) {
             // the source starts in the custom dictionary, which logically precedes the output: a plain copy from the
@@ -2026,6 +2094,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   cp_async_wait_all();  // input blocks requested in the last round: the per-metablock code reads the ring right away
   if (ran) LN_SAVE();
 #undef LN_PEEK
+#undef LN_APPEND_A
+#undef LN_FLUSH_A
 #undef LN_HEAD_CHECK
 #undef LN_CP16_IF_KEEP
 #undef LN_CP16_IF_STREAM
