@@ -41,7 +41,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) brotli_decode_lane_kernel(Batch
   c.ring = hw::to_sref(s_dyn + (size_t)threadIdx.x * 16);
   c.ring_stride = WARPS * 32 * 16;
   c.hist = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 32 + (size_t)threadIdx.x * 32);  // 32-byte output history ring
-  c.stage = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 64 + (size_t)threadIdx.x * 64);  // cp.async landing zone
+  // cp.async landing zones: 48 bytes per lane (copy source, next phase-A entry) at a stride that spreads a warp's 16-byte
+  // writes over all banks, then the 16-byte blocks of the next phase-C entry
+  c.stage = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 64 + (size_t)threadIdx.x * 48);
+  c.stage_c = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 112 + (size_t)threadIdx.x * 16);
   c.slot = hw::to_sref(s_dyn + (size_t)WARPS * 32 * 128 + (size_t)threadIdx.x * la.slot_bytes);
   c.stab = c.slot + lane::kSlotHeaderBytes;
   c.E = (la.slot_bytes - lane::kSlotHeaderBytes) / 2;

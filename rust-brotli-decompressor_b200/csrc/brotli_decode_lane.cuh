@@ -101,6 +101,21 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #ifndef BD_LANE_WAIT_ALL_AT_P
 #define BD_LANE_WAIT_ALL_AT_P 0
 #endif
+// The copy chunk requested at the end of a round is retired (phase P) behind phase C1 and the next-A look-ahead of the
+// next round instead of right behind phase A: it has ~60 % of a round to arrive instead of ~40 %.  cp.async groups
+// complete in order, so nothing younger than the chunk may be waited for before phase P: the distance look-ahead of
+// phase A becomes a plain (predicated, top-level) global load into a register, tracked by its own scoreboard.
+#ifndef BD_LANE_LATE_RETIRE
+#define BD_LANE_LATE_RETIRE 0
+#endif
+// Look-ahead entries loaded into a register (predicated ld.global at the top level of the round, own scoreboard) instead of
+// cp.async into the staging area: 1 the distance symbol's, 2 the next phase-A symbol's as well.  Fewer cp.async requests
+// share the path into shared memory with the copy chunks.
+#ifndef BD_LANE_LA_REG
+#define BD_LANE_LA_REG 0
+#endif
+#define BD_LANE_DIST_LA_REG (BD_LANE_LATE_RETIRE || BD_LANE_LA_REG >= 1)
+#define BD_LANE_NEXT_LA_REG (BD_LANE_LA_REG >= 2)
 // MEASUREMENT ONLY (output is wrong; control flow of streams without literal contexts is unchanged): bit 0 drops the global
 // output stores, bit 1 the copy-source requests, bit 2 the history-ring mirror stores -- what do these instructions cost?
 #ifndef BD_LANE_PROBE_ABLATE
@@ -308,6 +323,9 @@ struct LaneCtx {
   uint8_t* ctx_dist;
   uint8_t* ctx_modes;
   hw::sref_t hist;       // shared: 32-byte ring mirroring this lane's most recent output words
+  hw::sref_t stage_c;    // shared, 16-byte aligned: the block holding the second-level table entry of the next phase-C symbol (its
+                         // own array, 16 bytes per lane: with stage at a 48-byte stride a warp's 16-byte cp.async writes are free
+                         // of bank conflicts; at 64 bytes per lane sixteen lanes shared each bank group)
   hw::sref_t stage;      // shared, 16-byte aligned: [0..31] two 16-byte blocks of copy source, [32..47] / [48..63] the
                          // block holding the second-level table entry of the next phase-A / phase-C symbol
   hw::sref_t ring;       // shared: this lane's first 16-byte input block buffer; the second one is ring_stride further
@@ -558,6 +576,7 @@ BD_DEV uint32_t bit_width(uint32_t x) { uint32_t r = 0; while (x) { x >>= 1; r++
 // [0..31] count[16] (u16: symbols per code length), [32..63] first the 5-bit lookup of the code-length code (u8[32]),
 // then next_code[16] (u16: the next canonical code of each length).  Local memory only holds the code lengths
 // themselves (one byte per symbol, read back four at a time): every access there is an L2 round trip.
+#error "BD_LANE_HEADER_V2 keeps 64 bytes of temporaries in c.stage, which is 48 bytes per lane now"
 BD_DEV hw::sref_t tmp_count(const LaneCtx& c, uint32_t l) { return c.stage + 2u * l; }
 BD_DEV hw::sref_t tmp_next(const LaneCtx& c, uint32_t l) { return c.stage + 32u + 2u * l; }
 
@@ -1480,6 +1499,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   const uint8_t* xdict = c.xdict;
   hw::sref_t hist = c.hist, stage = c.stage;
 #if defined(BROTLI_B200_HOSTSIM)
+  const hw::sref_t stage_c = c.stage_c;
+#else
+  const hw::sref_t stage_c = ring + kStride * 7u;  // (ring = dynamic shared memory + 16 x thread; see the kernel's layout)
+#endif
+#define LN_STAGE(SLOT) ((SLOT) == 48u ? stage_c : stage + (SLOT))
+#if defined(BROTLI_B200_HOSTSIM)
   const hw::sref_t cmd_lut = c.cmd_lut, word_info = c.word_info, transform_info = c.transform_info, ctx_lut_base = c.ctx_lut;
 #else
   const hw::sref_t cmd_lut = hw::to_sref(g_cmd_lut), word_info = hw::to_sref(g_word_info), transform_info = hw::to_sref(g_transform_info);
@@ -1709,15 +1734,44 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool ar_ = kArena && !in_;  /* root in the arena: request the root entry */            \
     const uint32_t i2_ = ar_ ? v_ - E : ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);  \
     BD_LANE_LA_STATS(SLOT, in_, two_);                                                           \
-    LN_CP16_IF_KEEP(two_ || ar_, stage + (SLOT), gtab + (i2_ & ~7u));                            \
+    LN_CP16_IF_KEEP(two_ || ar_, LN_STAGE(SLOT), gtab + (i2_ & ~7u));                            \
     PV = kArena || in_; PE = ar_ ? 0xC0000000u : (two_ ? 0x80000000u : e_); PSEL = (two_ || ar_) ? (i2_ & 7u) << 1 : PSEL; \
   } while (0)
 // entry of a looked-ahead symbol (its group has been waited for)
 #define LN_TAKE(SLOT, PV, PE, PSEL, TR, BITS, LEN, SYM)                                          \
   do {                                                                                           \
     BITS = LN_PEEK();                                                                            \
-    const uint32_t es_ = vlds16(stage + (SLOT) + PSEL);  /* unconditional: no branch */          \
+    const uint32_t es_ = vlds16(LN_STAGE(SLOT) + PSEL);  /* unconditional: no branch */          \
     uint32_t e_ = (PE & 0x80000000u) ? es_ : PE;                                                 \
+    if (kArena && BD_UNLIKELY((PE & 0x40000000u) != 0 && (e_ & 15u) > (TR))) {  /* arena root, long code */ \
+      BD_LANE_COUNT(9);                                                                          \
+      e_ = gtab[((e_ >> 4) << 2) + low_bits(BITS >> (TR), (e_ & 15u) - (TR))];                   \
+    }                                                                                            \
+    PV = false;                                                                                  \
+    LEN = e_ & 15u; SYM = e_ >> 4;                                                               \
+  } while (0)
+
+  // The same look-ahead with the entry loaded into a register: the root look-up happens here (inside phase A's branch),
+  // the load itself (PIDX: arena index, PNEED) is issued by LN_LOOKAHEAD_REG_LOAD at the top level of the round -- a
+  // load issued inside a branch is waited for where the branch rejoins.
+#define LN_LOOKAHEAD_REG(TV, TR, PV, PE, PIDX, PNEED)                                            \
+  do {                                                                                           \
+    const uint32_t bits_ = LN_PEEK();                                                            \
+    const uint32_t v_ = (TV) + low_bits(bits_, TR);                                              \
+    const bool in_ = v_ < E;                                                                     \
+    const uint32_t e_ = vlds16(stab + ((in_ ? v_ : 0u) << 1));                                   \
+    const bool two_ = in_ && (e_ & 15u) > (TR);                                                  \
+    const uint32_t sub_ = two_ ? (e_ & 15u) - (TR) : 0u;                                         \
+    const bool ar_ = kArena && !in_;                                                             \
+    PIDX = ar_ ? v_ - E : ((e_ >> 4) << 2) + low_bits(bits_ >> (TR), sub_);                      \
+    BD_LANE_LA_STATS(48u, in_, two_);                                                            \
+    PNEED = two_ || ar_;                                                                         \
+    PV = kArena || in_; PE = ar_ ? 0xC0000000u : (two_ ? 0x80000000u : e_);                      \
+  } while (0)
+#define LN_TAKE_REG(PLD, PV, PE, TR, BITS, LEN, SYM)                                             \
+  do {                                                                                           \
+    BITS = LN_PEEK();                                                                            \
+    uint32_t e_ = (PE & 0x80000000u) ? PLD : PE;                                                 \
     if (kArena && BD_UNLIKELY((PE & 0x40000000u) != 0 && (e_ & 15u) > (TR))) {  /* arena root, long code */ \
       BD_LANE_COUNT(9);                                                                          \
       e_ = gtab[((e_ >> 4) << 2) + low_bits(BITS >> (TR), (e_ & 15u) - (TR))];                   \
@@ -1729,6 +1783,12 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   // look-ahead state: pa_* for the symbol phase A will decode next, pc_* for the distance symbol of phase C
   bool pa_valid = false, pc_valid = false;
   uint32_t pa_e = 0, pa_sel = 0, pc_e = 0, pc_sel = 0;
+#if BD_LANE_DIST_LA_REG
+  uint32_t pc_ld = 0;  // second-level (or arena root) entry of the distance symbol, loaded by phase A's look-ahead
+#endif
+#if BD_LANE_NEXT_LA_REG
+  uint32_t pa_ld = 0;  // the same for the next phase-A symbol
+#endif
 
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
@@ -1741,6 +1801,14 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #endif
     uint32_t lit_pack = 0, lit_n = 0;  // literals decoded in phase A of their command's round, appended in phase P
     uint32_t dw_pos = 0xFFFFFFFFu, dw_word = 0;  // output word completed by phase A's literals, stored in phase P (BD_LANE_DEFER_A_STORES)
+#if BD_LANE_DIST_LA_REG
+    uint32_t pc_idx = 0;    // arena index of the entry the distance look-ahead loads
+    bool pc_need = false;
+#endif
+#if BD_LANE_NEXT_LA_REG
+    uint32_t pa_idx = 0;
+    bool pa_need = false;
+#endif
     // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
     cp_async_wait_all_but_latest();
 #ifdef BD_LANE_ROUND_STATS
@@ -1756,7 +1824,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (ev == kStCommands) {
         uint32_t bits, len, sym;
         if (BD_LIKELY(pa_valid)) {
+#if BD_LANE_NEXT_LA_REG
+          LN_TAKE_REG(pa_ld, pa_valid, pa_e, (is_lit ? r_lit : r_cmd), bits, len, sym);
+#else
           LN_TAKE(32u, pa_valid, pa_e, pa_sel, (is_lit ? r_lit : r_cmd), bits, len, sym);
+#endif
         } else {
           uint32_t tv = is_lit ? lit_tv : cmd_tv;
           const uint32_t tr = is_lit ? r_lit : r_cmd;
@@ -1845,7 +1917,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
         // look ahead for the distance symbol this lane decodes in phase C of this round
         if (ph == kPhDist && ev == kStCommands && !(cmd_bits & (1u << 26)) && bl_d != 0) {
           const uint32_t tvd = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
+#if BD_LANE_DIST_LA_REG
+          LN_LOOKAHEAD_REG(tvd, r_dist, pc_valid, pc_e, pc_idx, pc_need);
+#else
           LN_LOOKAHEAD(tvd, r_dist, 48u, pc_valid, pc_e, pc_sel);
+#endif
         }
       }
     }
@@ -1879,26 +1955,33 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       }
     }
     warp_sync();
-    cp_async_commit();  // group: what phase A requested (distance look-ahead)
-
     // ---- phase P: retire the copy chunk requested at the end of the previous round ----
+#define LN_PHASE_P()                                                                                       \
+  do {                                                                                                     \
+    LN_FLUSH_A();  /* (dw_pos is only ever set by a running lane) */                                       \
+    if (run && pend_n != 0) LN_RETIRE_CHUNK();                                                             \
+    if (kCmdLiterals != 0 && run) {  /* literals decoded in their command's round (phase A) */             \
+      append(out_al, bias, hist, posb, acc, lit_pack, lit_n);                                              \
+    }                                                                                                      \
+    if (BD_LANE_HEAD_PER_ROUND && run) LN_HEAD_CHECK(posb0);  /* phases A and P append at most 19 bytes */ \
+    /* overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business */     \
+    if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;                   \
+  } while (0)
+#if BD_LANE_DIST_LA_REG
+    // the distance look-ahead's load, at the top level of the round (see LN_LOOKAHEAD_REG)
+    ld16_if(pc_need, gtab + pc_idx, pc_ld);
+#endif
+#if !BD_LANE_LATE_RETIRE
+    cp_async_commit();  // group: what phase A requested (distance look-ahead, input blocks)
 #if BD_LANE_WAIT_ALL_AT_P
     cp_async_wait_all();  // experiment: nothing in flight while phase P stores
 #else
     cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
 #endif
-    LN_FLUSH_A();  // (dw_pos is only ever set by a running lane)
-    if (run && pend_n != 0) LN_RETIRE_CHUNK();
-    if (kCmdLiterals != 0 && run) {  // literals decoded in their command's round (phase A); nothing happens for lit_n == 0
-      append(out_al, bias, hist, posb, acc, lit_pack, lit_n);
-    }
-#if BD_LANE_HEAD_PER_ROUND
-    if (run) LN_HEAD_CHECK(posb0);  // phases A and P append at most 19 bytes
-#endif
-    // overshooting the metablock (BLOCK_LENGTH) or the output region: the exact decoder's business
-    if (run && ph == kPhLit && BD_UNLIKELY(mlen < 0 || ins > capb - posb)) ev = kStBail;
+    LN_PHASE_P();
     warp_sync();
     cp_async_wait_all();  // the distance look-ahead
+#endif
 
     // ---- phase C1: distance symbol (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049) ----
     int32_t dist = d0;
@@ -1909,7 +1992,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
       if (ev == kStCommands) {
         uint32_t bits, len, sym;
         if (BD_LIKELY(pc_valid)) {
+#if BD_LANE_DIST_LA_REG
+          LN_TAKE_REG(pc_ld, pc_valid, pc_e, r_dist, bits, len, sym);
+#else
           LN_TAKE(48u, pc_valid, pc_e, pc_sel, r_dist, bits, len, sym);
+#endif
         } else {
           const uint32_t tv = vlds32(slot + ((cmd_bits >> 24) & 3u) * 4u);
           BD_LANE_COUNT(7);
@@ -1955,19 +2042,32 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     if (run && !pa_valid && ev == kStCommands) {
       const bool next_cmd = go || ph == kPhCmd;
       const bool next_lit = ph == kPhLit;
-      if (next_cmd ? bl_c != 0 : (next_lit && bl_l != 0)) {
+      // (late retire: the literal context of a lane whose copy chunk is still to be appended is not known yet)
+      if ((next_cmd ? bl_c != 0 : (next_lit && bl_l != 0)) && !(BD_LANE_LATE_RETIRE && !next_cmd && !trivial && pend_n != 0)) {
         uint32_t tv = next_cmd ? cmd_tv : lit_tv;
         if (!next_cmd && !trivial) {  // tree by the context of the last two bytes (:2500-2507); phase P is over
           if (!ctx_fresh) { last_two(hist, bias, posb, acc, p1, p2); ctx_fresh = true; if (kDict && posb - bias < 2) { p1 = 0; p2 = 0; } }
           const uint32_t cx = vlds8(ctx_lut + p1) | vlds8(ctx_lut + 256 + p2);
           tv = root_lit + (vlds8(ctx_map + cx) << r_lit);
         }
+#if BD_LANE_NEXT_LA_REG
+        LN_LOOKAHEAD_REG(tv, next_cmd ? r_cmd : r_lit, pa_valid, pa_e, pa_idx, pa_need);
+#else
         LN_LOOKAHEAD(tv, next_cmd ? r_cmd : r_lit, 32u, pa_valid, pa_e, pa_sel);
+#endif
       }
     }
+#if BD_LANE_NEXT_LA_REG
+    ld16_if(pa_need, gtab + pa_idx, pa_ld);
+#endif
     LN_INPUT_BLOCK(run);
     warp_sync();
     cp_async_commit();  // group: next-A look-ahead and the round's input block
+#if BD_LANE_LATE_RETIRE
+    cp_async_wait_all_but_latest();  // the chunk (and everything older); the group just committed stays in flight
+    LN_PHASE_P();
+    warp_sync();
+#endif
 
     // ---- phase C2: the copy or static dictionary word (:2583-2689); its source bytes are requested below ----
     if (go && ev == kStCommands) {
@@ -2095,6 +2195,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   if (ran) LN_SAVE();
 #undef LN_PEEK
 #undef LN_APPEND_A
+#undef LN_STAGE
+#undef LN_PHASE_P
+#undef LN_LOOKAHEAD_REG
+#undef LN_TAKE_REG
 #undef LN_FLUSH_A
 #undef LN_HEAD_CHECK
 #undef LN_CP16_IF_KEEP

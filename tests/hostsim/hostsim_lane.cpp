@@ -39,6 +39,7 @@ extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8
   alignas(16) static uint8_t stage[64];
   c.hist = hw::to_sref(hist);
   c.stage = hw::to_sref(stage);
+  c.stage_c = hw::to_sref(stage + 48);
   c.ring = hw::to_sref(ring);
   c.ring_stride = 16;
   std::vector<uint8_t> padded(in_size + 64 + 16);
