@@ -66,6 +66,27 @@ constexpr uint32_t kMaxExtraLiterals = BD_LANE_EXTRA_LITERALS;  // literals a la
 #define BD_LANE_CMD_LITERALS 0
 #endif
 constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may decode in the round of their command
+// Latency configuration: the small geometries (at most 12 warps per SM) only run batches below one wave of lanes, where
+// the batch takes as long as one stream takes on its lane (rounds x the round's dependent chain) and issue slots are idle:
+// there, more work per round is what counts, not fewer instructions per round -- more literals per literal round, and a
+// command's first literals in the command's own round.
+#ifndef BD_LANE_EXTRA_LITERALS_LAT
+#define BD_LANE_EXTRA_LITERALS_LAT 4
+#endif
+#ifndef BD_LANE_CMD_LITERALS_LAT
+#define BD_LANE_CMD_LITERALS_LAT 3
+#endif
+#ifndef BD_LANE_BURST_LAT
+#define BD_LANE_BURST_LAT 0   /* literal bursts (see kBurst) in the latency configuration */
+#endif
+#ifndef BD_LANE_BURST_LANES_LAT
+#define BD_LANE_BURST_LANES_LAT 6
+#endif
+#if defined(BROTLI_B200_HOSTSIM)
+#define BD_LANE_IS_LATENCY_STRIDE(s) ((s) == 32u)  /* the host build's second instance (tests/hostsim) */
+#else
+#define BD_LANE_IS_LATENCY_STRIDE(s) ((s) <= 12u * 32u * 16u)
+#endif
 // Literal bursts: while at least kBurstLanes lanes of the warp are inside a literal run, up to kBurst extra literal-only
 // iterations follow phase A (table look-ups synchronous, nothing else of the round issued).  A round costs ~650
 // instructions whatever its lanes do; a burst iteration ~60, so literal-heavy streams (binary data, 4 KiB responses)
@@ -1475,6 +1496,12 @@ enum : uint32_t { kPhCmd = 0, kPhLit = 1, kPhDist = 2, kPhCopy = 3 };  // what a
 // kDict: the batch has a custom LZ77 dictionary (a separate kernel instance, so that streams without one pay nothing).
 template <uint32_t kStride, bool kDict, bool kArena>
 BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool run, uint32_t& st) {
+  // (these shadow the namespace-scope defaults: see the latency configuration)
+  constexpr bool kLatency = BD_LANE_IS_LATENCY_STRIDE(kStride);
+  constexpr uint32_t kMaxExtraLiterals = kLatency ? BD_LANE_EXTRA_LITERALS_LAT : BD_LANE_EXTRA_LITERALS;
+  constexpr uint32_t kCmdLiterals = kLatency ? BD_LANE_CMD_LITERALS_LAT : BD_LANE_CMD_LITERALS;
+  constexpr uint32_t kBurst = kLatency ? BD_LANE_BURST_LAT : BD_LANE_BURST;
+  constexpr uint32_t kBurstLanes = kLatency ? BD_LANE_BURST_LANES_LAT : BD_LANE_BURST_LANES;
   // register copies of the hot state
   const uint8_t* gin = nullptr;
   uint32_t lo = 0, hi = 0, nx = 0, k = 0, bp = 0, k_max = 0, last_blk = 0;

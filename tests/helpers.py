@@ -165,6 +165,8 @@ class HostSim:
         L.hostsim_stream_calls.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 10
         L.hostsim_stream_stats.restype = None
         L.hostsim_stream_stats.argtypes = [ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint64)]
+        L.hostsim_lane_set_latency_config.restype = None
+        L.hostsim_lane_set_latency_config.argtypes = [ctypes.c_int]
         L.hostsim_lane_decode.restype = ctypes.c_int
         L.hostsim_lane_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]

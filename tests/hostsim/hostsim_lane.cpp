@@ -16,6 +16,9 @@ extern "C" int hostsim_lane_decode(const uint8_t* in, size_t in_size, uint8_t* o
                                    uint64_t* used) {
   return hostsim_lane_decode_dict(in, in_size, out, cap, table_entries, decoded, used, nullptr, 0);
 }
+// 0: the throughput configuration of the command loop (what the large geometries run), 1: the latency configuration of the small ones
+static int g_latency_config = 0;
+extern "C" void hostsim_lane_set_latency_config(int on) { g_latency_config = on; }
 extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8_t* out, size_t cap, uint32_t table_entries, uint64_t* decoded,
                                         uint64_t* used, const uint8_t* dict, size_t dict_size) {
   using namespace brotli_b200;
@@ -34,14 +37,14 @@ extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8
   c.ctx_modes = a + lane::ArenaLayout::kCtxModes;
   // two 16-byte input blocks; the device copies whole aligned blocks, so give the stream padding on both sides
   // while keeping its address modulo 16
-  alignas(16) static uint8_t ring[32];
+  alignas(16) static uint8_t ring[48];  // blocks at +0 and +16 (stride 16) or +0 and +32 (stride 32: the latency instance)
   alignas(16) static uint8_t hist[32];
   alignas(16) static uint8_t stage[64];
   c.hist = hw::to_sref(hist);
   c.stage = hw::to_sref(stage);
   c.stage_c = hw::to_sref(stage + 48);
   c.ring = hw::to_sref(ring);
-  c.ring_stride = 16;
+  c.ring_stride = g_latency_config ? 32 : 16;
   std::vector<uint8_t> padded(in_size + 64 + 16);
   uint8_t* pin = padded.data() + 32;
   pin += (((uintptr_t)in & 15u) - ((uintptr_t)pin & 15u)) & 15u;
@@ -75,8 +78,10 @@ extern "C" int hostsim_lane_decode_dict(const uint8_t* in, size_t in_size, uint8
   if (dict_size) memcpy(dict_padded.data() + 32, dict, dict_size);
   c.cdict = dict_padded.data() + 32;
   c.cdict_len = dict_size;
-  const uint32_t r = dict_size ? lane::decode_streams<16, true>(c, true, in, in_size, out, cap, &d, &u)
-                               : lane::decode_streams<16, false>(c, true, in, in_size, out, cap, &d, &u);
+  const uint32_t r = g_latency_config ? (dict_size ? lane::decode_streams<32, true>(c, true, in, in_size, out, cap, &d, &u)
+                                                   : lane::decode_streams<32, false>(c, true, in, in_size, out, cap, &d, &u))
+                                      : (dict_size ? lane::decode_streams<16, true>(c, true, in, in_size, out, cap, &d, &u)
+                                                   : lane::decode_streams<16, false>(c, true, in, in_size, out, cap, &d, &u));
   *decoded = d;
   if (used) *used = u;
   return r == lane::kStDone ? 1 : 1000;

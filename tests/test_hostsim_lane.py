@@ -17,6 +17,15 @@ MUST_DECODE = ["alice29.txt.compressed", "asyoulik.txt.compressed", "lcet10.txt.
                "mapsdatazrh.compressed", "quickfox_repeated.compressed", "zeros.compressed"]
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["throughput", "latency"])
+def lane_config(request, hostsim):
+    """Both configurations of the command loop: what the large geometries run, and the latency configuration of the small ones
+    (more literals per round; BD_LANE_*_LAT in csrc/brotli_decode_lane.cuh)."""
+    hostsim.lib.hostsim_lane_set_latency_config(request.param)
+    yield
+    hostsim.lib.hostsim_lane_set_latency_config(0)
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_fixture(hostsim, name):
     e = MAN[name]
