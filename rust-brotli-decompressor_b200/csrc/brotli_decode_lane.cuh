@@ -150,6 +150,11 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #define BD_LANE_ARENA_LANES 2  /* lanes of a warp with a tree group in the arena from which the warp takes that loop instance */
 #endif
 // per-metablock table construction without the sort arrays (temporaries in the shared staging area)
+// per-metablock table construction with its small temporaries (count[], the code-length lookup, offs[]) in the shared
+// landing zones and the bit window in registers; length-ordered fill as before (0: everything in local memory)
+#ifndef BD_LANE_HEADER_SMEM
+#define BD_LANE_HEADER_SMEM 1
+#endif
 #ifndef BD_LANE_HEADER_V2
 #define BD_LANE_HEADER_V2 0
 #endif
@@ -798,6 +803,204 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
 }
 
 #else
+#if BD_LANE_HEADER_SMEM
+// ---- prefix-code tables from code lengths, length-ordered fill, small temporaries in shared memory ----
+// The lane's cp.async landing zones are idle outside the command loop: c.stage[0..31] holds count[16] (u16: symbols per
+// code length); the 32 bytes made of c.stage[32..47] and c.stage_c[0..15] hold first the 5-bit lookup of the code-length
+// code (u8[32]) and then offs[16] (u16: where the next symbol of each length goes in sorted[]).  Local memory keeps the
+// two big arrays (code length per symbol, symbols sorted by length); every access there is an L2 round trip, and the
+// small arrays used to be indexed dynamically, i.e. lived there too.  The bit window is a register copy (BitWin).
+BD_DEV hw::sref_t hc_count(const LaneCtx& c, uint32_t l) { return c.stage + 2u * l; }
+BD_DEV hw::sref_t hc_tmp(const LaneCtx& c, uint32_t b) { return b < 16u ? c.stage + 32u + b : c.stage_c + (b - 16u); }
+
+// Fill the lookup structure of one prefix code from its symbols sorted by (length, value); count[] in shared memory.
+// Root of 2^rbits entries at root_v; longer codes go to second-level tables allocated from cold_next (always in the
+// arena).  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
+BD_DEV int fill_table(const LaneCtx& c, uint32_t& cold_next, const uint32_t* sorted_w, uint32_t root_v, uint32_t rbits) {
+  uint32_t code = 0, idx = 0;
+  uint32_t pair = 0;  // sorted[] is read two symbols per (local-memory) load
+  uint32_t cur_prefix = 0xFFFFFFFFu, sub_w = 0, sub_v = 0;
+  for (uint32_t l = 1; l <= 15; l++) {
+    for (uint32_t j = vlds16(hc_count(c, l)); j != 0; j--) {
+      if ((idx & 1u) == 0) pair = sorted_w[idx >> 1];
+      const uint32_t sym = (idx & 1u) ? pair >> 16 : pair & 0xFFFFu;
+      idx++;
+      const uint32_t rev = hw::brev(code) >> (32 - l);
+      const uint32_t e = (sym << 4) | l;
+      if (l <= rbits) {
+        for (uint32_t t = rev; t < (1u << rbits); t += 1u << l) tab_store(c, root_v + t, e);
+      } else {
+        const uint32_t prefix = code >> (l - rbits);
+        if (prefix != cur_prefix) {  // first code under a new root slot: size its second-level table (NextTableBitSize, :181-193)
+          cur_prefix = prefix;
+          // symbols not yet placed: j of length l (this one included), all of every longer length
+          int32_t left = (1 << (l - rbits)) - (int32_t)j;
+          uint32_t ll = l;
+          while (ll < 15 && left > 0) {
+            ll++; left <<= 1;
+            if (ll < 15) left -= (int32_t)vlds16(hc_count(c, ll));
+          }
+          sub_w = ll - rbits;
+          sub_v = cold_next - c.E;  // index into the arena part
+          const uint32_t sub_size = sub_w < 2 ? 4u : 1u << sub_w;  // every arena allocation is a multiple of four entries
+          if (sub_v + sub_size > kGlobalTab) return kLaneBail;
+          cold_next += sub_size;
+          tab_store(c, root_v + (rev & mask_bits(rbits)), ((sub_v >> 2) << 4) | (rbits + sub_w));
+        }
+        for (uint32_t t = rev >> rbits; t < (1u << sub_w); t += 1u << (l - rbits)) c.gtab[sub_v + t] = (uint16_t)e;
+      }
+      code++;
+    }
+    code <<= 1;
+  }
+  return kLaneOk;
+}
+
+// ReadHuffmanCode, src/decode.rs:868-1013: one prefix-code description -> lookup structure.
+BD_DEV int read_huffman_code_impl(const LaneCtx& c, BitWin& L, uint32_t& cold_next, uint32_t alphabet_size, uint32_t max_symbol,
+                                  uint32_t root_v, uint32_t rbits) {
+  uint32_t sorted_w[352];  // u16 sorted[704]: symbols by (length, value)
+  uint16_t* const sorted = (uint16_t*)sorted_w;
+  for (uint32_t l = 0; l < 16; l += 2) sts32(hc_count(c, l), 0u);
+  const uint32_t hskip = L.read(2);
+  if (hskip == 1) {  // simple code: NSYM 1..4 explicit symbols (ReadSimpleHuffmanSymbols, :516-556)
+    const uint32_t nsym = L.read(2) + 1;
+    const uint32_t max_bits = bit_width(alphabet_size - 1);
+    uint32_t s[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < nsym; i++) {
+      s[i] = L.read(max_bits);
+      if (s[i] >= max_symbol) return kLaneBail;
+    }
+    for (uint32_t i = 0; i + 1 < nsym; i++)
+      for (uint32_t k = i + 1; k < nsym; k++) if (s[i] == s[k]) return kLaneBail;
+    if (nsym == 1) {
+      for (uint32_t t = 0; t < (1u << rbits); t++) tab_store(c, root_v + t, s[0] << 4);
+      return kLaneOk;
+    }
+    // canonical codes sorted by (length, value) reproduce BrotliBuildSimpleHuffmanTable (src/huffman/mod.rs:390-471)
+    uint32_t len[4] = {1, 1, 0, 0};
+    if (nsym == 3) { len[1] = 2; len[2] = 2; }
+    if (nsym == 4) {
+      if (L.read(1)) { len[0] = 1; len[1] = 2; len[2] = 3; len[3] = 3; } else { len[0] = len[1] = len[2] = len[3] = 2; }
+    }
+    uint32_t n = 0;
+    for (uint32_t l = 1; l <= 3; l++) {
+      const uint32_t first = n;
+      for (uint32_t i = 0; i < nsym; i++) if (len[i] == l) {
+        uint32_t q = n++;
+        while (q > first && sorted[q - 1] > s[i]) { sorted[q] = sorted[q - 1]; q--; }
+        sorted[q] = (uint16_t)s[i];
+        sts16(hc_count(c, l), vlds16(hc_count(c, l)) + 1u);
+      }
+    }
+    asm volatile("" ::: "memory");  // (sorted[] was written as u16, fill_table reads it as u32 pairs)
+    return fill_table(c, cold_next, sorted_w, root_v, rbits);
+  }
+  // complex code: code-length code lengths (ReadCodeLengthCodeLengths, :801-853)
+  uint8_t cl_cl[18];
+  for (uint32_t i = 0; i < 18; i++) cl_cl[i] = 0;
+  uint32_t space = 32, num_codes = 0;
+  for (uint32_t i = hskip; i < 18; i++) {
+    const uint32_t ix = L.peek() & 15u;
+    // kCodeLengthPrefixLength / kCodeLengthPrefixValue (src/decode.rs:59-61) packed four bits per entry
+    const uint32_t plen = (uint32_t)(0x4222322242223222ull >> (ix * 4)) & 15u;
+    const uint32_t v = (uint32_t)(0x5340234013402340ull >> (ix * 4)) & 15u;
+    L.skip(plen);
+    cl_cl[tbl::kCodeLengthCodeOrder[i]] = (uint8_t)v;
+    if (v != 0) {
+      space -= 32u >> v;
+      num_codes++;
+      if (space - 1u >= 32u) break;  // space is 0 or wrapped
+    }
+  }
+  if (!(num_codes == 1 || space == 0)) return kLaneBail;
+  // 5-bit lookup of the code-length code (BrotliBuildCodeLengthsHuffmanTable, src/huffman/mod.rs:196-271): symbol << 3 | length
+  if (num_codes == 1) {
+    uint32_t only = 0;
+    for (uint32_t i = 0; i < 18; i++) if (cl_cl[i]) only = i;
+    for (uint32_t t = 0; t < 32; t++) sts8(hc_tmp(c, t), only << 3);
+  } else {
+    uint32_t code = 0;
+    for (uint32_t l = 1; l <= 5; l++) {
+      for (uint32_t sy = 0; sy < 18; sy++) if (cl_cl[sy] == l) {
+        const uint32_t rev = hw::brev(code) >> (32 - l);
+        for (uint32_t t = rev; t < 32; t += 1u << l) sts8(hc_tmp(c, t), (sy << 3) | l);
+        code++;
+      }
+      code <<= 1;
+    }
+  }
+  // symbol code lengths with repeat codes (ReadSymbolCodeLengths, :661-731; Process*CodeLength :565-658)
+  uint32_t cl_w[176];  // u8 cl[704]: code length per symbol, read back four at a time
+  uint8_t* const cl = (uint8_t*)cl_w;
+  uint32_t symbol = 0, prev_len = 8, repeat = 0, repeat_len = 0;
+  space = 32768;
+  if (max_symbol > 704) return kLaneBail;
+  while (symbol < max_symbol && space > 0) {
+    const uint32_t p = vlds8(hc_tmp(c, L.peek() & 31u));
+    L.skip(p & 7u);
+    const uint32_t code_len = p >> 3;
+    if (code_len < 16) {
+      repeat = 0;
+      cl[symbol] = (uint8_t)code_len;
+      if (code_len != 0) {
+        prev_len = code_len;
+        space -= 32768u >> code_len;
+        const hw::sref_t cn = hc_count(c, code_len);
+        sts16(cn, vlds16(cn) + 1u);
+      }
+      symbol++;
+    } else {
+      const uint32_t extra_bits = code_len - 14;
+      uint32_t delta = L.read(extra_bits);
+      const uint32_t new_len = code_len == 16 ? prev_len : 0;
+      if (repeat_len != new_len) { repeat = 0; repeat_len = new_len; }
+      const uint32_t old_repeat = repeat;
+      if (repeat > 0) { repeat -= 2; repeat <<= extra_bits; }
+      repeat += delta + 3;
+      delta = repeat - old_repeat;
+      if (symbol + delta > max_symbol) { space = 0xFFFFF; break; }
+      for (uint32_t j = 0; j < delta; j++) cl[symbol + j] = (uint8_t)repeat_len;
+      symbol += delta;
+      if (repeat_len != 0) {
+        space -= delta << (15 - repeat_len);
+        const hw::sref_t cn = hc_count(c, repeat_len);
+        sts16(cn, vlds16(cn) + delta);
+      }
+    }
+  }
+  if (space != 0) return kLaneBail;
+  asm volatile("" ::: "memory");  // (cl[] was written as bytes, the loop below reads it as words)
+  // offs[] takes the place of the code-length lookup
+  uint32_t o = 0;
+  for (uint32_t l = 1; l <= 15; l++) { sts16(hc_tmp(c, 2u * l), o); o += vlds16(hc_count(c, l)); }
+  for (uint32_t base = 0; base < symbol; base += 4) {
+    uint32_t w = cl_w[base >> 2];
+    if (base + 4 > symbol) w &= mask_bits(8u * (symbol - base));  // bytes past the last symbol were never written
+    for (uint32_t sy = base; w != 0; sy++, w >>= 8) {
+      const uint32_t l = w & 0xFFu;
+      if (l) {
+        const hw::sref_t on = hc_tmp(c, 2u * l);
+        const uint32_t at = vlds16(on);
+        sorted[at] = (uint16_t)sy;
+        sts16(on, at + 1u);
+      }
+    }
+  }
+  asm volatile("" ::: "memory");  // (sorted[] was written as u16, fill_table reads it as u32 pairs; cl[] likewise above)
+  return fill_table(c, cold_next, sorted_w, root_v, rbits);
+}
+
+BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size, uint32_t max_symbol, uint32_t root_v, uint32_t rbits) {
+  BitWin b = L.win();
+  uint32_t cold_next = L.cold_next;
+  const int r = read_huffman_code_impl(c, b, cold_next, alphabet_size, max_symbol, root_v, rbits);
+  L.put(b);
+  L.cold_next = cold_next;
+  return r;
+}
+
+#else
 // Fill the lookup structure of one prefix code from its symbols sorted by (length, value).
 // count[l] = symbols of length l.  Root of 2^rbits entries at root_v; longer codes go to second-level
 // tables allocated from L.cold_next (always in the arena).  Same shape as BrotliBuildHuffmanTable (src/huffman/mod.rs:273-386).
@@ -961,6 +1164,7 @@ BD_COLD int read_huffman_code(const LaneCtx& c, Lane& L, uint32_t alphabet_size,
   return fill_table(c, L, sorted, count, root_v, rbits);
 }
 
+#endif
 #endif
 
 // A tree that lives wholly in the arena part of the table space (block-switch and context-map codes).
