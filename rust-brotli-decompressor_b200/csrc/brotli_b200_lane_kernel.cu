@@ -3,6 +3,8 @@
 // decoded afterwards by the exact warp-per-stream kernel (brotli_b200_kernels.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -103,6 +105,22 @@ __global__ void brotli_build_xdict_kernel(const uint8_t* dictionary, uint8_t* xd
                             dictionary + tbl::kBrotliDictOffsetsByLength[len] + idx * len, len, t);
   }
 }
+
+#if BD_LANE_WAIT_HIST
+// MEASUREMENT ONLY: adds up the per-warp wait histograms (4 sites x 64 buckets, then 4 cycle sums at [256..259]) into out[264] and clears them.
+extern "C" __attribute__((visibility("default"))) int BrotliB200ProbeWaitHist(unsigned long long* out) {
+  const size_t n = (size_t)lane::kWaitHistWarps * lane::kWaitHistRow;
+  unsigned long long* h = (unsigned long long*)calloc(n, sizeof(unsigned long long));
+  if (!h || cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpyFromSymbol(h, lane::g_wait_hist_all, n * sizeof(unsigned long long)) != cudaSuccess) return 0;
+  for (uint32_t i = 0; i < lane::kWaitHistRow; i++) out[i] = 0;
+  for (size_t w = 0; w < lane::kWaitHistWarps; w++) for (uint32_t i = 0; i < lane::kWaitHistRow; i++) out[i] += h[w * lane::kWaitHistRow + i];
+  memset(h, 0, n * sizeof(unsigned long long));
+  const int ok = cudaMemcpyToSymbol(lane::g_wait_hist_all, h, n * sizeof(unsigned long long)) == cudaSuccess;
+  free(h);
+  return ok;
+}
+#endif
 
 size_t xdict_bytes() { return (size_t)lane::xdict_layout().total + 64; }
 

@@ -137,6 +137,18 @@ constexpr uint32_t kCmdLiterals = BD_LANE_CMD_LITERALS;  // literals a lane may 
 #endif
 #define BD_LANE_DIST_LA_REG (BD_LANE_LATE_RETIRE || BD_LANE_LA_REG >= 1)
 #define BD_LANE_NEXT_LA_REG (BD_LANE_LA_REG >= 2)
+// The copy chunk's source blocks are loaded into registers (two predicated ld.global.cg.v4 at the top level of the round, each
+// with its own scoreboard) and put into the landing zone when phase P retires them, instead of cp.async.  Measured: 110.1
+// against 87.9 ms on the headline probe (profiles/r02/r08s_chunk_ldg.txt) -- register-destination loads held across a round
+// are what cp.async replaced in round 1, and they still lose.
+#ifndef BD_LANE_CHUNK_LDG
+#define BD_LANE_CHUNK_LDG 0
+#endif
+// MEASUREMENT ONLY (results stay right): every warp times its three cp.async waits and its rounds with clock64() and adds
+// them to a histogram in device memory (half-octave buckets of cycles; read by BrotliB200ProbeWaitHist, lane kernel TU)
+#ifndef BD_LANE_WAIT_HIST
+#define BD_LANE_WAIT_HIST 0
+#endif
 // MEASUREMENT ONLY (output is wrong; control flow of streams without literal contexts is unchanged): bit 0 drops the global
 // output stores, bit 1 the copy-source requests, bit 2 the history-ring mirror stores -- what do these instructions cost?
 #ifndef BD_LANE_PROBE_ABLATE
@@ -215,6 +227,10 @@ static inline uint32_t warp_count(bool p) { return p ? 32u : 0u; }  /* the one s
 #define BD_PIN64(x) ((void)0)
 static inline void ld32_if(bool cond, const uint8_t* p, uint32_t& dst) { if (cond) memcpy(&dst, p, 4); }
 static inline void probe_ldg16_if(bool, const void*) {}
+static inline void ldg128_if(bool cond, const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  if (cond) { uint32_t t[4]; memcpy(t, p, 16); a = t[0]; b = t[1]; c = t[2]; d = t[3]; }
+}
+static inline void sts128(hw::sref_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { uint32_t t[4] = {a, b, c, d}; memcpy((void*)dst, t, 16); }
 static inline void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) { if (cond) dst = *p; }
 // asynchronous 16-byte copy global -> "shared": immediate on the host
 static inline void cp_async16(hw::sref_t dst, const uint8_t* src) { memcpy((void*)dst, src, 16); }
@@ -318,6 +334,13 @@ BD_DEV void ld16_if(bool cond, const uint16_t* p, uint32_t& dst) {
 BD_DEV void probe_ldg16_if(bool cond, const void* p) {
   asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 a<4>;\n\tsetp.ne.u32 p, %0, 0;\n\t@p ld.global.cg.v4.u32 {a0, a1, a2, a3}, [%1];\n\t}" ::"r"((uint32_t)cond), "l"(p) : "memory");
 }
+BD_DEV void ldg128_if(bool cond, const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}"
+               : "+r"(a), "+r"(b), "+r"(c), "+r"(d) : "r"((uint32_t)cond), "l"(p) : "memory");
+}
+BD_DEV void sts128(hw::sref_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 BD_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }  // all 32 lanes take part
 BD_DEV uint32_t warp_count(bool p) { return __popc(__ballot_sync(0xffffffffu, p)); }
 #endif
@@ -337,6 +360,26 @@ __shared__ uint2 g_cmd_lut[704];                       // pack_cmd_lut
 __shared__ __align__(16) uint8_t g_ctx_lut[2048];      // kBrotliContextLookup
 __shared__ uint32_t g_word_info[25];                   // pack_word_info
 __shared__ uint32_t g_transform_info[BROTLI_NUM_TRANSFORMS];  // pack_transform_info
+#endif
+
+#if BD_LANE_WAIT_HIST && !defined(BROTLI_B200_HOSTSIM)
+constexpr uint32_t kWaitHistWarps = 4096, kWaitHistRow = 4 * 64 + 8;  // per warp (no contention): [site][bucket] counts, then the four cycle sums
+__device__ unsigned long long g_wait_hist_all[kWaitHistWarps * kWaitHistRow];
+BD_DEV void wait_hist_add(uint32_t site, long long dt) {
+  if ((threadIdx.x & 31u) != 0) return;
+  unsigned long long* const g_wait_hist = g_wait_hist_all + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kWaitHistWarps) * kWaitHistRow;
+  const unsigned long long d = dt < 0 ? 0ull : (unsigned long long)dt;
+  const uint32_t lg = 63u - (uint32_t)__clzll((long long)(d + 1));          // floor(log2(d + 1))
+  const uint32_t half = lg == 0 ? 0u : (uint32_t)(((d + 1) >> (lg - 1)) & 1u);  // upper half of the octave
+  uint32_t b = 2u * lg + half; if (b > 63u) b = 63u;
+  atomicAdd(&g_wait_hist[site * 64 + b], 1ull);
+  atomicAdd(&g_wait_hist[256 + site], d);
+}
+#define LN_WAIT_T0() const long long wt0_ = clock64()
+#define LN_WAIT_T1(SITE) wait_hist_add(SITE, clock64() - wt0_)
+#else
+#define LN_WAIT_T0() ((void)0)
+#define LN_WAIT_T1(SITE) ((void)0)
 #endif
 
 // Constant per-lane context (where this lane's storage lives).
@@ -1775,6 +1818,8 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   // copy chunk in flight: up to 16 source bytes starting pend_off bytes into the two aligned 16-byte blocks
   // on their way (cp.async) to stage[0..31]
   uint32_t pend_n = 0, pend_off = 0;
+  uint32_t cw0 = 0, cw1 = 0, cw2 = 0, cw3 = 0, cw4 = 0, cw5 = 0, cw6 = 0, cw7 = 0;  // BD_LANE_CHUNK_LDG: the chunk's two source blocks
+  (void)cw0; (void)cw1; (void)cw2; (void)cw3; (void)cw4; (void)cw5; (void)cw6; (void)cw7;
   const uint8_t* csrc = nullptr;  // next source byte of the copy being made
   uint32_t crem = 0;              // its remaining bytes
   bool dhave = false;
@@ -1915,14 +1960,20 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     const bool iss_ = (ISS);                                               \
     const uint32_t nn_ = crem < 16 ? crem : 16u;                           \
     const uint32_t off_ = (uint32_t)(uintptr_t)csrc & 15u;                 \
+    if (BD_LANE_CHUNK_LDG) {                                                                               \
+      ldg128_if(iss_, csrc - off_, cw0, cw1, cw2, cw3);                                                    \
+      ldg128_if(iss_ && off_ + nn_ > 16, csrc - off_ + 16, cw4, cw5, cw6, cw7);                            \
+    } else {                                                                                               \
     LN_CP16_IF_SRC(iss_ && !(BD_LANE_PROBE_ABLATE & 2), stage, csrc - off_);                              \
     LN_CP16_IF_SRC(iss_ && !(BD_LANE_PROBE_ABLATE & 2) && off_ + nn_ > 16, stage + 16, csrc - off_ + 16); \
+    }                                                                                                      \
     if (BD_LANE_PROBE_ABLATE & 8) { probe_ldg16_if(iss_, csrc - off_); probe_ldg16_if(iss_ && off_ + nn_ > 16, csrc - off_ + 16); } \
     if (iss_) { pend_n = nn_; pend_off = off_; crem -= nn_; csrc += 16; }  \
   } while (0)
 // append the chunk in flight to the output
 #define LN_RETIRE_CHUNK()                                                  \
   do {                                                                     \
+    if (BD_LANE_CHUNK_LDG) { sts128(stage, cw0, cw1, cw2, cw3); sts128(stage + 16, cw4, cw5, cw6, cw7); } \
     const hw::sref_t sw_ = stage + (pend_off & 12u);                       \
     const uint32_t s8_ = (pend_off & 3u) * 8u;                             \
     const uint32_t pw0_ = vlds32(sw_), pw1_ = vlds32(sw_ + 4), pw2_ = vlds32(sw_ + 8); \
@@ -2021,6 +2072,9 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
   uint32_t pa_ld = 0;  // the same for the next phase-A symbol
 #endif
 
+#if BD_LANE_WAIT_HIST && !defined(BROTLI_B200_HOSTSIM)
+  long long round_t0_ = 0;
+#endif
   while (warp_any(run)) {
     uint32_t ev = kStCommands;  // kStHeader: metablock complete; kStBail: give the stream up
 #if !BD_LANE_SKIP_LITE
@@ -2041,7 +2095,10 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
     bool pa_need = false;
 #endif
     // groups still pending here: [next-A look-ahead, copy chunk] of the previous round; phase A needs the first
-    cp_async_wait_all_but_latest();
+#if BD_LANE_WAIT_HIST && !defined(BROTLI_B200_HOSTSIM)
+    { const long long now_ = clock64(); if (round_t0_ != 0) wait_hist_add(3, now_ - round_t0_); round_t0_ = now_; }
+#endif
+    { LN_WAIT_T0(); cp_async_wait_all_but_latest(); LN_WAIT_T1(0); }
 #ifdef BD_LANE_ROUND_STATS
     BD_LANE_ROUND_STATS(ph, pa_valid);
 #endif
@@ -2207,11 +2264,11 @@ BD_DEV void run_commands(const LaneCtx& c, Lane& L, const BlockTrees& bt, bool r
 #if BD_LANE_WAIT_ALL_AT_P
     cp_async_wait_all();  // experiment: nothing in flight while phase P stores
 #else
-    cp_async_wait_all_but_latest();  // the chunk (and everything older); phase A's requests stay in flight
+    { LN_WAIT_T0(); cp_async_wait_all_but_latest(); LN_WAIT_T1(1); }  // the chunk (and everything older); phase A's requests stay in flight
 #endif
     LN_PHASE_P();
     warp_sync();
-    cp_async_wait_all();  // the distance look-ahead
+    { LN_WAIT_T0(); cp_async_wait_all(); LN_WAIT_T1(2); }  // the distance look-ahead
 #endif
 
     // ---- phase C1: distance symbol (ReadDistanceInternal :2066-2131, TakeDistanceFromRingBuffer :2017-2049) ----
